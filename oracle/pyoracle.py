@@ -1,0 +1,212 @@
+"""ctypes front end for the two CPU checkers (oracle_api.h).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  `Oracle(kind="ref")` drives the UNMODIFIED reference compiled as
+oracle/_ref/libfembrain_ref.so; `Oracle(kind="port")` drives the plain-C restatement
+oracle/libfembrain_port.so.  Both expose the same methods.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {"ref": os.path.join(_HERE, "_ref", "libfembrain_ref.so"), "port": os.path.join(_HERE, "libfembrain_port.so")}
+_PREFIX = {"ref": "fbref_", "port": "fbport_"}
+_loaded: dict = {}
+
+
+def build(kind: str, reference_root: str = "/root/reference") -> bool:
+    """Build one checker with oracle/Makefile.  'ref' needs the reference tree (this container only)."""
+    if kind == "ref" and not os.path.isdir(reference_root):
+        return os.path.exists(_LIBS["ref"])
+    subprocess.run(["make", "-C", _HERE, kind, f"REF={reference_root}", "-j8"], check=True, stdout=subprocess.DEVNULL)
+    return os.path.exists(_LIBS[kind])
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(_LIBS[kind])
+
+
+def _lib(kind: str):
+    if kind in _loaded:
+        return _loaded[kind]
+    if not os.path.exists(_LIBS[kind]):
+        raise FileNotFoundError(f"{_LIBS[kind]} missing: run `make -C oracle {kind}`")
+    lib = C.CDLL(_LIBS[kind])
+    p = _PREFIX[kind]
+    vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+    sig = {
+        "create": (vp, [ci, vp, ci, vp, cd, cd, cd, ci, vp, cd, cd, cd]),
+        "destroy": (None, [vp]),
+        "r": (ci, [vp]), "nnz_K": (ci, [vp]), "nnz_M": (ci, [vp]), "rows_sys": (ci, [vp]), "nnz_sys": (ci, [vp]),
+        "K_csr": (None, [vp, vp, vp, vp]), "M_csr": (None, [vp, vp, vp, vp]), "sys_csr": (None, [vp, vp, vp, vp]),
+        "element_maps": (None, [vp, vp, vp]), "element_data": (None, [vp, vp, vp]),
+        "super_maps": (None, [vp, vp, vp]), "submatrix_map": (None, [vp, vp]),
+        "force_and_matrix": (None, [vp, vp, vp, vp]),
+        "set_state": (None, [vp, vp, vp]), "get_state": (None, [vp, vp, vp, vp]),
+        "set_external_forces": (None, [vp, vp]), "do_timestep": (ci, [vp]),
+        "K_values": (None, [vp, vp]), "rhs": (None, [vp, vp]), "internal_forces": (None, [vp, vp]), "qdelta": (None, [vp, vp]),
+        "solve": (ci, [vp, vp, vp, cd, ci]), "solve_iters": (ci, [vp, vp, vp, ci]), "sys_spmv": (None, [vp, vp, vp]),
+        "assembly_time": (cd, [vp]), "solve_time": (cd, [vp]),
+        "polar": (cd, [vp, vp, vp, cd]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, p + name)
+        fn.restype, fn.argtypes = res, args
+    _loaded[kind] = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def polar(F, tol=1e-6, kind="ref"):
+    lib = _lib(kind)
+    F = _f64(F).reshape(9)
+    R, S = np.zeros(9), np.zeros(9)
+    det = getattr(lib, _PREFIX[kind] + "polar")(F.ctypes.data, R.ctypes.data, S.ctypes.data, tol)
+    return R.reshape(3, 3), S.reshape(3, 3), det
+
+
+class Oracle:
+    """One deformable model on the CPU checker; mirrors the methods of fembrain_b200.Simulation."""
+
+    def __init__(self, verts, tets, fixed_verts=(), E=1e7, nu=0.46, rho=1000.0, h=0.0333, damp_mass=0.0,
+                 damp_stiffness=0.01, kind="ref"):
+        self.kind = kind
+        self._lib = _lib(kind)
+        self._p = _PREFIX[kind]
+        v, t, fx = _f64(verts), _i32(tets), _i32(fixed_verts)
+        self.nV, self.nT = len(v), len(t)
+        self._h = self._fn("create")(self.nV, v.ctypes.data, self.nT, t.ctypes.data, E, nu, rho, len(fx),
+                                     fx.ctypes.data if len(fx) else None, h, damp_mass, damp_stiffness)
+        if not self._h:
+            raise RuntimeError("oracle create failed")
+        self.r = self._fn("r")(self._h)
+        self.nnz_K = self._fn("nnz_K")(self._h)
+        self.nnz_M = self._fn("nnz_M")(self._h)
+        self.rows_sys = self._fn("rows_sys")(self._h)
+        self.nnz_sys = self._fn("nnz_sys")(self._h)
+
+    def _fn(self, name):
+        return getattr(self._lib, self._p + name)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._fn("destroy")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _csr(self, name, n, nnz, values=True):
+        ia, ja = np.zeros(n + 1, np.int32), np.zeros(max(nnz, 1), np.int32)[:nnz]
+        a = np.zeros(max(nnz, 1))[:nnz] if values else None
+        self._fn(name)(self._h, ia.ctypes.data, ja.ctypes.data, a.ctypes.data if values else None)
+        return ia, ja, a
+
+    def K_csr(self, values=True):
+        return self._csr("K_csr", self.r, self.nnz_K, values)
+
+    def M_csr(self):
+        return self._csr("M_csr", self.r, self.nnz_M)
+
+    def sys_csr(self, values=True):
+        return self._csr("sys_csr", self.rows_sys, self.nnz_sys, values)
+
+    def element_maps(self):
+        row, col = np.zeros(4 * self.nT, np.int32), np.zeros(16 * self.nT, np.int32)
+        self._fn("element_maps")(self._h, row.ctypes.data, col.ctypes.data)
+        return row.reshape(-1, 4), col.reshape(-1, 16)
+
+    def element_data(self):
+        mi, k0 = np.zeros(16 * self.nT), np.zeros(144 * self.nT)
+        self._fn("element_data")(self._h, mi.ctypes.data, k0.ctypes.data)
+        return mi.reshape(-1, 16), k0.reshape(-1, 144)
+
+    def super_maps(self):
+        sr, si = np.zeros(max(self.rows_sys, 1), np.int32)[: self.rows_sys], np.zeros(max(self.nnz_sys, 1), np.int32)[: self.nnz_sys]
+        self._fn("super_maps")(self._h, sr.ctypes.data, si.ctypes.data)
+        return sr, si
+
+    def submatrix_map(self):
+        idx = np.zeros(max(self.nnz_M, 1), np.int32)[: self.nnz_M]
+        self._fn("submatrix_map")(self._h, idx.ctypes.data)
+        return idx
+
+    def force_and_matrix(self, u):
+        u = _f64(u).reshape(-1)
+        f, a = np.zeros(self.r), np.zeros(self.nnz_K)
+        self._fn("force_and_matrix")(self._h, u.ctypes.data, f.ctypes.data, a.ctypes.data)
+        return f, a
+
+    def set_state(self, q, qvel=None):
+        q = _f64(q).reshape(-1)
+        qv = _f64(qvel).reshape(-1) if qvel is not None else None
+        self._fn("set_state")(self._h, q.ctypes.data, qv.ctypes.data if qv is not None else None)
+
+    def get_state(self):
+        q, qv, qa = np.zeros(self.r), np.zeros(self.r), np.zeros(self.r)
+        self._fn("get_state")(self._h, q.ctypes.data, qv.ctypes.data, qa.ctypes.data)
+        return q, qv, qa
+
+    def set_external_forces(self, f):
+        f = _f64(f).reshape(-1)
+        assert f.size == self.r
+        self._fn("set_external_forces")(self._h, f.ctypes.data)
+
+    def do_timestep(self):
+        return self._fn("do_timestep")(self._h)
+
+    def _vec(self, name, n):
+        out = np.zeros(max(n, 1))[:n]
+        self._fn(name)(self._h, out.ctypes.data)
+        return out
+
+    def K_values(self):
+        return self._vec("K_values", self.nnz_K)
+
+    def rhs(self):
+        return self._vec("rhs", self.rows_sys)
+
+    def internal_forces(self):
+        return self._vec("internal_forces", self.r)
+
+    def qdelta(self):
+        return self._vec("qdelta", self.r)
+
+    def solve(self, b=None, eps=1e-6, max_iter=10000):
+        x = np.zeros(self.rows_sys)
+        bb = _f64(b) if b is not None else None
+        it = self._fn("solve")(self._h, bb.ctypes.data if bb is not None else None, x.ctypes.data, eps, max_iter)
+        return x, it
+
+    def solve_iters(self, iters, b=None):
+        x = np.zeros(self.rows_sys)
+        bb = _f64(b) if b is not None else None
+        it = self._fn("solve_iters")(self._h, bb.ctypes.data if bb is not None else None, x.ctypes.data, iters)
+        return x, it
+
+    def sys_spmv(self, x):
+        x = _f64(x)
+        y = np.zeros(self.rows_sys)
+        self._fn("sys_spmv")(self._h, x.ctypes.data, y.ctypes.data)
+        return y
+
+    def assembly_time(self):
+        return self._fn("assembly_time")(self._h)
+
+    def solve_time(self):
+        return self._fn("solve_time")(self._h)

@@ -1,0 +1,8 @@
+"""fembrain_b200 — B200-native (sm_100a CUDA) implementation of FemBrain's per-frame soft-tissue
+FEM step behind a C ABI (include/fembrain_b200.h).  This package is host-side plumbing only:
+`api` binds the shared library with ctypes, `meshes` builds the reference's synthetic inputs,
+`build` compiles the library.  There is no CPU or PyTorch compute path."""
+from .api import FbParams, FemBrainError, Simulation, default_params, load_library  # noqa: F401
+from . import meshes  # noqa: F401
+
+__all__ = ["Simulation", "FbParams", "FemBrainError", "default_params", "load_library", "meshes"]

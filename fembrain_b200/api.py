@@ -1,0 +1,429 @@
+"""ctypes binding of include/fembrain_b200.h — thin plumbing over the C ABI, no compute here.
+
+`Simulation` mirrors the reference's integrator surface (SetExternalForces / DoTimestep / GetqState,
+vegafem/integrator/integratorBase.h:107-205) plus the parity-inspection hooks.  There is no CPU path:
+importing works without a GPU (so symbols can be checked), creating a Simulation without one raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfembrain_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fembrain_b200.h")
+
+FB_OK = 0
+FB_ERR_INVALID_ARGUMENT = 1
+FB_ERR_NO_DEVICE = 2
+FB_ERR_CUDA = 3
+FB_ERR_OUT_OF_MEMORY = 4
+FB_ERR_SOLVER_NOT_CONVERGED = 5
+FB_ERR_BAD_MESH = 6
+FB_ERR_COMM = 7
+FB_ERR_NOT_SUPPORTED = 8
+
+
+class FbParams(C.Structure):
+    _fields_ = [
+        ("youngs_modulus", C.c_double),
+        ("poisson_ratio", C.c_double),
+        ("density", C.c_double),
+        ("timestep", C.c_double),
+        ("damping_mass", C.c_double),
+        ("damping_stiffness", C.c_double),
+        ("cg_epsilon", C.c_double),
+        ("cg_max_iterations", C.c_int),
+        ("polar_tolerance", C.c_double),
+        ("internal_force_scaling", C.c_double),
+        ("device", C.c_int),
+        ("keep_raw_stiffness", C.c_int),
+        ("reserved", C.c_int * 6),
+    ]
+
+
+class FemBrainError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str):
+        super().__init__(f"{where}: status {status} ({detail})")
+        self.status = status
+
+
+_lib = None
+
+
+def load_library():
+    """Load libfembrain_b200.so; raise loudly if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m fembrain_b200.build` (nvcc, sm_100a). "
+            "fembrain_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, ci, cd, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+    pp = C.POINTER(vp)
+    prm = C.POINTER(FbParams)
+    sig = {
+        "fb_default_params": (None, [prm]),
+        "fb_abi_version": (ci, []),
+        "fb_status_string": (C.c_char_p, [ci]),
+        "fb_last_error_string": (C.c_char_p, []),
+        "fb_create": (ci, [pp, ci, vp, ci, vp, ci, vp, prm]),
+        "fb_create_with_materials": (ci, [pp, ci, vp, ci, vp, ci, vp, vp, vp, vp, prm]),
+        "fb_create_with_constrained_dofs": (ci, [pp, ci, vp, ci, vp, ci, vp, prm]),
+        "fb_destroy": (None, [vp]),
+        "fb_set_fixed_vertices": (ci, [vp, ci, vp]),
+        "fb_num_vertices": (ci, [vp]), "fb_num_tets": (ci, [vp]), "fb_num_dofs": (ci, [vp]),
+        "fb_num_constrained_dofs": (ci, [vp]),
+        "fb_nnz_stiffness": (ll, [vp]), "fb_nnz_mass": (ll, [vp]), "fb_nnz_system": (ll, [vp]),
+        "fb_set_external_forces": (ci, [vp, vp]), "fb_add_external_forces": (ci, [vp, vp]),
+        "fb_set_external_forces_to_zero": (ci, [vp]), "fb_get_external_forces": (ci, [vp, vp]),
+        "fb_set_state": (ci, [vp, vp, vp, vp]), "fb_get_state": (ci, [vp, vp, vp, vp]),
+        "fb_reset_to_rest": (ci, [vp]),
+        "fb_set_external_forces_dev": (ci, [vp, vp]), "fb_get_state_dev": (ci, [vp, vp, vp, vp]),
+        "fb_displacements_dev": (vp, [vp]),
+        "fb_set_timestep": (ci, [vp, cd]), "fb_set_damping": (ci, [vp, cd, cd]),
+        "fb_set_internal_force_scaling": (ci, [vp, cd]), "fb_set_cg": (ci, [vp, cd, ci]),
+        "fb_step": (ci, [vp]),
+        "fb_deformable_timestep": (ci, [vp]), "fb_deformable_set_gravity": (ci, [vp, ci]),
+        "fb_deformable_set_floor": (ci, [vp, ci, cd]),
+        "fb_deformable_set_haptic_forces": (ci, [vp, ci, vp, vp, ci]),
+        "fb_deformable_set_haptic_neighborhood": (ci, [vp, ci]),
+        "fb_deformable_contact_count": (ci, [vp]),
+        "fb_force_assembly_seconds": (cd, [vp]), "fb_system_solve_seconds": (cd, [vp]), "fb_step_seconds": (cd, [vp]),
+        "fb_last_cg_iterations": (ci, [vp]), "fb_last_cg_residual_ratio": (cd, [vp]),
+        "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]),
+        "fb_get_stiffness_csr": (ci, [vp, vp, vp]), "fb_get_mass_csr": (ci, [vp, vp, vp, vp]),
+        "fb_get_system_csr": (ci, [vp, vp, vp, vp]), "fb_get_element_maps": (ci, [vp, vp, vp]),
+        "fb_get_element_data": (ci, [vp, vp, vp]), "fb_get_super_maps": (ci, [vp, vp, vp]),
+        "fb_get_submatrix_map": (ci, [vp, vp]), "fb_get_constrained_dofs": (ci, [vp, vp]),
+        "fb_compute_force_and_matrix": (ci, [vp, vp, vp, vp]),
+        "fb_get_effective_stiffness_values": (ci, [vp, vp]), "fb_get_rhs": (ci, [vp, vp]),
+        "fb_get_internal_forces": (ci, [vp, vp]), "fb_get_qdelta": (ci, [vp, vp]),
+        "fb_solve": (ci, [vp, vp, vp, cd, ci, C.POINTER(ci)]), "fb_system_multiply": (ci, [vp, vp, vp]),
+        "fb_bench_spmv": (ci, [vp, ci, C.POINTER(cd)]), "fb_bench_assembly": (ci, [vp, ci, C.POINTER(cd)]),
+        "fb_bench_cg_iteration": (ci, [vp, ci, C.POINTER(cd)]),
+        "fb_comm_unique_id": (ci, [vp]),
+        "fb_create_partitioned": (ci, [pp, ci, vp, ci, vp, ci, vp, prm, ci, ci, vp]),
+        "fb_partition_range": (ci, [vp, C.POINTER(ci), C.POINTER(ci)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib._fb_signatures = sig
+    _lib = lib
+    return lib
+
+
+def default_params(**overrides) -> FbParams:
+    lib = load_library()
+    p = FbParams()
+    lib.fb_default_params(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"fb_params has no field {k}")
+        setattr(p, k, v)
+    return p
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None and a.size else None
+
+
+class Simulation:
+    """One deformable model on one B200: the C-ABI context behind the reference's integrator interface."""
+
+    def __init__(self, verts, tets, fixed_verts=(), constrained_dofs=None, materials=None, partition=None, **params):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        v, t = _f64(verts).reshape(-1, 3), _i32(tets).reshape(-1, 4)
+        self.nV, self.nT = len(v), len(t)
+        p = default_params(**params)
+        self.params = p
+        if partition is not None:
+            rank, world, comm_id = partition
+            fx = _i32(fixed_verts)
+            idbuf = (C.c_char * 128).from_buffer_copy(bytes(comm_id)) if comm_id is not None else None
+            st = self._lib.fb_create_partitioned(C.byref(self._h), self.nV, _ptr(v), self.nT, _ptr(t), len(fx), _ptr(fx),
+                                                 C.byref(p), rank, world, C.cast(idbuf, C.c_void_p) if idbuf is not None else None)
+        elif constrained_dofs is not None:
+            cd = _i32(constrained_dofs)
+            st = self._lib.fb_create_with_constrained_dofs(C.byref(self._h), self.nV, _ptr(v), self.nT, _ptr(t), len(cd), _ptr(cd), C.byref(p))
+        elif materials is not None:
+            E, nu, rho = (None if m is None else _f64(m) for m in materials)
+            fx = _i32(fixed_verts)
+            st = self._lib.fb_create_with_materials(C.byref(self._h), self.nV, _ptr(v), self.nT, _ptr(t), len(fx), _ptr(fx),
+                                                    _ptr(E) if E is not None else None, _ptr(nu) if nu is not None else None,
+                                                    _ptr(rho) if rho is not None else None, C.byref(p))
+        else:
+            fx = _i32(fixed_verts)
+            st = self._lib.fb_create(C.byref(self._h), self.nV, _ptr(v), self.nT, _ptr(t), len(fx), _ptr(fx), C.byref(p))
+        self._check(st, "fb_create")
+        self.r = self._lib.fb_num_dofs(self._h)
+
+    # -- plumbing ------------------------------------------------------------------------------------
+    def _check(self, st, where):
+        if st != FB_OK:
+            detail = self._lib.fb_last_error_string().decode() or self._lib.fb_status_string(st).decode()
+            raise FemBrainError(st, where, detail)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.fb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- sizes -----------------------------------------------------------------------------------------
+    @property
+    def nnz_K(self):
+        return int(self._lib.fb_nnz_stiffness(self._h))
+
+    @property
+    def nnz_M(self):
+        return int(self._lib.fb_nnz_mass(self._h))
+
+    @property
+    def nnz_sys(self):
+        return int(self._lib.fb_nnz_system(self._h))
+
+    @property
+    def num_constrained(self):
+        return self._lib.fb_num_constrained_dofs(self._h)
+
+    @property
+    def rows_sys(self):
+        return self.r - self.num_constrained
+
+    # -- forces / state ------------------------------------------------------------------------------------
+    def set_external_forces(self, f):
+        f = _f64(f).reshape(-1)
+        assert f.size == self.r
+        self._check(self._lib.fb_set_external_forces(self._h, _ptr(f)), "fb_set_external_forces")
+
+    def add_external_forces(self, f):
+        f = _f64(f).reshape(-1)
+        assert f.size == self.r
+        self._check(self._lib.fb_add_external_forces(self._h, _ptr(f)), "fb_add_external_forces")
+
+    def set_external_forces_to_zero(self):
+        self._check(self._lib.fb_set_external_forces_to_zero(self._h), "fb_set_external_forces_to_zero")
+
+    def get_external_forces(self):
+        f = np.zeros(self.r)
+        self._check(self._lib.fb_get_external_forces(self._h, _ptr(f)), "fb_get_external_forces")
+        return f
+
+    def set_state(self, q, qvel=None, qaccel=None):
+        q = _f64(q).reshape(-1)
+        qv = _f64(qvel).reshape(-1) if qvel is not None else None
+        qa = _f64(qaccel).reshape(-1) if qaccel is not None else None
+        self._check(self._lib.fb_set_state(self._h, _ptr(q), _ptr(qv) if qv is not None else None,
+                                           _ptr(qa) if qa is not None else None), "fb_set_state")
+
+    def get_state(self, out=None):
+        if out is None:
+            out = (np.zeros(self.r), np.zeros(self.r), np.zeros(self.r))
+        q, qv, qa = out
+        self._check(self._lib.fb_get_state(self._h, _ptr(q) if q is not None else None, _ptr(qv) if qv is not None else None,
+                                           _ptr(qa) if qa is not None else None), "fb_get_state")
+        return out
+
+    def reset_to_rest(self):
+        self._check(self._lib.fb_reset_to_rest(self._h), "fb_reset_to_rest")
+
+    def set_fixed_vertices(self, fixed):
+        fx = _i32(fixed)
+        self._check(self._lib.fb_set_fixed_vertices(self._h, len(fx), _ptr(fx)), "fb_set_fixed_vertices")
+
+    def set_cg(self, eps, max_iter):
+        self._check(self._lib.fb_set_cg(self._h, eps, max_iter), "fb_set_cg")
+
+    def set_timestep(self, h):
+        self._check(self._lib.fb_set_timestep(self._h, h), "fb_set_timestep")
+
+    def set_damping(self, dm, dk):
+        self._check(self._lib.fb_set_damping(self._h, dm, dk), "fb_set_damping")
+
+    # -- the step --------------------------------------------------------------------------------------------
+    def do_timestep(self):
+        """VolumeConservingIntegrator::DoTimestep.  Returns 0; raises FemBrainError on solver failure."""
+        self._check(self._lib.fb_step(self._h), "fb_step")
+        return 0
+
+    def step_raw(self) -> int:
+        return self._lib.fb_step(self._h)
+
+    def deformable_timestep(self):
+        self._check(self._lib.fb_deformable_timestep(self._h), "fb_deformable_timestep")
+
+    def set_gravity(self, enabled):
+        self._check(self._lib.fb_deformable_set_gravity(self._h, int(enabled)), "fb_deformable_set_gravity")
+
+    def set_floor(self, enabled, y=0.0):
+        self._check(self._lib.fb_deformable_set_floor(self._h, int(enabled), y), "fb_deformable_set_floor")
+
+    def set_haptic_forces(self, indices, forces, in_progress=True):
+        idx, f = _i32(indices), _f64(forces).reshape(-1)
+        assert f.size == 3 * idx.size
+        self._check(self._lib.fb_deformable_set_haptic_forces(self._h, len(idx), _ptr(idx), _ptr(f), int(in_progress)),
+                    "fb_deformable_set_haptic_forces")
+
+    def set_haptic_neighborhood(self, rings):
+        self._check(self._lib.fb_deformable_set_haptic_neighborhood(self._h, rings), "fb_deformable_set_haptic_neighborhood")
+
+    @property
+    def contact_count(self):
+        return self._lib.fb_deformable_contact_count(self._h)
+
+    # -- statistics ------------------------------------------------------------------------------------------
+    def assembly_time(self):
+        return self._lib.fb_force_assembly_seconds(self._h)
+
+    def solve_time(self):
+        return self._lib.fb_system_solve_seconds(self._h)
+
+    def step_time(self):
+        return self._lib.fb_step_seconds(self._h)
+
+    @property
+    def last_cg_iterations(self):
+        return self._lib.fb_last_cg_iterations(self._h)
+
+    @property
+    def last_cg_residual_ratio(self):
+        return self._lib.fb_last_cg_residual_ratio(self._h)
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.fb_kernel_launches(self._h))
+
+    @property
+    def device_bytes(self):
+        return int(self._lib.fb_device_bytes(self._h))
+
+    # -- inspection ---------------------------------------------------------------------------------------------
+    def K_csr(self, values=False):
+        ia, ja = np.zeros(self.r + 1, np.int32), np.zeros(self.nnz_K, np.int32)
+        self._check(self._lib.fb_get_stiffness_csr(self._h, _ptr(ia), _ptr(ja)), "fb_get_stiffness_csr")
+        return ia, ja, None
+
+    def M_csr(self):
+        n = self.nnz_M
+        ia, ja, a = np.zeros(self.r + 1, np.int32), np.zeros(n, np.int32), np.zeros(n)
+        self._check(self._lib.fb_get_mass_csr(self._h, _ptr(ia), _ptr(ja), _ptr(a)), "fb_get_mass_csr")
+        return ia, ja, a
+
+    def sys_csr(self, values=True):
+        n = self.nnz_sys
+        ia, ja = np.zeros(self.rows_sys + 1, np.int32), np.zeros(n, np.int32)
+        a = np.zeros(n) if values else None
+        self._check(self._lib.fb_get_system_csr(self._h, _ptr(ia), _ptr(ja), _ptr(a) if values else None), "fb_get_system_csr")
+        return ia, ja, a
+
+    def element_maps(self):
+        row, col = np.zeros(4 * self.nT, np.int32), np.zeros(16 * self.nT, np.int32)
+        self._check(self._lib.fb_get_element_maps(self._h, _ptr(row), _ptr(col)), "fb_get_element_maps")
+        return row.reshape(-1, 4), col.reshape(-1, 16)
+
+    def element_data(self):
+        mi, k0 = np.zeros(16 * self.nT), np.zeros(144 * self.nT)
+        self._check(self._lib.fb_get_element_data(self._h, _ptr(mi), _ptr(k0)), "fb_get_element_data")
+        return mi.reshape(-1, 16), k0.reshape(-1, 144)
+
+    def super_maps(self):
+        sr, si = np.zeros(self.rows_sys, np.int32), np.zeros(self.nnz_sys, np.int32)
+        self._check(self._lib.fb_get_super_maps(self._h, _ptr(sr), _ptr(si)), "fb_get_super_maps")
+        return sr, si
+
+    def submatrix_map(self):
+        idx = np.zeros(self.nnz_M, np.int32)
+        self._check(self._lib.fb_get_submatrix_map(self._h, _ptr(idx)), "fb_get_submatrix_map")
+        return idx
+
+    def constrained_dofs(self):
+        d = np.zeros(self.num_constrained, np.int32)
+        self._check(self._lib.fb_get_constrained_dofs(self._h, _ptr(d)), "fb_get_constrained_dofs")
+        return d
+
+    def force_and_matrix(self, u):
+        u = _f64(u).reshape(-1)
+        assert u.size == self.r
+        f, a = np.zeros(self.r), np.zeros(self.nnz_K)
+        self._check(self._lib.fb_compute_force_and_matrix(self._h, _ptr(u), _ptr(f), _ptr(a)), "fb_compute_force_and_matrix")
+        return f, a
+
+    def K_values(self):
+        a = np.zeros(self.nnz_K)
+        self._check(self._lib.fb_get_effective_stiffness_values(self._h, _ptr(a)), "fb_get_effective_stiffness_values")
+        return a
+
+    def rhs(self):
+        b = np.zeros(self.rows_sys)
+        self._check(self._lib.fb_get_rhs(self._h, _ptr(b)), "fb_get_rhs")
+        return b
+
+    def internal_forces(self):
+        f = np.zeros(self.r)
+        self._check(self._lib.fb_get_internal_forces(self._h, _ptr(f)), "fb_get_internal_forces")
+        return f
+
+    def qdelta(self):
+        d = np.zeros(self.r)
+        self._check(self._lib.fb_get_qdelta(self._h, _ptr(d)), "fb_get_qdelta")
+        return d
+
+    def solve(self, b=None, eps=1e-6, max_iter=10000):
+        x = np.zeros(self.rows_sys)
+        bb = _f64(b) if b is not None else None
+        it = C.c_int(0)
+        self._check(self._lib.fb_solve(self._h, _ptr(bb) if bb is not None else None, _ptr(x), eps, max_iter, C.byref(it)), "fb_solve")
+        return x, it.value
+
+    def sys_spmv(self, x):
+        x = _f64(x)
+        y = np.zeros(self.rows_sys)
+        self._check(self._lib.fb_system_multiply(self._h, _ptr(x), _ptr(y)), "fb_system_multiply")
+        return y
+
+    # -- micro-benchmarks ---------------------------------------------------------------------------------------------
+    def bench_spmv(self, repeats=20):
+        s = C.c_double(0)
+        self._check(self._lib.fb_bench_spmv(self._h, repeats, C.byref(s)), "fb_bench_spmv")
+        return s.value
+
+    def bench_assembly(self, repeats=5):
+        s = C.c_double(0)
+        self._check(self._lib.fb_bench_assembly(self._h, repeats, C.byref(s)), "fb_bench_assembly")
+        return s.value
+
+    def bench_cg_iteration(self, repeats=50):
+        s = C.c_double(0)
+        self._check(self._lib.fb_bench_cg_iteration(self._h, repeats, C.byref(s)), "fb_bench_cg_iteration")
+        return s.value

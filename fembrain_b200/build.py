@@ -1,0 +1,79 @@
+"""Builds fembrain_b200/libfembrain_b200.so (sm_100a only) with nvcc, in-tree.
+
+    python -m fembrain_b200.build [--force]
+
+One object per translation unit.  fb_fem.cu is compiled with -fmad=false: the element / assembly
+arithmetic is kept bit-identical to the reference (see fb_element_math.h); the PCG kernels in
+fb_pcg.cu use FMA.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libfembrain_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+UNITS = {
+    "fb_api.cu": [],
+    "fb_setup.cu": [],
+    "fb_fem.cu": ["-fmad=false"],
+    "fb_pcg.cu": [],
+    "fb_dist.cu": [],
+}
+HEADERS = ["fb_internal.h", "fb_element_math.h", os.path.join("..", "..", "include", "fembrain_b200.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    logs = []
+    for unit, extra in UNITS.items():
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdrs):
+            cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", src, "-o", obj]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
+            if res.returncode != 0:
+                sys.stderr.write(logs[-1])
+                raise RuntimeError(f"nvcc failed on {unit}")
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lnccl"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
+        if res.returncode != 0:
+            sys.stderr.write(logs[-1])
+            raise RuntimeError("link failed")
+    if logs:
+        with open(os.path.join(OBJ, "build.log"), "w") as fh:
+            fh.write("\n".join(logs))
+        if verbose:
+            print("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

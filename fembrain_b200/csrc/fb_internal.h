@@ -1,0 +1,147 @@
+// fb_internal.h — context layout and kernel-launcher prototypes shared by the translation units of
+// libfembrain_b200.so.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/fembrain_b200.h"
+
+// ---- error plumbing -------------------------------------------------------------------------
+void fb_set_error(const char *fmt, ...);
+#define FB_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      fb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return (e__ == cudaErrorMemoryAllocation) ? FB_ERR_OUT_OF_MEMORY : FB_ERR_CUDA;      \
+    }                                                                                      \
+  } while (0)
+#define FB_TRY(call)             \
+  do {                           \
+    int s__ = (call);            \
+    if (s__ != FB_OK) return s__; \
+  } while (0)
+
+// ---- device-resident scalars of the PCG loop --------------------------------------------------
+// rho[it & 1] holds sum r_i^2 / diag_i after iteration `it` (it = 0: initial); the loop reads
+// rho[(it-1)&1] and writes rho[it&1], so no kernel both reads and writes one slot.
+struct FbScalars {
+  double rho[2];
+  double rho0;
+  double dq;        // d . (A d) of the current iteration
+  double eps2;      // epsilon^2
+  int max_it;
+  int iters;        // iterations completed
+  int done;         // loop condition of CGSolver.cpp:150 is false
+  unsigned int ticket_a;  // last-block tickets (reset by the last block)
+  unsigned int ticket_b;
+  int pad[3];
+};
+
+#define FB_MAX_PARTIALS 4096
+
+struct FbDist;  // multi-GPU state (fb_dist.cu)
+
+struct fb_context {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  fb_params prm;
+  double lambda_uniform, mu_uniform;
+
+  // sizes
+  int nV, nT, r;
+  int nB;         // 3x3 blocks of K (vertex-pair adjacency incl. self)
+  int nC;         // constrained DOFs
+  long long nnzK;  // 9 * nB
+  size_t bytes;   // device bytes held
+
+  // mesh
+  double *x0;  // [3 nV] rest positions
+  int *tets;   // [4 nT]
+  // per-element data, structure-of-arrays planes of nT doubles each:
+  // 0..11 G (upper 4x3 of MInverse), 12 volume, 13 lambda, 14 mu, 15 density
+  double *edata;
+
+  // block structure of K: row pointer, block columns, owning row of each block, diagonal block of each row
+  int *bp;    // [nV+1]
+  int *bc;    // [nB]
+  int *brow;  // [nB]
+  int *diag;  // [nV]
+  // contributions: for block b, entries seg[b]..seg[b+1] of src, each el*16 + 4*i + j, ascending el
+  int *seg;            // [nB+1]
+  unsigned int *src;   // [16 nT]
+  int *colIdx;         // [16 nT] element -> block position inside row (reference's columnIndices)
+  double *mblk;        // [nB] mass scalar of each block (M = mblk (x) I3)
+  unsigned char *fixed;  // [r] 1 = constrained DOF (or, in partitioned contexts, a row this rank does not own)
+  int *cdofs;            // [nC] sorted constrained DOFs (device)
+  int *cdofs_host;
+
+  // matrices in the reference's CSR value order: idx = 9*bp[v] + k*3*nb(v) + 3*jpos + l
+  double *T;     // h*K + D   (the matrix DoTimestep multiplies qvel with)
+  double *Keff;  // M + h*D + h^2*K
+  double *Kraw;  // raw K, only when prm.keep_raw_stiffness or inspection asked for it
+  // per-element scratch of the two-phase deterministic assembly
+  double *scrK;  // [16][nT][9]
+  double *scrF;  // [12][nT]
+
+  // integrator state and work vectors, all [r]
+  double *q, *qvel, *qaccel, *fext, *fint, *qres, *rhs, *x, *res, *dir, *Ad, *invD, *tmp;
+  FbScalars *sc;        // device
+  FbScalars *sc_host;   // pinned, 4 slots
+  double *partials;     // [2][FB_MAX_PARTIALS]
+  cudaEvent_t ev[8];
+  cudaEvent_t evChunk[4];
+
+  // Deformable-level options
+  int gravity, floor_enabled, haptic_in_progress, haptic_rings, contact_count;
+  double floor_y;
+  int nHaptic;
+  int *haptic_idx_host;
+  double *haptic_f_host;
+  int *adj_host_bp, *adj_host_bc;  // host copy of vertex adjacency for ring spreading
+  double *fext_host;
+  int *contact_dev;
+
+  // stats
+  float ms_assembly, ms_solve, ms_step;
+  int last_iters;        // signed like the reference's return value
+  double last_ratio;
+  long long launches;
+  int spmv_group;        // lanes per block row chosen at setup
+
+  FbDist *dist;
+};
+
+// ---- fb_setup.cu ---------------------------------------------------------------------------------
+int fb_build_topology(fb_context *c);
+// ---- fb_fem.cu (compiled with -fmad=false) ---------------------------------------------------------
+int fb_launch_element_data(fb_context *c, const double *E, const double *nu, const double *rho);
+int fb_launch_mass(fb_context *c);
+int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effective);
+int fb_launch_rhs(fb_context *c);
+int fb_launch_spmv_exact(fb_context *c, const double *A, const double *x, double *y);
+int fb_launch_state_update(fb_context *c);
+int fb_launch_expand_element(fb_context *c, double *minv16_dev, double *k0_dev, int el0, int n);
+// ---- fb_pcg.cu -------------------------------------------------------------------------------------
+int fb_pcg_solve(fb_context *c, double eps, int max_it);  // solves Keff x = rhs (masked), x0 = 0
+int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked);
+int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec);
+// ---- fb_dist.cu ------------------------------------------------------------------------------------
+int fb_dist_halo_exchange(fb_context *c, double *vec);
+int fb_dist_allreduce_scalar(fb_context *c, double *dev_scalar);
+void fb_dist_destroy(fb_context *c);
+
+template <typename T>
+static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void **)p, bytes);
+  if (e != cudaSuccess) {
+    fb_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    *p = nullptr;
+    return FB_ERR_OUT_OF_MEMORY;
+  }
+  c->bytes += bytes;
+  return FB_OK;
+}

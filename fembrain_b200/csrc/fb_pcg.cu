@@ -1,0 +1,354 @@
+// fb_pcg.cu — Jacobi-preconditioned conjugate gradients on the constrained effective matrix.
+//
+// Reference: CGSolver::SolveLinearSystemWithJacobiPreconditioner
+// (src/3rdparty/vegafem/sparseSolver/CGSolver.cpp:129-190; SpMV sparseMatrix/sparseMatrix.cpp:405-413):
+//   invD = 1/diag(A); r = b - A x0 (x0 = 0 => r = b); d = invD r; rho = sum r^2 invD; rho0 = rho
+//   while rho > eps^2 rho0 and it <= maxIt:
+//     q = A d; alpha = rho / (d.q); x += alpha d
+//     it % 30 == 0 ? r = b - A x : r -= alpha q
+//     rho' = sum r^2 invD; beta = rho'/rho; d = invD r + beta d
+// Same recurrences, same refresh period, same stopping rule; sums are parallel reductions with a
+// FIXED association order (deterministic run to run), so iterates agree with the reference's
+// sequential sums to rounding, not bitwise.
+//
+// The constrained system (fixed rows/columns removed, CGSolver on systemMatrix) is solved IN PLACE
+// on full-length vectors: rows of constrained DOFs produce 0 and their entries of d, r, x stay 0,
+// which contributes exact zeros to every sum — arithmetically the compacted system, without the
+// per-step gather of AssignSuperMatrix (sparseMatrix.cpp:993-1002).
+//
+// Three kernels per iteration, all HBM-streaming, scalars (alpha, beta, rho, loop condition)
+// stay on the device:
+//   k_spmv_cg     q = A d  (+ d.q)            A values + block columns streamed once, d gathered
+//   k_update      x += alpha d; r -= alpha q  (+ rho')
+//   k_direction   d = invD r + beta d         (+ loop bookkeeping)
+// Block-level partial sums go to a fixed slot per CTA; the last CTA to finish (integer ticket)
+// adds the slots in index order.
+//
+// Matrix layout: the reference's CSR value order with 3x3-block-compressed column indices:
+// block row v owns 9*nb doubles at 9*bp[v]: three scalar rows of 3*nb values each; column of entry
+// t of a scalar row is 3*bc[bp[v] + t/3] + t%3.  8.44 bytes per nonzero instead of CSR's 12.
+#include "fb_internal.h"
+
+namespace {
+
+constexpr int SPMV_TB = 256;
+constexpr int VEC_TB = 256;
+
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+// Deterministic block reduction followed by the "last block adds all slots in order" pattern.
+// Returns true in every thread of the last block; *total is then valid in thread 0.
+template <int TB>
+__device__ __forceinline__ bool block_reduce_to_total(double v, double *slots, unsigned int *ticket, double *total) {
+  __shared__ double wsum[TB / 32];
+  __shared__ bool isLast;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) wsum[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double s = (lane < TB / 32) ? wsum[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      slots[blockIdx.x] = s;
+      __threadfence();
+      unsigned int tk = atomicAdd(ticket, 1u);
+      isLast = (tk == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!isLast) return false;
+  __threadfence();
+  // fixed-order final sum: thread t adds slots t, t+TB, ...; then the same block tree
+  double s = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += TB) s += ((volatile double *)slots)[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if (lane == 0) wsum[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double z = (lane < TB / 32) ? wsum[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_down_sync(0xffffffffu, z, o);
+    if (lane == 0) {
+      *total = z;
+      *ticket = 0u;
+    }
+  }
+  return true;
+}
+
+// MODE 0: y = A x                     (no mask, no reduction)       — generic product
+// MODE 1: y = mask(A x), sum x.y      (x = d, y = q)                — CG iteration
+// MODE 2: y = mask(b - A x), sum y^2 invD   (x = x, y = r)          — exact-residual refresh
+template <int G, int MODE>
+__global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
+                                                  const double *__restrict__ A, const double *__restrict__ x,
+                                                  double *__restrict__ y, const unsigned char *__restrict__ fixed,
+                                                  const double *__restrict__ b, const double *__restrict__ invD,
+                                                  FbScalars *sc, double *slots, int it) {
+  if (MODE != 0) {
+    if (sc->done) return;
+  }
+  const int lane = threadIdx.x & (G - 1);
+  const int groupsPerBlock = SPMV_TB / G;
+  const int group = blockIdx.x * groupsPerBlock + threadIdx.x / G;
+  const int nGroups = gridDim.x * groupsPerBlock;
+  double part = 0.0;
+  for (int v = group; v < nV; v += nGroups) {
+    const int rs = __ldg(bp + v), re = __ldg(bp + v + 1);
+    const int n3 = 3 * (re - rs);
+    const double *a0 = A + 9 * (size_t)rs;
+    const double *a1 = a0 + n3;
+    const double *a2 = a1 + n3;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    int t = lane;
+    // two passes per trip: six independent streaming loads in flight per lane
+    for (; t + G < n3; t += 2 * G) {
+      const int jb0 = t / 3, l0 = t - 3 * jb0;
+      const int t1 = t + G;
+      const int jb1 = t1 / 3, l1 = t1 - 3 * jb1;
+      const int c0 = __ldg(bc + rs + jb0), c1 = __ldg(bc + rs + jb1);
+      const double v00 = ld_stream(a0 + t), v01 = ld_stream(a1 + t), v02 = ld_stream(a2 + t);
+      const double v10 = ld_stream(a0 + t1), v11 = ld_stream(a1 + t1), v12 = ld_stream(a2 + t1);
+      const double x0 = __ldg(x + 3 * (size_t)c0 + l0), x1 = __ldg(x + 3 * (size_t)c1 + l1);
+      acc0 = fma(v00, x0, acc0); acc1 = fma(v01, x0, acc1); acc2 = fma(v02, x0, acc2);
+      acc0 = fma(v10, x1, acc0); acc1 = fma(v11, x1, acc1); acc2 = fma(v12, x1, acc2);
+    }
+    if (t < n3) {
+      const int jb0 = t / 3, l0 = t - 3 * jb0;
+      const int c0 = __ldg(bc + rs + jb0);
+      const double v00 = ld_stream(a0 + t), v01 = ld_stream(a1 + t), v02 = ld_stream(a2 + t);
+      const double x0 = __ldg(x + 3 * (size_t)c0 + l0);
+      acc0 = fma(v00, x0, acc0); acc1 = fma(v01, x0, acc1); acc2 = fma(v02, x0, acc2);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o, G);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o, G);
+      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o, G);
+    }
+    if (lane < 3) {
+      double s = (lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2);
+      const size_t row = 3 * (size_t)v + lane;
+      if (MODE == 0) {
+        y[row] = s;
+      } else if (MODE == 1) {
+        if (fixed[row]) s = 0.0;
+        y[row] = s;
+        part = fma(x[row], s, part);
+      } else {
+        double rr = fixed[row] ? 0.0 : (b[row] - s);
+        y[row] = rr;
+        part += (rr * rr) * invD[row];
+      }
+    }
+  }
+  if (MODE == 1) {
+    double total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->dq = total;
+  } else if (MODE == 2) {
+    double total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->rho[it & 1] = total;
+  }
+}
+
+// r = b (x0 = 0), d = invD r, x = 0, rho0 = sum r^2 invD           (CGSolver.cpp:139-147)
+__global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restrict__ b, const double *__restrict__ invD,
+                                                    double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
+                                                    FbScalars *sc, double *slots, double eps, int maxIt) {
+  double part = 0.0;
+  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB) {
+    const double bi = b[i], di = invD[i];
+    x[i] = 0.0;
+    r[i] = bi;
+    d[i] = di * bi;
+    part += (bi * bi) * di;
+  }
+  double total;
+  if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) {
+    sc->rho[0] = total;
+    sc->rho0 = total;
+    sc->eps2 = eps * eps;
+    sc->max_it = maxIt;
+    sc->iters = 0;
+    sc->dq = 0.0;
+    // while ((residualNorm2 > eps*eps*initialResidualNorm2) && (iteration <= maxIterations)), iteration = 1
+    sc->done = !((total > eps * eps * total) && (1 <= maxIt));
+  }
+}
+
+// x += alpha d; REFRESH ? nothing more : (r -= alpha q; rho' = sum r^2 invD)     (CGSolver.cpp:155-174)
+template <bool REFRESH>
+__global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restrict__ d, const double *__restrict__ q,
+                                                   const double *__restrict__ invD, double *__restrict__ x,
+                                                   double *__restrict__ r, FbScalars *sc, double *slots, int it) {
+  if (sc->done) return;
+  const double alpha = sc->rho[(it - 1) & 1] / sc->dq;
+  double part = 0.0;
+  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB) {
+    const double di = d[i];
+    x[i] = fma(alpha, di, x[i]);
+    if (!REFRESH) {
+      const double ri = fma(-alpha, q[i], r[i]);
+      r[i] = ri;
+      part += (ri * ri) * invD[i];
+    }
+  }
+  if (!REFRESH) {
+    double total;
+    if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) sc->rho[it & 1] = total;
+  }
+}
+
+// beta = rho'/rho; d = invD r + beta d; iteration++ and loop condition            (CGSolver.cpp:176-183, 150)
+__global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__restrict__ r, const double *__restrict__ invD,
+                                                      double *__restrict__ d, FbScalars *sc, int it) {
+  if (sc->done) return;
+  const double rhoNew = sc->rho[it & 1], rhoOld = sc->rho[(it - 1) & 1];
+  const double beta = rhoNew / rhoOld;
+  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB)
+    d[i] = fma(invD[i], r[i], beta * d[i]);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    sc->iters = it;
+    // `done` is read at kernel entry by this kernel's other blocks too; a block that sees the new value
+    // early only skips a direction update nobody will use.
+    if (!((rhoNew > sc->eps2 * sc->rho0) && (it + 1 <= sc->max_it))) sc->done = 1;
+  }
+}
+
+int vec_grid(const fb_context *c, size_t n) {
+  size_t want = (n + VEC_TB - 1) / VEC_TB;
+  size_t cap = (size_t)c->sm_count * 8;
+  if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+int spmv_grid(const fb_context *c, int G) {
+  size_t groupsPerBlock = SPMV_TB / G;
+  size_t want = ((size_t)c->nV + groupsPerBlock - 1) / groupsPerBlock;
+  size_t cap = (size_t)c->sm_count * 8;
+  if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+template <int MODE>
+void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, int it) {
+  const int G = c->spmv_group;
+  const int grid = spmv_grid(c, G);
+  double *slots = c->partials;
+#define FB_SPMV_CASE(GG)                                                                                               \
+  case GG:                                                                                                             \
+    k_spmv<GG, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc, slots, it); \
+    break;
+  switch (G) {
+    FB_SPMV_CASE(8)
+    FB_SPMV_CASE(16)
+    FB_SPMV_CASE(32)
+    default:
+      k_spmv<16, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc, slots, it);
+  }
+#undef FB_SPMV_CASE
+  c->launches++;
+}
+
+void enqueue_iteration(fb_context *c, int it) {
+  const int n = c->r;
+  const int vg = vec_grid(c, (size_t)n);
+  double *slotsB = c->partials + FB_MAX_PARTIALS;
+  launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, it);
+  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq);
+  if (it % 30 == 0) {
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it);
+    c->launches++;
+    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, it);
+  } else {
+    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it);
+    c->launches++;
+  }
+  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho[it & 1]);
+  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it);
+  c->launches++;
+  if (c->dist) fb_dist_halo_exchange(c, c->dir);
+}
+
+}  // namespace
+
+int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked) {
+  (void)masked;
+  if (c->nV == 0) return FB_OK;
+  launch_spmv_mode<0>(c, A, x, y, 0);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+// Solves Keff x = rhs on the constrained DOFs, x0 = 0.  On return c->last_iters holds the
+// reference's return value: +iterations if converged, -iterations otherwise (CGSolver.cpp:189).
+int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
+  const int n = c->r;
+  cudaStream_t st = c->stream;
+  if (n == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
+  const int vg = vec_grid(c, (size_t)n);
+  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, eps, maxIt);
+  c->launches++;
+  if (c->dist) {
+    // rho0 is a global sum: reduce, then recompute the loop condition on every rank identically
+    return FB_ERR_NOT_SUPPORTED;
+  }
+  // Iterations are enqueued in chunks; the loop condition lives on the device (kernels turn into
+  // no-ops once `done` is set).  The host looks at the flag of chunk k-1 while chunk k runs.
+  const int CH = 32;
+  int it = 1, slot = 0, pending = 0;
+  bool finished = false;
+  while (!finished && it <= maxIt) {
+    const int end = (it + CH - 1 < maxIt) ? it + CH - 1 : maxIt;
+    for (; it <= end; it++) enqueue_iteration(c, it);
+    FB_CUDA(cudaMemcpyAsync(&c->sc_host[slot], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaEventRecord(c->evChunk[slot], st));
+    pending++;
+    if (pending == 2) {
+      const int prev = slot ^ 1;
+      FB_CUDA(cudaEventSynchronize(c->evChunk[prev]));
+      if (c->sc_host[prev].done) finished = true;
+      pending--;
+    }
+    slot ^= 1;
+  }
+  FB_CUDA(cudaMemcpyAsync(&c->sc_host[2], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_CUDA(cudaGetLastError());
+  const FbScalars &s = c->sc_host[2];
+  const double rhoFinal = s.rho[s.iters & 1];
+  const bool notConverged = rhoFinal > s.eps2 * s.rho0;
+  c->last_iters = s.iters * (notConverged ? -1 : 1);
+  c->last_ratio = (s.rho0 != 0.0) ? rhoFinal / s.rho0 : 0.0;
+  return FB_OK;
+}
+
+int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
+  // time `repeats` full CG iterations on the current system without the stopping rule
+  const int n = c->r;
+  if (n == 0 || repeats <= 0) { *sec = 0.0; return FB_OK; }
+  cudaStream_t st = c->stream;
+  const int vg = vec_grid(c, (size_t)n);
+  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, 0.0, 1 << 30);
+  c->launches++;
+  for (int it = 1; it <= 3; it++) enqueue_iteration(c, it);
+  FB_CUDA(cudaEventRecord(c->ev[6], st));
+  for (int it = 4; it < 4 + repeats; it++) enqueue_iteration(c, it);
+  FB_CUDA(cudaEventRecord(c->ev[7], st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+  *sec = 1e-3 * ms / repeats;
+  return FB_OK;
+}

@@ -1,0 +1,204 @@
+/*
+ * fembrain_b200.h — C ABI of the B200-native soft-tissue FEM step.
+ *
+ * Drop-in boundary for ONE path of pouryashirazian/FemBrain: Deformable::timestep() ->
+ * VolumeConservingIntegrator::DoTimestep() -> corotational assembly -> Jacobi-PCG implicit-Euler
+ * solve.  The reference has no C ABI or FFI for this path; its seam is the C++ interface of
+ * `class Deformable` and Vega's ForceModel / IntegratorBaseSparse.  Each entry point below names
+ * the reference interface it replaces (paths relative to /root/reference/src; VEGA =
+ * 3rdparty/vegafem, DEF = deformable).  include/fembrain_b200_vega.hpp is the header-only C++
+ * adapter with the reference's class shape on top of these calls; INTEGRATION.md shows the edit a
+ * maintainer makes in DEF/Deformable.cpp.
+ *
+ * Rules of the ABI: plain pointers and sizes, no exceptions, no C++ or torch types; every call
+ * returns an fb_status (0 = ok) unless documented otherwise; one context = one CUDA device + one
+ * CUDA stream = one caller thread at a time (the reference is single-threaded and non-reentrant,
+ * graphics/SceneGraph.cpp:187-193); contexts are independent of one another.  All reals are
+ * double, all indices 0-based int, DOF d of vertex v is 3*v+d.  Buffer arguments named *_dev are
+ * device pointers on the context's device; all others are host pointers.  There is no CPU
+ * fallback: creation fails with FB_ERR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef FEMBRAIN_B200_H
+#define FEMBRAIN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+
+typedef enum fb_status {
+  FB_OK = 0,
+  FB_ERR_INVALID_ARGUMENT = 1,     /* NULL pointer, negative size, index out of range, unsorted input where sorted is required */
+  FB_ERR_NO_DEVICE = 2,            /* no CUDA device / device is not sm_100: there is no fallback */
+  FB_ERR_CUDA = 3,                 /* a CUDA runtime call failed; see fb_last_error_string() */
+  FB_ERR_OUT_OF_MEMORY = 4,
+  FB_ERR_SOLVER_NOT_CONVERGED = 5, /* PCG hit cg_max_iter: the reference printf+exit(-1)s here
+                                      (DEF/PS_VolumeConservingIntegrator.cpp:203-209); state is left unchanged */
+  FB_ERR_BAD_MESH = 6,             /* vertex index out of range, or a vertex that belongs to no tetrahedron
+                                      (the reference dereferences diagonal index -1 in that case, sparseMatrix.cpp:622-630) */
+  FB_ERR_COMM = 7,                 /* NCCL failure in a partitioned context */
+  FB_ERR_NOT_SUPPORTED = 8
+} fb_status;
+
+/* Parameters the reference hard-codes (defaults set by fb_default_params). */
+typedef struct fb_params {
+  double youngs_modulus;     /* 1e7      DEF/Deformable.cpp:178 */
+  double poisson_ratio;      /* 0.46     DEF/Deformable.cpp:178 */
+  double density;            /* 1000     DEF/Deformable.cpp:178 */
+  double timestep;           /* 0.0333   DEF/Deformable.cpp:113 */
+  double damping_mass;       /* 0.0      DEF/Deformable.cpp:107 */
+  double damping_stiffness;  /* 0.01     DEF/Deformable.cpp:110 */
+  double cg_epsilon;         /* 1e-6     DEF/PS_VolumeConservingIntegrator.cpp:196 */
+  int cg_max_iterations;     /* 10000    DEF/PS_VolumeConservingIntegrator.cpp:197 */
+  double polar_tolerance;    /* 1e-6     VEGA/corotationalLinearFEM/corotationalLinearFEM.cpp:263 */
+  double internal_force_scaling; /* 1.0  VEGA/integrator/integratorBase.cpp:46 */
+  int device;                /* CUDA device ordinal, default 0 */
+  int keep_raw_stiffness;    /* 0: K is consumed in registers; 1: also store raw K every step for fb_get_stiffness_values */
+  int reserved[6];
+} fb_params;
+
+typedef struct fb_context fb_context;
+
+void fb_default_params(fb_params *p);
+int fb_abi_version(void);
+const char *fb_status_string(int status);
+/* text of the most recent failure on the calling thread (CUDA error string, offending index, ...) */
+const char *fb_last_error_string(void);
+
+/* ---- lifetime --------------------------------------------------------------------------------
+ * Replaces the setup chain of Deformable::syncForceModel (DEF/Deformable.cpp:127-220): TetMesh
+ * (VEGA/volumetricMesh/tetMesh.cpp:129-131), CorotationalLinearFEM ctor (corotationalLinearFEM.cpp:40-146),
+ * GenerateMassMatrix::computeMassMatrix(inflate3Dim) (generateMassMatrix.cpp:33-76),
+ * FixedVerticesToFixedDOF (Deformable.cpp:294-314; the vertex list need not be sorted, duplicates are
+ * an error) and the VolumeConservingIntegrator / ImplicitNewmarkSparse ctor
+ * (implicitNewmarkSparse.cpp:39-83).  rest_positions: 3*num_vertices; tets: 4*num_tets.  Inputs are copied. */
+int fb_create(fb_context **out, int num_vertices, const double *rest_positions, int num_tets,
+              const int *tets, int num_fixed_vertices, const int *fixed_vertices, const fb_params *params);
+/* Same, with per-element materials (E, nu, density arrays of num_tets entries; NULL = use params):
+ * what a .veg file with several *MATERIAL / *REGION sections produces (volumetricMesh.cpp:45-...). */
+int fb_create_with_materials(fb_context **out, int num_vertices, const double *rest_positions,
+                             int num_tets, const int *tets, int num_fixed_vertices,
+                             const int *fixed_vertices, const double *E, const double *nu,
+                             const double *density, const fb_params *params);
+/* Same as fb_create with an arbitrary sorted, 0-indexed constrained-DOF list, the argument the
+ * integrator constructor itself takes (DEF/PS_VolumeConservingIntegrator.h:21-26). */
+int fb_create_with_constrained_dofs(fb_context **out, int num_vertices, const double *rest_positions,
+                                    int num_tets, const int *tets, int num_constrained_dofs,
+                                    const int *constrained_dofs, const fb_params *params);
+void fb_destroy(fb_context *ctx);
+
+/* Deformable::setFixedVertices + the integrator rebuild it needs.  (IntegratorBaseSparse::setConstrainedDOF,
+ * integratorBaseSparse.cpp:73-87, updates the list but not systemMatrix — a reference bug; here the
+ * constrained system always matches the list.) */
+int fb_set_fixed_vertices(fb_context *ctx, int num_fixed_vertices, const int *fixed_vertices);
+
+/* ---- sizes ------------------------------------------------------------------------------------ */
+int fb_num_vertices(const fb_context *ctx);
+int fb_num_tets(const fb_context *ctx);
+int fb_num_dofs(const fb_context *ctx);              /* r = 3*num_vertices (ForceModel::Getr) */
+int fb_num_constrained_dofs(const fb_context *ctx);
+long long fb_nnz_stiffness(const fb_context *ctx);   /* scalar nnz of K (SparseMatrix::GetNumEntries) */
+long long fb_nnz_mass(const fb_context *ctx);
+long long fb_nnz_system(const fb_context *ctx);      /* scalar nnz of the constrained systemMatrix */
+
+/* ---- forces and state: IntegratorBase API (VEGA/integrator/integratorBase.cpp:84-132) ---------- */
+int fb_set_external_forces(fb_context *ctx, const double *f);          /* SetExternalForces */
+int fb_add_external_forces(fb_context *ctx, const double *f);          /* AddExternalForces */
+int fb_set_external_forces_to_zero(fb_context *ctx);                   /* SetExternalForcesToZero */
+int fb_get_external_forces(fb_context *ctx, double *f);                /* GetExternalForces */
+int fb_set_state(fb_context *ctx, const double *q, const double *qvel, const double *qaccel); /* SetqState; qvel/qaccel may be NULL */
+int fb_get_state(fb_context *ctx, double *q, double *qvel, double *qaccel);                   /* GetqState; any may be NULL */
+int fb_reset_to_rest(fb_context *ctx);                                 /* ResetToRest */
+/* device-resident variants (no host copy; pointers must live on the context's device) */
+int fb_set_external_forces_dev(fb_context *ctx, const double *f_dev);
+int fb_get_state_dev(fb_context *ctx, double *q_dev, double *qvel_dev, double *qaccel_dev);
+/* read-only device pointer to the displacement vector q (r doubles): the hand-off to rendering
+ * (GPUPoly::applyFemDisplacements, implicit/OclPolygonizer.cpp:1543-1584) without a host round trip */
+const double *fb_displacements_dev(const fb_context *ctx);
+
+int fb_set_timestep(fb_context *ctx, double h);                        /* IntegratorBase::SetTimestep */
+int fb_set_damping(fb_context *ctx, double damping_mass, double damping_stiffness); /* SetDampingMassCoef / SetDampingStiffnessCoef */
+int fb_set_internal_force_scaling(fb_context *ctx, double s);          /* SetInternalForceScalingFactor */
+int fb_set_cg(fb_context *ctx, double epsilon, int max_iterations);
+
+/* ---- the step ---------------------------------------------------------------------------------
+ * VolumeConservingIntegrator::DoTimestep (DEF/PS_VolumeConservingIntegrator.cpp:46-260), PCG branch,
+ * one Newton iteration: assemble f_int and K at q; Keff = M + h*D + h^2*K with D = dampK*K + dampM*M;
+ * rhs = -h*((h*K + D)*qvel + f_int - f_ext); solve the constrained system by Jacobi-PCG from x0 = 0;
+ * qvel += dv; q += h*qvel; constrained DOFs zeroed.  Returns FB_OK or FB_ERR_SOLVER_NOT_CONVERGED. */
+int fb_step(fb_context *ctx);
+
+/* Deformable::timestep (DEF/Deformable.cpp:318-420) around fb_step: zero forces, optional gravity
+ * (-10000 on y when enabled and no contact, :331-338), haptic forces with ring spreading
+ * (applyHapticForces, :634-706), the step, then the floor-plane post-step (:350-402).  See
+ * fb_deformable_* setters below. */
+int fb_deformable_timestep(fb_context *ctx);
+int fb_deformable_set_gravity(fb_context *ctx, int enabled);                       /* Deformable::setGravity */
+int fb_deformable_set_floor(fb_context *ctx, int enabled, double floor_y);         /* m_collisionObj origin y (:351) */
+/* Deformable::hapticSetCurrentForces (:712-717) + m_bHapticInProgress; forces: 3*count */
+int fb_deformable_set_haptic_forces(fb_context *ctx, int count, const int *vertex_indices, const double *forces, int in_progress);
+int fb_deformable_set_haptic_neighborhood(fb_context *ctx, int rings);             /* m_hapticForceNeighorhoodSize (5) */
+int fb_deformable_contact_count(const fb_context *ctx);                            /* m_ctCollided */
+
+/* ---- timing / solver statistics (IntegratorBaseSparse::GetForceAssemblyTime / GetSystemSolveTime,
+ * integratorBaseSparse.h:66-67; CGSolver return value, CGSolver.cpp:189) -------------------------- */
+double fb_force_assembly_seconds(const fb_context *ctx); /* CUDA-event time of the last step's assembly kernels */
+double fb_system_solve_seconds(const fb_context *ctx);   /* CUDA-event time of the last step's PCG */
+double fb_step_seconds(const fb_context *ctx);           /* whole fb_step, device time */
+int fb_last_cg_iterations(const fb_context *ctx);
+double fb_last_cg_residual_ratio(const fb_context *ctx); /* rho_final / rho_0 (M^-1-weighted, squared) */
+long long fb_kernel_launches(const fb_context *ctx);     /* kernels of this library launched so far on this context */
+size_t fb_device_bytes(const fb_context *ctx);           /* device memory held by the context */
+
+/* ---- inspection hooks for parity (outputs are host buffers sized by the fb_nnz_ / fb_num_ calls) -
+ * CSR in the layout of SparseMatrix::GenerateCompressedRowMajorFormat (sparseMatrix.cpp:1151-1175). */
+int fb_get_stiffness_csr(fb_context *ctx, int *ia, int *ja);                 /* GetStiffnessMatrixTopology, corotationalLinearFEM.cpp:163-186 */
+int fb_get_mass_csr(fb_context *ctx, int *ia, int *ja, double *a);           /* computeMassMatrix */
+int fb_get_system_csr(fb_context *ctx, int *ia, int *ja, double *a);         /* systemMatrix: RemoveRowsColumns (sparseMatrix.cpp:1296-1357) + AssignSuperMatrix of the last Keff */
+int fb_get_element_maps(fb_context *ctx, int *row_indices4, int *column_indices16); /* BuildRowColumnIndices, corotationalLinearFEM.cpp:482-502 */
+int fb_get_element_data(fb_context *ctx, double *minverse16, double *k0_144);/* MInverse / KElementUndeformed (corotationalLinearFEM.cpp:70-145) */
+int fb_get_super_maps(fb_context *ctx, int *super_rows, int *super_indices); /* BuildSuperMatrixIndices, sparseMatrix.cpp:945-991 */
+int fb_get_submatrix_map(fb_context *ctx, int *indices);                     /* BuildSubMatrixIndices(M), sparseMatrix.cpp:1004-1047 */
+int fb_get_constrained_dofs(fb_context *ctx, int *dofs);
+/* ForceModel::GetForceAndMatrix(u, f, K) (corotationalLinearFEM.cpp:219-470, warp=1): f has r entries,
+ * K_values nnz_stiffness entries; either may be NULL.  Does not touch the integrator state. */
+int fb_compute_force_and_matrix(fb_context *ctx, const double *u, double *f, double *K_values);
+/* after fb_step: Keff (tangentStiffnessMatrix as DoTimestep leaves it), rhs (bufferConstrained,
+ * r - num_constrained entries), internal forces, qdelta */
+int fb_get_effective_stiffness_values(fb_context *ctx, double *a);
+int fb_get_rhs(fb_context *ctx, double *b_constrained);
+int fb_get_internal_forces(fb_context *ctx, double *f);
+int fb_get_qdelta(fb_context *ctx, double *d);
+/* CGSolver::SolveLinearSystemWithJacobiPreconditioner (CGSolver.cpp:129-190) on the current Keff:
+ * b_constrained / x_constrained have r - num_constrained entries, x0 = 0; *iterations receives the
+ * reference's return value (+n converged, -n not converged).  b NULL = the last step's rhs. */
+int fb_solve(fb_context *ctx, const double *b_constrained, double *x_constrained, double epsilon,
+             int max_iterations, int *iterations);
+/* y = systemMatrix * x on constrained vectors (SparseMatrix::MultiplyVector, sparseMatrix.cpp:405-413) */
+int fb_system_multiply(fb_context *ctx, const double *x_constrained, double *y_constrained);
+
+/* ---- micro-benchmark hooks (bench.py roofline section): run `repeats` launches of one kernel on the
+ * context's current matrices and return the mean device time per launch in seconds -------------- */
+int fb_bench_spmv(fb_context *ctx, int repeats, double *seconds_per_launch);
+int fb_bench_assembly(fb_context *ctx, int repeats, double *seconds_per_launch);
+int fb_bench_cg_iteration(fb_context *ctx, int repeats, double *seconds_per_iteration);
+
+/* ---- partitioned (multi-GPU) contexts: one process per GPU, row-block partition -----------------
+ * No reference counterpart (the reference is single-threaded CPU code).  Every rank
+ * passes the same global mesh; the context keeps rows [vertex_begin, vertex_end) of this rank plus
+ * ghost columns.  comm_id: the 128-byte ncclUniqueId produced by fb_comm_unique_id on rank 0 and
+ * broadcast by the host program (torch.distributed / MPI / files). */
+int fb_comm_unique_id(void *id128);
+int fb_create_partitioned(fb_context **out, int num_vertices, const double *rest_positions,
+                          int num_tets, const int *tets, int num_fixed_vertices,
+                          const int *fixed_vertices, const fb_params *params, int rank, int world,
+                          const void *comm_id128);
+int fb_partition_range(const fb_context *ctx, int *vertex_begin, int *vertex_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMBRAIN_B200_H */

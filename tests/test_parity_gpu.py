@@ -1,0 +1,125 @@
+"""GPU parity: CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): CSR structure and index maps bit-exact; FP64 stiffness values within
+1e-12 relative (measured: bit-exact); displacements within 1e-8 relative after convergence to the same
+residual.  The oracle is oracle/vega_port.c (pinned bit-for-bit to the compiled reference in
+tests/test_oracle.py) and, where it was built, the compiled reference itself (oracle/_ref).
+"""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(port_oracle, v, t, fixed, **kw):
+    import fembrain_b200 as fb
+
+    sim = fb.Simulation(v, t, fixed, **kw)
+    ora = port_oracle.Oracle(v, t, fixed, kind="port")
+    return sim, ora
+
+
+CASES = {
+    "two_tetra": lambda: (*__import__("fembrain_b200").meshes.two_tetra(), np.array([0], np.int32)),
+    "one_tetra": lambda: (*__import__("fembrain_b200").meshes.one_tetra(), np.array([1], np.int32)),
+    "cube3": lambda: cases.cube_case(3)[:3],
+    "cube7": lambda: cases.cube_case(7)[:3],
+    "slab_5x3x9": lambda: cases.cube_case(5, 3, 9)[:3],
+    "cube12_unsorted_fixed": lambda: (lambda v, t, f, l: (v, t, f[::-1].copy()))(*cases.cube_case(12)),
+    "cube6_nofixed": lambda: (*cases.cube_case(6)[:2], np.zeros(0, np.int32)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_structure_bit_exact(port_oracle, name):
+    v, t, fixed = CASES[name]()
+    sim, ora = _mk(port_oracle, v, t, fixed)
+    assert sim.r == ora.r and sim.nnz_K == ora.nnz_K and sim.nnz_M == ora.nnz_M
+    assert sim.rows_sys == ora.rows_sys and sim.nnz_sys == ora.nnz_sys
+    ia, ja, _ = sim.K_csr()
+    oia, oja, _ = ora.K_csr(values=False)
+    assert np.array_equal(ia, oia) and np.array_equal(ja, oja)
+    for a, b in zip(sim.element_maps(), ora.element_maps()):
+        assert np.array_equal(a, b)
+    for a, b in zip(sim.M_csr(), ora.M_csr()):
+        assert np.array_equal(a, b)  # mass values bit-exact too
+    assert np.array_equal(sim.submatrix_map(), ora.submatrix_map())
+    sia, sja, _ = sim.sys_csr(values=False)
+    osia, osja, _ = ora.sys_csr(values=False)
+    assert np.array_equal(sia, osia) and np.array_equal(sja, osja)
+    for a, b in zip(sim.super_maps(), ora.super_maps()):
+        assert np.array_equal(a, b)
+    mi, k0 = sim.element_data()
+    omi, ok0 = ora.element_data()
+    assert np.array_equal(mi.reshape(-1, 4, 4)[:, :, :3], omi.reshape(-1, 4, 4)[:, :, :3])
+    assert np.array_equal(k0, ok0)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_force_and_stiffness_bit_exact(port_oracle, name):
+    v, t, fixed = CASES[name]()
+    sim, ora = _mk(port_oracle, v, t, fixed)
+    for seed, scale in ((0, 0.0), (1, 1.0), (2, 4.0)):
+        u = cases.perturbation(v, scale, seed)
+        f, K = sim.force_and_matrix(u)
+        of, oK = ora.force_and_matrix(u)
+        assert cases.rel_err(K, oK) <= 1e-12  # the stated bar
+        assert cases.rel_err(f, of) <= 1e-12
+        assert np.array_equal(K, oK), f"K not bit-exact: rel {cases.rel_err(K, oK):.3e}"
+        assert np.array_equal(f, of), f"f not bit-exact: rel {cases.rel_err(f, of):.3e}"
+
+
+@pytest.mark.parametrize("name", ["two_tetra", "cube7", "slab_5x3x9", "cube12_unsorted_fixed"])
+def test_timestep_parity(port_oracle, name):
+    v, t, fixed = CASES[name]()
+    sim, ora = _mk(port_oracle, v, t, fixed)
+    r = sim.r
+    load_vertex = int(np.argmax(v[:, 1] * 1000 + v[:, 0]))
+    f = cases.point_load(r, load_vertex)
+    u0 = cases.perturbation(v, 0.5, 3)
+    fixed_dofs = sim.constrained_dofs()
+    u0[fixed_dofs] = 0.0
+    v0 = 0.3 * cases.perturbation(v, 0.5, 4)
+    v0[fixed_dofs] = 0.0
+    for s in (sim, ora):
+        s.set_state(u0, v0)
+        s.set_external_forces(f)
+    for step in range(3):
+        assert sim.do_timestep() == 0 and ora.do_timestep() == 0
+        # everything that defines the linear system is bit-exact
+        assert np.array_equal(sim.K_values(), ora.K_values()), "Keff"
+        assert np.array_equal(sim.internal_forces(), ora.internal_forces()), "fint"
+        if step == 0:
+            assert np.array_equal(sim.rhs(), ora.rhs()), "rhs"
+        _, oit = ora.solve(eps=1e-6)
+        assert abs(sim.last_cg_iterations - oit) <= max(3, oit // 50), (sim.last_cg_iterations, oit)
+        q, qv, qa = sim.get_state()
+        oq, oqv, oqa = ora.get_state()
+        # both stopped at eps = 1e-6 (possibly an iteration apart): loose check here, tight check below
+        assert cases.rel_err(qv, oqv) <= 1e-4 and cases.rel_err(q, oq) <= 1e-4
+        assert np.all(q[fixed_dofs] == 0) and np.all(qv[fixed_dofs] == 0) and np.all(qa == 0)
+        # keep the two trajectories on identical inputs for the next step's bit-exact checks
+        sim.set_state(oq, oqv, oqa)
+
+
+@pytest.mark.parametrize("name", ["cube7", "slab_5x3x9"])
+def test_converged_displacement_1e8(port_oracle, name):
+    """SURVEY §7 protocol (b): both solvers driven to eps = 1e-12 on the same system => <= 1e-8 relative."""
+    v, t, fixed = CASES[name]()
+    sim, ora = _mk(port_oracle, v, t, fixed)
+    f = cases.point_load(sim.r, int(np.argmax(v[:, 1] * 1000 + v[:, 0])))
+    for s in (sim, ora):
+        s.set_external_forces(f)
+        s.do_timestep()
+    x, it = sim.solve(eps=1e-12, max_iter=20000)
+    ox, oit = ora.solve(eps=1e-12, max_iter=20000)
+    assert it > 0 and oit > 0
+    assert cases.rel_err(x, ox) <= 1e-8, cases.rel_err(x, ox)
+    # displacement after the state update q = q0 + h (v0 + dv) inherits the bound
+    h = sim.params.timestep
+    assert cases.rel_err(h * x, h * ox) <= 1e-8
+    # SpMV on the constrained system
+    y, oy = sim.sys_spmv(ox), ora.sys_spmv(ox)
+    assert cases.rel_err(y, oy) <= 1e-13

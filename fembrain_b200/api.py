@@ -105,6 +105,9 @@ def load_library():
         "fb_get_effective_stiffness_values": (ci, [vp, vp]), "fb_get_rhs": (ci, [vp, vp]),
         "fb_get_internal_forces": (ci, [vp, vp]), "fb_get_qdelta": (ci, [vp, vp]),
         "fb_solve": (ci, [vp, vp, vp, cd, ci, C.POINTER(ci)]), "fb_system_multiply": (ci, [vp, vp, vp]),
+        "fb_timer_start": (ci, [vp]), "fb_timer_stop": (ci, [vp, C.POINTER(cd)]),
+        "fb_set_profiling": (ci, [vp, ci]),
+        "fb_get_spmv_profile": (ci, [vp, C.POINTER(cd), C.POINTER(ci), C.POINTER(cd)]),
         "fb_bench_spmv": (ci, [vp, ci, C.POINTER(cd)]), "fb_bench_assembly": (ci, [vp, ci, C.POINTER(cd)]),
         "fb_bench_cg_iteration": (ci, [vp, ci, C.POINTER(cd)]),
         "fb_comm_unique_id": (ci, [vp]),
@@ -411,6 +414,38 @@ class Simulation:
         y = np.zeros(self.rows_sys)
         self._check(self._lib.fb_system_multiply(self._h, _ptr(x), _ptr(y)), "fb_system_multiply")
         return y
+
+    # -- timing --------------------------------------------------------------------------------------------------------
+    def timer_start(self):
+        self._check(self._lib.fb_timer_start(self._h), "fb_timer_start")
+
+    def timer_stop(self) -> float:
+        s = C.c_double(0)
+        self._check(self._lib.fb_timer_stop(self._h, C.byref(s)), "fb_timer_stop")
+        return s.value
+
+    def set_profiling(self, enabled=True):
+        self._check(self._lib.fb_set_profiling(self._h, int(enabled)), "fb_set_profiling")
+
+    def spmv_profile(self):
+        m, n, b = C.c_double(0), C.c_int(0), C.c_double(0)
+        self._check(self._lib.fb_get_spmv_profile(self._h, C.byref(m), C.byref(n), C.byref(b)), "fb_get_spmv_profile")
+        return m.value, n.value, b.value
+
+    def set_external_forces_dev(self, dev_ptr: int):
+        self._check(self._lib.fb_set_external_forces_dev(self._h, C.c_void_p(dev_ptr)), "fb_set_external_forces_dev")
+
+    def get_state_dev(self, q_ptr=None, qvel_ptr=None, qaccel_ptr=None):
+        self._check(self._lib.fb_get_state_dev(self._h, C.c_void_p(q_ptr) if q_ptr else None, C.c_void_p(qvel_ptr) if qvel_ptr else None,
+                                               C.c_void_p(qaccel_ptr) if qaccel_ptr else None), "fb_get_state_dev")
+
+    def set_external_forces_ptr(self, host_ptr: int):
+        """SetExternalForces from a caller-owned host buffer (e.g. pinned memory), no numpy copy."""
+        self._check(self._lib.fb_set_external_forces(self._h, C.c_void_p(host_ptr)), "fb_set_external_forces")
+
+    def get_state_ptr(self, q_ptr=None, qvel_ptr=None, qaccel_ptr=None):
+        self._check(self._lib.fb_get_state(self._h, C.c_void_p(q_ptr) if q_ptr else None, C.c_void_p(qvel_ptr) if qvel_ptr else None,
+                                           C.c_void_p(qaccel_ptr) if qaccel_ptr else None), "fb_get_state")
 
     # -- micro-benchmarks ---------------------------------------------------------------------------------------------
     def bench_spmv(self, repeats=20):

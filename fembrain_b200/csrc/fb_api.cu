@@ -138,6 +138,8 @@ void free_all(fb_context *c) {
     if (e) cudaEventDestroy(e);
   for (auto &e : c->evChunk)
     if (e) cudaEventDestroy(e);
+  for (auto &e : c->evProf)
+    if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   free(c->cdofs_host);
   free(c->haptic_idx_host);
@@ -814,17 +816,52 @@ int fb_system_multiply(fb_context *c, const double *x, double *y) {
   return FB_OK;
 }
 
+// ---- timers / profiling ------------------------------------------------------------------------------------
+int fb_timer_start(fb_context *c) {
+  CHECK_CTX(c);
+  FB_CUDA(cudaEventRecord(c->ev[5], c->stream));
+  return FB_OK;
+}
+int fb_timer_stop(fb_context *c, double *seconds) {
+  CHECK_CTX(c);
+  if (!seconds) return FB_ERR_INVALID_ARGUMENT;
+  FB_CUDA(cudaEventRecord(c->ev[6], c->stream));
+  FB_CUDA(cudaEventSynchronize(c->ev[6]));
+  float ms = 0;
+  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]));
+  *seconds = 1e-3 * ms;
+  return FB_OK;
+}
+int fb_set_profiling(fb_context *c, int enabled) {
+  CHECK_CTX(c);
+  if (enabled && !c->evProf[0])
+    for (auto &e : c->evProf) FB_CUDA(cudaEventCreate(&e));
+  c->profiling = enabled != 0;
+  c->prof_sum_s = 0.0;
+  c->prof_samples = 0;
+  return FB_OK;
+}
+int fb_get_spmv_profile(fb_context *c, double *mean, int *samples, double *bytes) {
+  if (!c) return FB_ERR_INVALID_ARGUMENT;
+  if (mean) *mean = c->prof_samples ? c->prof_sum_s / c->prof_samples : 0.0;
+  if (samples) *samples = c->prof_samples;
+  // 8 B value per scalar nonzero + 4 B block column per 3x3 block + per block row: 4 B row pointer,
+  // 24 B of x (compulsory read), 24 B of y (write) [+ 3 B mask + 24 B d re-read for the fused dot]
+  if (bytes) *bytes = 8.0 * (double)c->nnzK + 4.0 * (double)c->nB + 52.0 * (double)c->nV;
+  return FB_OK;
+}
+
 // ---- micro-benchmarks -------------------------------------------------------------------------------------
 int fb_bench_spmv(fb_context *c, int repeats, double *sec) {
   CHECK_CTX(c);
   if (!sec || repeats <= 0) return FB_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < 3; i++) FB_TRY(fb_launch_spmv(c, c->Keff, c->dir, c->Ad, false));
-  FB_CUDA(cudaEventRecord(c->ev[6], c->stream));
+  FB_CUDA(cudaEventRecord(c->ev[3], c->stream));
   for (int i = 0; i < repeats; i++) FB_TRY(fb_launch_spmv(c, c->Keff, c->dir, c->Ad, false));
   FB_CUDA(cudaEventRecord(c->ev[7], c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
   float ms = 0;
-  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]));
   *sec = 1e-3 * ms / repeats;
   return FB_OK;
 }
@@ -832,12 +869,12 @@ int fb_bench_assembly(fb_context *c, int repeats, double *sec) {
   CHECK_CTX(c);
   if (!sec || repeats <= 0) return FB_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < 2; i++) FB_TRY(fb_launch_assembly(c, c->q, nullptr, true));
-  FB_CUDA(cudaEventRecord(c->ev[6], c->stream));
+  FB_CUDA(cudaEventRecord(c->ev[3], c->stream));
   for (int i = 0; i < repeats; i++) FB_TRY(fb_launch_assembly(c, c->q, nullptr, true));
   FB_CUDA(cudaEventRecord(c->ev[7], c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
   float ms = 0;
-  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]));
   *sec = 1e-3 * ms / repeats;
   return FB_OK;
 }

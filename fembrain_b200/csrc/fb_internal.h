@@ -110,6 +110,11 @@ struct fb_context {
   double last_ratio;
   long long launches;
   int spmv_group;        // lanes per block row chosen at setup
+  // optional sampling of SpMV launch durations inside fb_step
+  int profiling, nprof;
+  cudaEvent_t evProf[128];
+  double prof_sum_s;
+  int prof_samples;
 
   FbDist *dist;
 };

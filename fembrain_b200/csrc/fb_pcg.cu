@@ -265,7 +265,10 @@ void enqueue_iteration(fb_context *c, int it) {
   const int n = c->r;
   const int vg = vec_grid(c, (size_t)n);
   double *slotsB = c->partials + FB_MAX_PARTIALS;
+  const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64;
+  if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
   launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, it);
+  if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq);
   if (it % 30 == 0) {
     k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it);
@@ -307,6 +310,7 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
   // Iterations are enqueued in chunks; the loop condition lives on the device (kernels turn into
   // no-ops once `done` is set).  The host looks at the flag of chunk k-1 while chunk k runs.
   const int CH = 32;
+  c->nprof = 0;
   int it = 1, slot = 0, pending = 0;
   bool finished = false;
   while (!finished && it <= maxIt) {
@@ -326,6 +330,11 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
   FB_CUDA(cudaMemcpyAsync(&c->sc_host[2], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   FB_CUDA(cudaGetLastError());
+  for (int i = 0; i < c->nprof; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->evProf[2 * i], c->evProf[2 * i + 1]) == cudaSuccess) { c->prof_sum_s += 1e-3 * ms; c->prof_samples++; }
+  }
+  c->nprof = 0;
   const FbScalars &s = c->sc_host[2];
   const double rhoFinal = s.rho[s.iters & 1];
   const bool notConverged = rhoFinal > s.eps2 * s.rho0;
@@ -343,12 +352,12 @@ int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
   k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, 0.0, 1 << 30);
   c->launches++;
   for (int it = 1; it <= 3; it++) enqueue_iteration(c, it);
-  FB_CUDA(cudaEventRecord(c->ev[6], st));
+  FB_CUDA(cudaEventRecord(c->ev[3], st));
   for (int it = 4; it < 4 + repeats; it++) enqueue_iteration(c, it);
   FB_CUDA(cudaEventRecord(c->ev[7], st));
   FB_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
-  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+  FB_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]));
   *sec = 1e-3 * ms / repeats;
   return FB_OK;
 }

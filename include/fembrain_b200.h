@@ -180,6 +180,16 @@ int fb_solve(fb_context *ctx, const double *b_constrained, double *x_constrained
 /* y = systemMatrix * x on constrained vectors (SparseMatrix::MultiplyVector, sparseMatrix.cpp:405-413) */
 int fb_system_multiply(fb_context *ctx, const double *x_constrained, double *y_constrained);
 
+/* ---- device-side timing of a region of calls (bench.py): events are recorded on the context's stream -- */
+int fb_timer_start(fb_context *ctx);
+int fb_timer_stop(fb_context *ctx, double *seconds);
+/* When enabled, fb_step brackets every 16th PCG iteration's SpMV launch with a CUDA-event pair (at most 64
+ * per step).  fb_get_spmv_profile returns the mean duration of those launches over all steps since the
+ * profile was enabled, the number of samples, and the algorithmic bytes one launch streams
+ * (values + block columns + row pointers + x read + y write). */
+int fb_set_profiling(fb_context *ctx, int enabled);
+int fb_get_spmv_profile(fb_context *ctx, double *mean_seconds, int *samples, double *bytes_per_launch);
+
 /* ---- micro-benchmark hooks (bench.py roofline section): run `repeats` launches of one kernel on the
  * context's current matrices and return the mean device time per launch in seconds -------------- */
 int fb_bench_spmv(fb_context *ctx, int repeats, double *seconds_per_launch);

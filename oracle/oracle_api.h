@@ -81,6 +81,9 @@ int FBO(solve)(void *sim, const double *b, double *x, double eps, int maxIter);
 /* same, but stops after exactly `iters` iterations irrespective of convergence (timing sample);
  * implemented by calling the solver with eps = 0 */
 int FBO(solve_iters)(void *sim, const double *b, double *x, int iters);
+/* systemMatrix->AssignSuperMatrix(tangentStiffnessMatrix) (sparseMatrix.cpp:993-1002): load the constrained
+ * matrix from whatever tangentStiffnessMatrix currently holds (bench.py's bounded CPU sample) */
+void FBO(assign_system)(void *sim);
 /* y = systemMatrix * x (sparseMatrix.cpp:405-413) */
 void FBO(sys_spmv)(void *sim, const double *x, double *y);
 

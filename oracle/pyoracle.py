@@ -50,7 +50,7 @@ def _lib(kind: str):
         "set_state": (None, [vp, vp, vp]), "get_state": (None, [vp, vp, vp, vp]),
         "set_external_forces": (None, [vp, vp]), "do_timestep": (ci, [vp]),
         "K_values": (None, [vp, vp]), "rhs": (None, [vp, vp]), "internal_forces": (None, [vp, vp]), "qdelta": (None, [vp, vp]),
-        "solve": (ci, [vp, vp, vp, cd, ci]), "solve_iters": (ci, [vp, vp, vp, ci]), "sys_spmv": (None, [vp, vp, vp]),
+        "solve": (ci, [vp, vp, vp, cd, ci]), "solve_iters": (ci, [vp, vp, vp, ci]), "sys_spmv": (None, [vp, vp, vp]), "assign_system": (None, [vp]),
         "assembly_time": (cd, [vp]), "solve_time": (cd, [vp]),
         "polar": (cd, [vp, vp, vp, cd]),
     }
@@ -198,6 +198,9 @@ class Oracle:
         bb = _f64(b) if b is not None else None
         it = self._fn("solve_iters")(self._h, bb.ctypes.data if bb is not None else None, x.ctypes.data, iters)
         return x, it
+
+    def load_system_from_K(self):
+        self._fn("assign_system")(self._h)
 
     def sys_spmv(self, x):
         x = _f64(x)

@@ -188,6 +188,10 @@ int fbref_solve(void *p, const double *b, double *x, double eps, int maxIter) {
 int fbref_solve_iters(void *p, const double *b, double *x, int iters) {
   return fbref_solve(p, b, x, 0.0, iters);
 }
+void fbref_assign_system(void *p) {
+  RefSim *s = (RefSim *)p;
+  s->integrator->systemMatrix->AssignSuperMatrix(s->integrator->tangentStiffnessMatrix);
+}
 void fbref_sys_spmv(void *p, const double *x, double *y) {
   ((RefSim *)p)->integrator->systemMatrix->MultiplyVector(x, y);
 }

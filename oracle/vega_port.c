@@ -650,6 +650,13 @@ int fbport_solve(void *p, const double *b, double *x, double eps, int maxIter) {
   return pcg_jacobi(s, x, b ? b : s->bufC, eps, maxIter);
 }
 int fbport_solve_iters(void *p, const double *b, double *x, int iters) { return fbport_solve(p, b, x, 0.0, iters); }
+void fbport_assign_system(void *p) {
+  Port *s = (Port *)p;
+  for (int i = 0; i < s->nS; i++) {
+    const double *row = s->Ka + s->Kia[s->superRows[i]];
+    for (int pp = s->Sia[i]; pp < s->Sia[i + 1]; pp++) s->Sa[pp] = row[s->superIdx[pp]];
+  }
+}
 void fbport_sys_spmv(void *p, const double *x, double *y) {
   Port *s = (Port *)p;
   spmv(s->nS, s->Sia, s->Sja, s->Sa, x, y);

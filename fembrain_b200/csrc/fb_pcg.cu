@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
     if (sc->done) return;
   }
   const int lane = threadIdx.x & (G - 1);
+  // the G lanes of a group always take the same trips through the row loop; other groups of the warp may
+  // not, so shuffles name only the group's own lanes
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   const int groupsPerBlock = SPMV_TB / G;
   const int group = blockIdx.x * groupsPerBlock + threadIdx.x / G;
   const int nGroups = gridDim.x * groupsPerBlock;
@@ -131,9 +134,9 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o, G);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o, G);
-      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o, G);
+      acc0 += __shfl_xor_sync(gmask, acc0, o, G);
+      acc1 += __shfl_xor_sync(gmask, acc1, o, G);
+      acc2 += __shfl_xor_sync(gmask, acc2, o, G);
     }
     if (lane < 3) {
       double s = (lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2);

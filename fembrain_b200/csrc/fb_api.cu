@@ -129,7 +129,7 @@ void free_all(fb_context *c) {
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,
-                  c->contact_dev};
+                  c->contact_dev, c->ctaRows};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -297,6 +297,7 @@ int create_impl(fb_context **out, int nV, const double *x0, int nT, const int *t
   // lanes per block row for the SpMV: rows hold 3*nb scalars
   double avg3 = nV ? 3.0 * (double)c->nB / (double)nV : 0.0;
   c->spmv_group = avg3 <= 12.0 ? 8 : (avg3 <= 72.0 ? 16 : 32);
+  CR(fb_spmv_plan(c));
   CRC(cudaStreamSynchronize(c->stream));
   CRC(cudaGetLastError());
 #undef CR

@@ -110,6 +110,8 @@ struct fb_context {
   double last_ratio;
   long long launches;
   int spmv_group;        // lanes per block row chosen at setup
+  int use_tiled;         // 1: k_spmv_rows3 (16 lanes per row, all loads of a row in flight), 0: k_spmv<G>
+  int *ctaRows;          // reserved
   // optional sampling of SpMV launch durations inside fb_step
   int profiling, nprof;
   cudaEvent_t evProf[128];
@@ -133,6 +135,7 @@ int fb_launch_expand_element(fb_context *c, double *minv16_dev, double *k0_dev, 
 int fb_pcg_solve(fb_context *c, double eps, int max_it);  // solves Keff x = rhs (masked), x0 = 0
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked);
 int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec);
+int fb_spmv_plan(fb_context *c);  // call once after the block structure exists
 // ---- fb_dist.cu ------------------------------------------------------------------------------------
 int fb_dist_halo_exchange(fb_context *c, double *vec);
 int fb_dist_allreduce_scalar(fb_context *c, double *dev_scalar);

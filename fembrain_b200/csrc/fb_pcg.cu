@@ -27,6 +27,9 @@
 // Matrix layout: the reference's CSR value order with 3x3-block-compressed column indices:
 // block row v owns 9*nb doubles at 9*bp[v]: three scalar rows of 3*nb values each; column of entry
 // t of a scalar row is 3*bc[bp[v] + t/3] + t%3.  8.44 bytes per nonzero instead of CSR's 12.
+#include <cstdlib>
+#include <cstring>
+
 #include "fb_internal.h"
 
 namespace {
@@ -163,6 +166,118 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
   }
 }
 
+// lanes per block row and scalars covered by the three unrolled passes of k_spmv_rows3
+constexpr int TILE_G = 16;
+constexpr int TILE_CHUNK = 3 * TILE_G;
+
+struct RowVals {
+  double v[3][3];  // [pass][k]
+};
+
+__device__ __forceinline__ void load_row_chunk(const double *__restrict__ A, int rs, int n3, int base, int lane, RowVals &o) {
+  const double *a0 = A + 9 * (size_t)rs + base;
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int t = base + lane + TILE_G * p;
+    const bool ok = t < n3;
+    const double *q = a0 + lane + TILE_G * p;
+    o.v[p][0] = ok ? ld_stream(q) : 0.0;
+    o.v[p][1] = ok ? ld_stream(q + n3) : 0.0;
+    o.v[p][2] = ok ? ld_stream(q + 2 * (size_t)n3) : 0.0;
+  }
+}
+
+// ---- row-per-16-lanes SpMV with every load of a row in flight at once (no shared memory, no block syncs) ----
+// Same mapping as k_spmv<16,*>, but the three 16-wide passes over a row are fully unrolled and predicated, so a
+// lane has 9 streaming value loads + 3 column loads outstanding before the first multiply, and the row pointers
+// of the group's next row are fetched one row ahead.  MINB = resident CTAs per SM requested from the compiler.
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
+                                                              const double *__restrict__ A, const double *__restrict__ x,
+                                                              double *__restrict__ y, const unsigned char *__restrict__ fixed,
+                                                              const double *__restrict__ b, const double *__restrict__ invD,
+                                                              FbScalars *sc, double *slots, int it) {
+  if (MODE != 0) {
+    if (sc->done) return;
+  }
+  const int lane = threadIdx.x & (TILE_G - 1);
+  const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+  const int groupsPerBlock = SPMV_TB / TILE_G;
+  const int group = blockIdx.x * groupsPerBlock + threadIdx.x / TILE_G;
+  const int nGroups = gridDim.x * groupsPerBlock;
+  double part = 0.0;
+  int v = group;
+  int rs = 0, re = 0;
+  if (v < nV) { rs = __ldg(bp + v); re = __ldg(bp + v + 1); }
+  while (v < nV) {
+    const int vn = v + nGroups;
+    int rsn = 0, ren = 0;
+    if (vn < nV) { rsn = __ldg(bp + vn); ren = __ldg(bp + vn + 1); }
+    const int n3 = 3 * (re - rs);
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    for (int base = 0; base < n3; base += TILE_CHUNK) {
+      RowVals val;
+      int col[3];
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        const int t = base + lane + TILE_G * p;
+        col[p] = (t < n3) ? __ldg(bc + rs + t / 3) : -1;
+      }
+      load_row_chunk(A, rs, n3, base, lane, val);
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        const int t = base + lane + TILE_G * p;
+        const double xv = (col[p] >= 0) ? __ldg(x + 3 * (size_t)col[p] + (t % 3)) : 0.0;
+        acc0 = fma(val.v[p][0], xv, acc0); acc1 = fma(val.v[p][1], xv, acc1); acc2 = fma(val.v[p][2], xv, acc2);
+      }
+    }
+#pragma unroll
+    for (int o = TILE_G / 2; o > 0; o >>= 1) {
+      acc0 += __shfl_xor_sync(gmask, acc0, o, TILE_G);
+      acc1 += __shfl_xor_sync(gmask, acc1, o, TILE_G);
+      acc2 += __shfl_xor_sync(gmask, acc2, o, TILE_G);
+    }
+    if (lane < 3) {
+      double s = (lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2);
+      const size_t row = 3 * (size_t)v + lane;
+      if (MODE == 0) {
+        y[row] = s;
+      } else if (MODE == 1) {
+        if (fixed[row]) s = 0.0;
+        y[row] = s;
+        part = fma(x[row], s, part);
+      } else {
+        const double rres = fixed[row] ? 0.0 : (b[row] - s);
+        y[row] = rres;
+        part += (rres * rres) * invD[row];
+      }
+    }
+    v = vn; rs = rsn; re = ren;
+  }
+  if (MODE == 1) {
+    double total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->dq = total;
+  } else if (MODE == 2) {
+    double total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->rho[it & 1] = total;
+  }
+}
+
+template <int MODE, int MINB>
+void launch_rows3(fb_context *c, const double *A, const double *x, double *y, int it) {
+  static int perSM = 0;
+  if (!perSM) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_rows3<MODE, MINB>, SPMV_TB, 0) != cudaSuccess || perSM < 1) perSM = 1;
+  }
+  const size_t groupsPerBlock = SPMV_TB / TILE_G;
+  size_t want = ((size_t)c->nV + groupsPerBlock - 1) / groupsPerBlock;
+  size_t cap = (size_t)c->sm_count * (size_t)perSM;
+  if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
+  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  k_spmv_rows3<MODE, MINB><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc, c->partials, it);
+  c->launches++;
+}
+
 // r = b (x0 = 0), d = invD r, x = 0, rho0 = sum r^2 invD           (CGSolver.cpp:139-147)
 __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restrict__ b, const double *__restrict__ invD,
                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
@@ -227,41 +342,51 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
   }
 }
 
+// Grids are sized to ONE resident wave: sm_count x (blocks of this kernel that fit on an SM), so the
+// grid-stride loops see every SM equally loaded (no partial second wave) and the number of per-CTA
+// partial sums stays small and fixed.
 int vec_grid(const fb_context *c, size_t n) {
+  static int perSM = 0;
+  if (!perSM) {
+    int a = 1, b = 1, d = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_update<false>, VEC_TB, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_direction, VEC_TB, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_cg_init, VEC_TB, 0);
+    perSM = a < b ? a : b;
+    if (d < perSM) perSM = d;
+    if (perSM < 1) perSM = 1;
+  }
   size_t want = (n + VEC_TB - 1) / VEC_TB;
-  size_t cap = (size_t)c->sm_count * 8;
+  size_t cap = (size_t)c->sm_count * (size_t)perSM;
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
 }
 
-int spmv_grid(const fb_context *c, int G) {
-  size_t groupsPerBlock = SPMV_TB / G;
+template <int G, int MODE>
+void launch_spmv_g(fb_context *c, const double *A, const double *x, double *y, int it) {
+  static int perSM = 0;  // resident CTAs of this instantiation per SM (same for every B200)
+  if (!perSM) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv<G, MODE>, SPMV_TB, 0) != cudaSuccess || perSM < 1) perSM = 1;
+  }
+  const size_t groupsPerBlock = SPMV_TB / G;
   size_t want = ((size_t)c->nV + groupsPerBlock - 1) / groupsPerBlock;
-  size_t cap = (size_t)c->sm_count * 8;
+  size_t cap = (size_t)c->sm_count * (size_t)perSM;
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
-  if (want < 1) want = 1;
-  return (int)(want < cap ? want : cap);
+  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  k_spmv<G, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc,
+                                                           c->partials, it);
+  c->launches++;
 }
 
 template <int MODE>
 void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, int it) {
-  const int G = c->spmv_group;
-  const int grid = spmv_grid(c, G);
-  double *slots = c->partials;
-#define FB_SPMV_CASE(GG)                                                                                               \
-  case GG:                                                                                                             \
-    k_spmv<GG, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc, slots, it); \
-    break;
-  switch (G) {
-    FB_SPMV_CASE(8)
-    FB_SPMV_CASE(16)
-    FB_SPMV_CASE(32)
-    default:
-      k_spmv<16, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc, slots, it);
+  if (c->use_tiled) { launch_rows3<MODE, 5>(c, A, x, y, it); return; }
+  switch (c->spmv_group) {
+    case 8: launch_spmv_g<8, MODE>(c, A, x, y, it); break;
+    case 32: launch_spmv_g<32, MODE>(c, A, x, y, it); break;
+    default: launch_spmv_g<16, MODE>(c, A, x, y, it); break;
   }
-#undef FB_SPMV_CASE
-  c->launches++;
 }
 
 void enqueue_iteration(fb_context *c, int it) {
@@ -288,6 +413,16 @@ void enqueue_iteration(fb_context *c, int it) {
 }
 
 }  // namespace
+
+// Chooses the SpMV variant for this mesh.  Measured on B200, 998,250-tet cube (profiles/r01_spmv_variants.txt):
+// k_spmv<16> 45.0 us in step / 36.8 us isolated; k_spmv_rows3 at 48 registers (5 CTAs/SM) 42.8 / 36.6 us; forcing
+// 40 or 32 registers spills and is slower (54 / 66 us); a shared-memory-tiled variant with x staged per 64-row tile
+// was slower too (60 us: three block-wide barriers per tile, 3 CTAs/SM) and was removed.
+int fb_spmv_plan(fb_context *c) {
+  const char *env = getenv("FEMBRAIN_B200_SPMV");
+  c->use_tiled = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
+  return FB_OK;
+}
 
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked) {
   (void)masked;

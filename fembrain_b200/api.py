@@ -94,6 +94,7 @@ def load_library():
         "fb_deformable_set_haptic_forces": (ci, [vp, ci, vp, vp, ci]),
         "fb_deformable_set_haptic_neighborhood": (ci, [vp, ci]),
         "fb_deformable_contact_count": (ci, [vp]),
+        "fb_deformable_set_edge_list": (ci, [vp, ci, vp, ci]),
         "fb_force_assembly_seconds": (cd, [vp]), "fb_system_solve_seconds": (cd, [vp]), "fb_step_seconds": (cd, [vp]),
         "fb_last_cg_iterations": (ci, [vp]), "fb_last_cg_residual_ratio": (cd, [vp]),
         "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]),
@@ -300,6 +301,10 @@ class Simulation:
 
     def set_haptic_neighborhood(self, rings):
         self._check(self._lib.fb_deformable_set_haptic_neighborhood(self._h, rings), "fb_deformable_set_haptic_neighborhood")
+
+    def set_edge_list(self, edges, reference_quirk=True):
+        e = _i32(edges).reshape(-1)
+        self._check(self._lib.fb_deformable_set_edge_list(self._h, e.size // 2, _ptr(e), int(reference_quirk)), "fb_deformable_set_edge_list")
 
     @property
     def contact_count(self):

@@ -25,6 +25,7 @@ UNITS = {
     "fb_fem.cu": ["-fmad=false"],
     "fb_pcg.cu": [],
     "fb_dist.cu": [],
+    "fb_deformable.cu": ["-fmad=false"],
 }
 HEADERS = ["fb_internal.h", "fb_element_math.h", os.path.join("..", "..", "include", "fembrain_b200.h")]
 

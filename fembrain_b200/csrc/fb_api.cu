@@ -81,32 +81,6 @@ __global__ void k_count_isolated(int nV, const int *__restrict__ diag, int *__re
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < nV && diag[v] < 0) atomicMin(out, v);
 }
-// Deformable::timestep post-step (DEF/Deformable.cpp:350-402): count contacts, rewrite every node's
-// velocity v <- (v - v_n) - 0.4 v_n with n = (0,1,0), zero accelerations, snap penetrating nodes
-__global__ void k_floor_poststep(int nV, double floorY, const double *__restrict__ x0, double *__restrict__ q,
-                                 double *__restrict__ qvel, double *__restrict__ qaccel, int *__restrict__ contacts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nV) return;
-  const double pry = x0[3 * (size_t)i + 1];
-  const double qy = q[3 * (size_t)i + 1];
-  const double pcy = pry + qy;
-  const double vx = qvel[3 * (size_t)i], vy = qvel[3 * (size_t)i + 1], vz = qvel[3 * (size_t)i + 2];
-  // vn = n * dot(v, n); vp = v - vn; vr = vp - vn * 0.4
-  const double dotvn = vx * 0.0 + vy * 1.0 + vz * 0.0;
-  const double vnx = 0.0 * dotvn, vny = 1.0 * dotvn, vnz = 0.0 * dotvn;
-  const double vpx = vx - vnx, vpy = vy - vny, vpz = vz - vnz;
-  qvel[3 * (size_t)i] = vpx - vnx * 0.4;
-  qvel[3 * (size_t)i + 1] = vpy - vny * 0.4;
-  qvel[3 * (size_t)i + 2] = vpz - vnz * 0.4;
-  qaccel[3 * (size_t)i] = 0.0;
-  qaccel[3 * (size_t)i + 1] = 0.0;
-  qaccel[3 * (size_t)i + 2] = 0.0;
-  if (pcy <= floorY) {
-    atomicAdd(contacts, 1);
-    q[3 * (size_t)i + 1] = floorY - pry;
-  }
-}
-
 inline unsigned gridFor(size_t n, int tb) { return (unsigned)((n + tb - 1) / tb); }
 
 int upload(fb_context *c, void *dst, const void *src, size_t bytes) {
@@ -146,6 +120,8 @@ void free_all(fb_context *c) {
   free(c->haptic_f_host);
   free(c->adj_host_bp);
   free(c->adj_host_bc);
+  free(c->edges_host);
+  free(c->edge_degree_host);
   delete c;
 }
 
@@ -306,14 +282,18 @@ int create_impl(fb_context **out, int nV, const double *x0, int nT, const int *t
   return FB_OK;
 }
 
+}  // namespace
 // host copies of the block structure (inspection + haptic ring spreading)
-int fetch_structure(fb_context *c, std::vector<int> &bp, std::vector<int> &bc) {
+int fb_fetch_structure(fb_context *c, std::vector<int> &bp, std::vector<int> &bc) {
   bp.resize((size_t)c->nV + 1);
   bc.resize((size_t)c->nB);
   FB_TRY(download(c, bp.data(), c->bp, sizeof(int) * bp.size()));
   FB_TRY(download(c, bc.data(), c->bc, sizeof(int) * bc.size()));
   return FB_OK;
 }
+
+namespace {
+int fetch_structure(fb_context *c, std::vector<int> &bp, std::vector<int> &bc) { return fb_fetch_structure(c, bp, bc); }
 
 // old DOF -> constrained DOF (or -1), the map of SparseMatrix::RemoveRowsColumns (sparseMatrix.cpp:1296-1322)
 void old_to_new(const fb_context *c, std::vector<int> &m) {
@@ -345,7 +325,8 @@ void compress_constrained(const fb_context *c, const double *full, double *xc) {
   while (row < c->r) xc[n++] = full[row++];
 }
 
-int do_step(fb_context *c) {
+}  // namespace
+int fb_do_step(fb_context *c) {
   cudaStream_t st = c->stream;
   FB_CUDA(cudaEventRecord(c->ev[0], st));
   // forceModel->GetForceAndMatrix(q, internalForces, tangentStiffnessMatrix) + Keff formation
@@ -372,8 +353,6 @@ int do_step(fb_context *c) {
   }
   return FB_OK;
 }
-
-}  // namespace
 
 // =====================================================================================================
 extern "C" {
@@ -518,95 +497,7 @@ int fb_set_cg(fb_context *c, double eps, int maxIt) {
 // ---- the step --------------------------------------------------------------------------------------
 int fb_step(fb_context *c) {
   CHECK_CTX(c);
-  return do_step(c);
-}
-
-int fb_deformable_set_gravity(fb_context *c, int enabled) { if (!c) return FB_ERR_INVALID_ARGUMENT; c->gravity = enabled != 0; return FB_OK; }
-int fb_deformable_set_floor(fb_context *c, int enabled, double y) {
-  if (!c) return FB_ERR_INVALID_ARGUMENT;
-  c->floor_enabled = enabled != 0; c->floor_y = y;
-  return FB_OK;
-}
-int fb_deformable_set_haptic_forces(fb_context *c, int count, const int *idx, const double *forces, int inProgress) {
-  if (!c || count < 0 || (count > 0 && (!idx || !forces))) return FB_ERR_INVALID_ARGUMENT;
-  for (int i = 0; i < count; i++)
-    if (idx[i] < 0 || idx[i] >= c->nV) { fb_set_error("haptic vertex %d out of range", idx[i]); return FB_ERR_INVALID_ARGUMENT; }
-  free(c->haptic_idx_host); free(c->haptic_f_host);
-  c->haptic_idx_host = (int *)malloc(sizeof(int) * (size_t)(count ? count : 1));
-  c->haptic_f_host = (double *)malloc(sizeof(double) * 3 * (size_t)(count ? count : 1));
-  memcpy(c->haptic_idx_host, idx, sizeof(int) * (size_t)count);
-  memcpy(c->haptic_f_host, forces, sizeof(double) * 3 * (size_t)count);
-  c->nHaptic = count;
-  c->haptic_in_progress = inProgress != 0;
-  return FB_OK;
-}
-int fb_deformable_set_haptic_neighborhood(fb_context *c, int rings) {
-  if (!c || rings < 0) return FB_ERR_INVALID_ARGUMENT;
-  c->haptic_rings = rings;
-  return FB_OK;
-}
-int fb_deformable_contact_count(const fb_context *c) { return c ? c->contact_count : 0; }
-
-int fb_deformable_timestep(fb_context *c) {
-  CHECK_CTX(c);
-  const size_t r = (size_t)c->r;
-  if (!c->fext_host) FB_CUDA(cudaMallocHost(&c->fext_host, sizeof(double) * (r ? r : 1)));
-  double *f = c->fext_host;
-  // SetExternalForcesToZero + memset(m_arrExtForces)                                    (:325-328)
-  memset(f, 0, sizeof(double) * r);
-  // gravity: applyGravity = m_bApplyGravity && m_ctCollided == 0; ext[3i+1] += -10000   (:331-338)
-  if (c->gravity && c->contact_count == 0)
-    for (size_t i = 1; i < r; i += 3) f[i] += -10000.0;
-  // applyHapticForces                                                                    (:634-706)
-  if (c->nHaptic > 0 && c->haptic_in_progress) {
-    for (int i = 0; i < c->nHaptic; i++)
-      for (int d = 0; d < 3; d++) f[3 * (size_t)c->haptic_idx_host[i] + d] += c->haptic_f_host[3 * (size_t)i + d];
-    if (c->haptic_rings > 1) {
-      if (!c->adj_host_bp) {
-        std::vector<int> bp, bc;
-        FB_TRY(fetch_structure(c, bp, bc));
-        c->adj_host_bp = (int *)malloc(sizeof(int) * bp.size());
-        c->adj_host_bc = (int *)malloc(sizeof(int) * (bc.size() ? bc.size() : 1));
-        memcpy(c->adj_host_bp, bp.data(), sizeof(int) * bp.size());
-        memcpy(c->adj_host_bc, bc.data(), sizeof(int) * bc.size());
-      }
-      const int R = c->haptic_rings;
-      for (int iv = 0; iv < c->nHaptic; iv++) {
-        std::set<int> affected, last;
-        affected.insert(c->haptic_idx_host[iv]);
-        last.insert(c->haptic_idx_host[iv]);
-        const double *ef = c->haptic_f_host + 3 * (size_t)iv;
-        for (int j = 1; j < R; j++) {
-          const double mag = 1.0 * (R - j) / static_cast<double>(R);  // linear kernel (:657-658)
-          std::set<int> fresh;
-          for (int vtx : last)
-            for (int p = c->adj_host_bp[vtx]; p < c->adj_host_bp[vtx + 1]; p++) {
-              int nb = c->adj_host_bc[p];
-              if (nb != vtx && affected.find(nb) == affected.end()) fresh.insert(nb);
-            }
-          last.clear();
-          for (int nb : fresh) {
-            f[3 * (size_t)nb] += mag * ef[0];
-            f[3 * (size_t)nb + 1] += mag * ef[1];
-            f[3 * (size_t)nb + 2] += mag * ef[2];
-            last.insert(nb);
-            affected.insert(nb);
-          }
-        }
-      }
-    }
-  }
-  FB_CUDA(cudaMemcpyAsync(c->fext, f, sizeof(double) * r, cudaMemcpyHostToDevice, c->stream));
-  FB_TRY(do_step(c));
-  if (c->floor_enabled) {
-    FB_CUDA(cudaMemsetAsync(c->contact_dev, 0, sizeof(int), c->stream));
-    if (c->nV) {
-      k_floor_poststep<<<gridFor(c->nV, 256), 256, 0, c->stream>>>(c->nV, c->floor_y, c->x0, c->q, c->qvel, c->qaccel, c->contact_dev);
-      c->launches++;
-    }
-    FB_TRY(download(c, &c->contact_count, c->contact_dev, sizeof(int)));
-  }
-  return FB_OK;
+  return fb_do_step(c);
 }
 
 // ---- statistics --------------------------------------------------------------------------------------

@@ -101,6 +101,9 @@ struct fb_context {
   int *haptic_idx_host;
   double *haptic_f_host;
   int *adj_host_bp, *adj_host_bc;  // host copy of vertex adjacency for ring spreading
+  int nEdges, *edges_host;         // optional reference edge array (VolMesh::m_vEdges order), 2 ints per edge
+  int *edge_degree_host;           // incident-edge count per vertex of that array
+  int haptic_quirk;                // replicate VolMesh::get_node_neighbors (DEF/VolMesh.cpp:1346-1363) exactly
   double *fext_host;
   int *contact_dev;
 
@@ -121,6 +124,12 @@ struct fb_context {
   FbDist *dist;
 };
 
+// ---- fb_api.cu -----------------------------------------------------------------------------------
+int fb_do_step(fb_context *c);
+#ifdef __cplusplus
+#include <vector>
+int fb_fetch_structure(fb_context *c, std::vector<int> &bp, std::vector<int> &bc);
+#endif
 // ---- fb_setup.cu ---------------------------------------------------------------------------------
 int fb_build_topology(fb_context *c);
 // ---- fb_fem.cu (compiled with -fmad=false) ---------------------------------------------------------

@@ -142,6 +142,11 @@ int fb_deformable_set_floor(fb_context *ctx, int enabled, double floor_y);      
 int fb_deformable_set_haptic_forces(fb_context *ctx, int count, const int *vertex_indices, const double *forces, int in_progress);
 int fb_deformable_set_haptic_neighborhood(fb_context *ctx, int rings);             /* m_hapticForceNeighorhoodSize (5) */
 int fb_deformable_contact_count(const fb_context *ctx);                            /* m_ctCollided */
+/* Ring spreading walks VolMesh::get_node_neighbors (DEF/VolMesh.cpp:1346-1363), which indexes the GLOBAL edge array
+ * with a counter that runs over the node's incident-edge COUNT.  Default here: true mesh adjacency.  Passing the
+ * host's edge array (num_edges pairs from,to in VolMesh::m_vEdges order) with reference_quirk = 1 reproduces the
+ * reference's rings exactly; reference_quirk = 0 or num_edges = 0 returns to true adjacency. */
+int fb_deformable_set_edge_list(fb_context *ctx, int num_edges, const int *from_to, int reference_quirk);
 
 /* ---- timing / solver statistics (IntegratorBaseSparse::GetForceAssemblyTime / GetSystemSolveTime,
  * integratorBaseSparse.h:66-67; CGSolver return value, CGSolver.cpp:189) -------------------------- */

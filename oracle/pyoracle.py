@@ -57,6 +57,11 @@ def _lib(kind: str):
     for name, (res, args) in sig.items():
         fn = getattr(lib, p + name)
         fn.restype, fn.argtypes = res, args
+    if kind == "port":
+        lib.fbport_deformable_timestep.restype = ci
+        lib.fbport_deformable_timestep.argtypes = [vp, ci, ci, vp, vp, ci, ci, ci, vp, ci, ci, cd, C.POINTER(ci)]
+        lib.fbport_get_external_forces.restype = None
+        lib.fbport_get_external_forces.argtypes = [vp, vp]
     _loaded[kind] = lib
     return lib
 
@@ -207,6 +212,24 @@ class Oracle:
         y = np.zeros(self.rows_sys)
         self._fn("sys_spmv")(self._h, x.ctypes.data, y.ctypes.data)
         return y
+
+    # -- Deformable::timestep restatement (port only; see oracle/deformable_port.inc) ---------------------------
+    def deformable_timestep(self, gravity=False, haptic_idx=(), haptic_forces=(), in_progress=True, rings=5, edges=None,
+                            quirk=False, floor=False, floor_y=0.0, contacts=0):
+        assert self.kind == "port", "Deformable.cpp cannot be compiled here; only the restatement has this call"
+        idx, f = _i32(haptic_idx), _f64(haptic_forces).reshape(-1)
+        e = _i32(edges).reshape(-1) if edges is not None else None
+        ct = C.c_int(contacts)
+        rc = self._lib.fbport_deformable_timestep(self._h, int(gravity), len(idx), idx.ctypes.data if len(idx) else None,
+                                                  f.ctypes.data if f.size else None, int(in_progress), rings,
+                                                  (e.size // 2) if e is not None else 0, e.ctypes.data if e is not None else None,
+                                                  int(quirk), int(floor), floor_y, C.byref(ct))
+        return rc, ct.value
+
+    def get_external_forces(self):
+        f = np.zeros(self.r)
+        self._lib.fbport_get_external_forces(self._h, f.ctypes.data)
+        return f
 
     def assembly_time(self):
         return self._fn("assembly_time")(self._h)

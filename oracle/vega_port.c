@@ -664,3 +664,5 @@ void fbport_sys_spmv(void *p, const double *x, double *y) {
 double fbport_assembly_time(void *p) { return ((Port *)p)->tAsm; }
 double fbport_solve_time(void *p) { return ((Port *)p)->tSolve; }
 double fbport_polar(const double *F9, double *R9, double *S9, double tol) { return polar_compute(F9, R9, S9, tol); }
+
+#include "deformable_port.inc"

@@ -1,0 +1,92 @@
+"""GPU parity of the caller around the step — Deformable::timestep (DEF/Deformable.cpp:318-420): gravity,
+haptic force ring spreading (both neighbour rules), floor-plane post-step — against the restatement in
+oracle/deformable_port.inc (unpinned against a compiled reference: Deformable.cpp does not build here)."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def unique_edges(tets, seed=0):
+    """A deterministic stand-in for VolMesh::m_vEdges: unique undirected edges in first-seen order."""
+    seen, out = set(), []
+    for t in tets:
+        for a, b in ((1, 2), (2, 3), (3, 1), (2, 0), (0, 3), (0, 1)):  # maskTetEdges, VolMesh.cpp:465
+            k = (min(t[a], t[b]), max(t[a], t[b]))
+            if k not in seen:
+                seen.add(k)
+                out.append((int(t[a]), int(t[b])))
+    return np.array(out, np.int32)
+
+
+@pytest.mark.parametrize("quirk", [False, True])
+@pytest.mark.parametrize("gravity", [False, True])
+def test_deformable_timestep_matches_restatement(port_oracle, quirk, gravity):
+    import fembrain_b200 as fb
+
+    v, t, fixed, load = cases.cube_case(6)
+    sim = fb.Simulation(v, t, fixed)
+    ora = port_oracle.Oracle(v, t, fixed, kind="port")
+    edges = unique_edges(t)
+    hidx = np.array([load, load - 7, 40], np.int32)
+    hf = np.array([[1e4, 0, 0], [0, -3e3, 2e3], [5e2, 5e2, 5e2]], dtype=np.float64)
+    floor_y = 0.35  # a plane inside the cube so that some nodes are in contact
+    sim.set_gravity(gravity)
+    sim.set_floor(True, floor_y)
+    sim.set_haptic_neighborhood(5)
+    sim.set_haptic_forces(hidx, hf, True)
+    sim.set_edge_list(edges if quirk else np.zeros((0, 2), np.int32), quirk)
+    contacts = 0
+    for step in range(3):
+        rc, contacts = ora.deformable_timestep(gravity=gravity, haptic_idx=hidx, haptic_forces=hf, in_progress=True, rings=5,
+                                               edges=edges if quirk else None, quirk=quirk, floor=True, floor_y=floor_y,
+                                               contacts=contacts)
+        assert rc == 0
+        sim.deformable_timestep()
+        # the external force vector is pure host set arithmetic: bit-exact
+        assert np.array_equal(sim.get_external_forces(), ora.get_external_forces()), "external forces"
+        assert sim.contact_count == contacts
+        q, qv, qa = sim.get_state()
+        oq, oqv, oqa = ora.get_state()
+        assert np.all(qa == 0) and np.all(oqa == 0)
+        assert cases.rel_err(q, oq) <= 1e-4 and cases.rel_err(qv, oqv) <= 1e-4  # both solves stop at eps = 1e-6
+        sim.set_state(oq, oqv, oqa)  # keep trajectories on identical inputs
+
+
+def test_haptic_not_in_progress_and_rings_one(port_oracle):
+    import fembrain_b200 as fb
+
+    v, t, fixed, load = cases.cube_case(5)
+    sim = fb.Simulation(v, t, fixed)
+    sim.set_floor(False)
+    sim.set_haptic_forces([load], [[1e4, 0, 0]], in_progress=False)  # m_bHapticInProgress == false => no forces
+    sim.deformable_timestep()
+    assert not sim.get_external_forces().any()
+    sim.set_haptic_forces([load], [[1e4, 0, 0]], in_progress=True)
+    sim.set_haptic_neighborhood(1)  # no spreading loop at all (j from 1 to < 1)
+    sim.deformable_timestep()
+    f = sim.get_external_forces()
+    assert f[3 * load] == 1e4 and np.count_nonzero(f) == 1
+
+
+def test_floor_poststep_rewrites_every_velocity(port_oracle):
+    """The reference damps the normal velocity of EVERY node each frame (v_y <- -0.4 v_y), contact or not (:373-392)."""
+    import fembrain_b200 as fb
+
+    v, t, fixed, load = cases.cube_case(4)
+    sim = fb.Simulation(v, t, fixed)
+    ora = port_oracle.Oracle(v, t, fixed, kind="port")
+    rng = np.random.default_rng(5)
+    v0 = rng.standard_normal(sim.r) * 0.1
+    v0[sim.constrained_dofs()] = 0
+    for s in (sim, ora):
+        s.set_state(np.zeros(sim.r), v0)
+    sim.set_floor(True, -100.0)
+    sim.deformable_timestep()
+    rc, ct = ora.deformable_timestep(floor=True, floor_y=-100.0)
+    assert ct == 0 and sim.contact_count == 0
+    q, qv, _ = sim.get_state()
+    oq, oqv, _ = ora.get_state()
+    assert cases.rel_err(qv, oqv) <= 1e-4 and cases.rel_err(q, oq) <= 1e-4

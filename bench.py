@@ -221,7 +221,15 @@ def run_ours(args):
     v, t, fixed, f = workload(nx)
     nT, r = len(t), 3 * len(v)
     t0 = time.perf_counter()
-    sim = fb.Simulation(v, t, fixed, device=local)
+    partitioned = args.partitioned and world > 1
+    if partitioned:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(fb.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sim = fb.Simulation(v, t, fixed, partition=(rank, world, bytes(idt.cpu().numpy().tobytes())), device=local)
+    else:
+        sim = fb.Simulation(v, t, fixed, device=local)
     t_setup = time.perf_counter() - t0
 
     f_pinned = torch.from_numpy(f).pin_memory()
@@ -236,8 +244,9 @@ def run_ours(args):
         for _ in range(n_steps):
             if e2e:
                 sim.set_external_forces_ptr(f_pinned.data_ptr())      # H2D from pinned host memory
-            else:
+            elif not partitioned:
                 sim.set_external_forces_dev(f_dev.data_ptr())         # resident in HBM
+            # (partitioned: the force vector set before the region stays resident on every rank)
             sim.do_timestep()
             if e2e:
                 sim.get_state_ptr(q_pinned.data_ptr())                # D2H of the displacement vector
@@ -249,6 +258,8 @@ def run_ours(args):
 
     # warm-up (from rest), then K timed steps resident, then state reset and the same K steps end to end
     sim.reset_to_rest()
+    if partitioned:
+        sim.set_external_forces(f)
     _, it_warm, _, _ = timed_region(args.warmup, False)
     sim.set_profiling(True)
     l0 = sim.kernel_launches
@@ -267,7 +278,7 @@ def run_ours(args):
 
     # isolated kernel timings on the final matrices (back to back, matrix >> L2)
     t_spmv_iso = sim.bench_spmv(50)
-    t_iter_iso = sim.bench_cg_iteration(60)
+    t_iter_iso = sim.bench_cg_iteration(60) if not partitioned else float("nan")
     t_asm_iso = sim.bench_assembly(5)
 
     # max over ranks
@@ -283,7 +294,7 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         nnz = sim.nnz_K
         rows = r
-        units = world  # independent meshes stepped concurrently
+        units = 1 if partitioned else world  # partitioned: one mesh; otherwise independent meshes stepped concurrently
         value = units * args.steps / sec
         e2e_value = units * args.steps / sec_e2e
         achieved = spmv_bytes / spmv_mean / 1e9 if spmv_mean > 0 else None
@@ -294,8 +305,8 @@ def run_ours(args):
         solve_bytes = sum(iters) * b_iter + refresh * spmv_bytes
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(nx, nT, world, False),
+            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "strong" if partitioned else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(nx, nT, world, partitioned),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * r, "d2h_bytes_per_step": 8 * r,
                     "ms_per_step": 1e3 * sec_e2e / args.steps},
@@ -341,6 +352,8 @@ def main():
     ap.add_argument("--nx", type=int, default=56, help="cube resolution: 56 = configs[1] (1M tets), 120 = configs[2] (10M tets)")
     ap.add_argument("--cpu-cg-iters", type=int, default=40, help="PCG iterations in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partitioned", action="store_true",
+                    help="N>1: split ONE mesh by row blocks across the ranks (NCCL halo exchange, strong scaling) instead of one mesh per rank")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: timing rules ask for >= 3 warm-up steps", file=sys.stderr)

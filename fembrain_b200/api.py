@@ -114,6 +114,7 @@ def load_library():
         "fb_comm_unique_id": (ci, [vp]),
         "fb_create_partitioned": (ci, [pp, ci, vp, ci, vp, ci, vp, prm, ci, ci, vp]),
         "fb_partition_range": (ci, [vp, C.POINTER(ci), C.POINTER(ci)]),
+        "fb_plan_partition": (ci, [ci, ci, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -132,6 +133,43 @@ def default_params(**overrides) -> FbParams:
             raise AttributeError(f"fb_params has no field {k}")
         setattr(p, k, v)
     return p
+
+
+def comm_unique_id() -> bytes:
+    """ncclUniqueId (128 bytes) for fb_create_partitioned; create on rank 0 and broadcast."""
+    lib = load_library()
+    buf = (C.c_char * 128)()
+    st = lib.fb_comm_unique_id(C.cast(buf, C.c_void_p))
+    if st != FB_OK:
+        raise FemBrainError(st, "fb_comm_unique_id", lib.fb_last_error_string().decode())
+    return bytes(buf)
+
+
+def plan_partition(num_vertices, tets, world, rank):
+    """Host-only partition plan (no GPU): dict with range, local-to-global map, local tets and halo lists."""
+    lib = load_library()
+    t = np.ascontiguousarray(tets, dtype=np.int32).reshape(-1, 4)
+    counts = np.zeros(7, np.int32)
+    args = (num_vertices, len(t), t.ctypes.data if len(t) else None, world, rank)
+    st = lib.fb_plan_partition(*args, counts.ctypes.data, None, None, None, None, None, None, None)
+    if st != FB_OK:
+        raise FemBrainError(st, "fb_plan_partition", lib.fb_last_error_string().decode())
+    n = [max(int(c), 1) for c in counts]
+    l2g, lt = np.zeros(n[2], np.int32), np.zeros(n[3], np.int32)
+    nbr, sc, rc = np.zeros(n[4], np.int32), np.zeros(n[4], np.int32), np.zeros(n[4], np.int32)
+    sg, rg = np.zeros(n[5], np.int32), np.zeros(n[6], np.int32)
+    st = lib.fb_plan_partition(*args, counts.ctypes.data, l2g.ctypes.data, lt.ctypes.data, nbr.ctypes.data, sc.ctypes.data,
+                               rc.ctypes.data, sg.ctypes.data, rg.ctypes.data)
+    if st != FB_OK:
+        raise FemBrainError(st, "fb_plan_partition", lib.fb_last_error_string().decode())
+    k = int(counts[4])
+    so, ro = np.concatenate([[0], np.cumsum(sc[:k])]), np.concatenate([[0], np.cumsum(rc[:k])])
+    return {
+        "begin": int(counts[0]), "end": int(counts[1]), "l2g": l2g[: counts[2]], "local_tets": lt[: counts[3]],
+        "neighbours": [int(x) for x in nbr[:k]],
+        "send": {int(nbr[i]): sg[so[i]:so[i + 1]] for i in range(k)},
+        "recv": {int(nbr[i]): rg[ro[i]:ro[i + 1]] for i in range(k)},
+    }
 
 
 def _f64(a):
@@ -182,6 +220,11 @@ class Simulation:
         if st != FB_OK:
             detail = self._lib.fb_last_error_string().decode() or self._lib.fb_status_string(st).decode()
             raise FemBrainError(st, where, detail)
+
+    def partition_range(self):
+        b, e = C.c_int(0), C.c_int(0)
+        self._check(self._lib.fb_partition_range(self._h, C.byref(b), C.byref(e)), "fb_partition_range")
+        return b.value, e.value
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

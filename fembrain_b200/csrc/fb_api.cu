@@ -125,7 +125,8 @@ void free_all(fb_context *c) {
   delete c;
 }
 
-int apply_constraints(fb_context *c, int nC, const int *cdofs_sorted) {
+}  // namespace
+int fb_apply_constraints(fb_context *c, int nC, const int *cdofs_sorted) {
   // validates like SparseMatrix::BuildRenumberingVector (sparseMatrix.cpp:896-938): in range, strictly ascending
   for (int i = 0; i < nC; i++) {
     if (cdofs_sorted[i] < 0 || cdofs_sorted[i] >= c->r) {
@@ -153,6 +154,7 @@ int apply_constraints(fb_context *c, int nC, const int *cdofs_sorted) {
   return FB_OK;
 }
 
+namespace {
 int fixed_vertices_to_dofs(int nV, int nFixed, const int *fv, std::vector<int> &dofs) {
   // Deformable::FixedVerticesToFixedDOF (DEF/Deformable.cpp:294-314): sort, then 3v, 3v+1, 3v+2
   if (nFixed < 0 || (nFixed > 0 && !fv)) {
@@ -178,8 +180,9 @@ int fixed_vertices_to_dofs(int nV, int nFixed, const int *fv, std::vector<int> &
   return FB_OK;
 }
 
-int create_impl(fb_context **out, int nV, const double *x0, int nT, const int *tets, int nC, const int *cdofs,
-                const double *E, const double *nu, const double *rho, const fb_params *prm) {
+}  // namespace
+int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const int *tets, int nC, const int *cdofs,
+                    const double *E, const double *nu, const double *rho, const fb_params *prm) {
   if (!out) { fb_set_error("out is NULL"); return FB_ERR_INVALID_ARGUMENT; }
   *out = nullptr;
   if (nV < 0 || nT < 0 || (nV > 0 && !x0) || (nT > 0 && !tets)) {
@@ -253,7 +256,8 @@ int create_impl(fb_context **out, int nV, const double *x0, int nT, const int *t
   CR(fb_dev_alloc(c, &c->mblk, (size_t)c->nB));
   CR(fb_launch_mass(c));
   CR(fb_dev_alloc(c, &c->fixed, (size_t)c->r));
-  CR(apply_constraints(c, nC, cdofs));
+  c->rowmask = c->fixed;
+  CR(fb_apply_constraints(c, nC, cdofs));
   CR(fb_dev_alloc(c, &c->T, (size_t)c->nnzK));
   CR(fb_dev_alloc(c, &c->Keff, (size_t)c->nnzK));
   if (p.keep_raw_stiffness) CR(fb_dev_alloc(c, &c->Kraw, (size_t)c->nnzK));
@@ -282,7 +286,6 @@ int create_impl(fb_context **out, int nV, const double *x0, int nT, const int *t
   return FB_OK;
 }
 
-}  // namespace
 // host copies of the block structure (inspection + haptic ring spreading)
 int fb_fetch_structure(fb_context *c, std::vector<int> &bp, std::vector<int> &bc) {
   bp.resize((size_t)c->nV + 1);
@@ -367,13 +370,13 @@ int fb_create_with_materials(fb_context **out, int nV, const double *x0, int nT,
                              const fb_params *prm) {
   std::vector<int> dofs;
   FB_TRY(fixed_vertices_to_dofs(nV, nFixed, fixedVerts, dofs));
-  return create_impl(out, nV, x0, nT, tets, (int)dofs.size(), dofs.data(), E, nu, rho, prm);
+  return fb_create_local(out, nV, x0, nT, tets, (int)dofs.size(), dofs.data(), E, nu, rho, prm);
 }
 
 int fb_create_with_constrained_dofs(fb_context **out, int nV, const double *x0, int nT, const int *tets, int nC,
                                     const int *cdofs, const fb_params *prm) {
   if (nC < 0 || (nC > 0 && !cdofs)) { fb_set_error("bad constrained DOF list"); return FB_ERR_INVALID_ARGUMENT; }
-  return create_impl(out, nV, x0, nT, tets, nC, cdofs, nullptr, nullptr, nullptr, prm);
+  return fb_create_local(out, nV, x0, nT, tets, nC, cdofs, nullptr, nullptr, nullptr, prm);
 }
 
 void fb_destroy(fb_context *c) { free_all(c); }
@@ -381,13 +384,26 @@ void fb_destroy(fb_context *c) { free_all(c); }
 int fb_set_fixed_vertices(fb_context *c, int nFixed, const int *fv) {
   CHECK_CTX(c);
   std::vector<int> dofs;
+  if (c->dist) { fb_set_error("fb_set_fixed_vertices on a partitioned context: recreate it"); return FB_ERR_NOT_SUPPORTED; }
   FB_TRY(fixed_vertices_to_dofs(c->nV, nFixed, fv, dofs));
-  return apply_constraints(c, (int)dofs.size(), dofs.data());
+  return fb_apply_constraints(c, (int)dofs.size(), dofs.data());
 }
 
-int fb_num_vertices(const fb_context *c) { return c ? c->nV : 0; }
-int fb_num_tets(const fb_context *c) { return c ? c->nT : 0; }
-int fb_num_dofs(const fb_context *c) { return c ? c->r : 0; }
+int fb_num_vertices(const fb_context *c) {
+  int nV = 0, nT = 0;
+  if (c && fb_dist_global_sizes(c, &nV, &nT) == FB_OK) return nV;
+  return c ? c->nV : 0;
+}
+int fb_num_tets(const fb_context *c) {
+  int nV = 0, nT = 0;
+  if (c && fb_dist_global_sizes(c, &nV, &nT) == FB_OK) return nT;
+  return c ? c->nT : 0;
+}
+int fb_num_dofs(const fb_context *c) {
+  int nV = 0, nT = 0;
+  if (c && fb_dist_global_sizes(c, &nV, &nT) == FB_OK) return 3 * nV;
+  return c ? c->r : 0;
+}
 int fb_num_constrained_dofs(const fb_context *c) { return c ? c->nC : 0; }
 long long fb_nnz_stiffness(const fb_context *c) { return c ? c->nnzK : 0; }
 long long fb_nnz_mass(const fb_context *c) { return c ? 3ll * c->nB : 0; }
@@ -416,6 +432,7 @@ long long fb_nnz_system(const fb_context *cc) {
 int fb_set_external_forces(fb_context *c, const double *f) {
   CHECK_CTX(c);
   if (!f) { fb_set_error("f is NULL"); return FB_ERR_INVALID_ARGUMENT; }
+  if (c->dist) return fb_dist_upload_global(c, f, c->fext);
   return upload(c, c->fext, f, sizeof(double) * (size_t)c->r);
 }
 int fb_set_external_forces_dev(fb_context *c, const double *f) {
@@ -427,7 +444,8 @@ int fb_set_external_forces_dev(fb_context *c, const double *f) {
 int fb_add_external_forces(fb_context *c, const double *f) {
   CHECK_CTX(c);
   if (!f) { fb_set_error("f is NULL"); return FB_ERR_INVALID_ARGUMENT; }
-  FB_TRY(upload(c, c->tmp, f, sizeof(double) * (size_t)c->r));
+  if (c->dist) FB_TRY(fb_dist_upload_global(c, f, c->tmp));
+  else FB_TRY(upload(c, c->tmp, f, sizeof(double) * (size_t)c->r));
   if (c->r) { k_axpy<<<gridFor(c->r, 256), 256, 0, c->stream>>>(c->r, 1.0, c->tmp, c->fext); c->launches++; }
   FB_CUDA(cudaStreamSynchronize(c->stream));
   return FB_OK;
@@ -440,11 +458,18 @@ int fb_set_external_forces_to_zero(fb_context *c) {
 int fb_get_external_forces(fb_context *c, double *f) {
   CHECK_CTX(c);
   if (!f) { fb_set_error("f is NULL"); return FB_ERR_INVALID_ARGUMENT; }
+  if (c->dist) return fb_dist_download_owned(c, c->fext, f);
   return download(c, f, c->fext, sizeof(double) * (size_t)c->r);
 }
 int fb_set_state(fb_context *c, const double *q, const double *qvel, const double *qaccel) {
   CHECK_CTX(c);
   if (!q) { fb_set_error("q is NULL"); return FB_ERR_INVALID_ARGUMENT; }
+  if (c->dist) {
+    FB_TRY(fb_dist_upload_global(c, q, c->q));
+    if (qvel) FB_TRY(fb_dist_upload_global(c, qvel, c->qvel));
+    if (qaccel) FB_TRY(fb_dist_upload_global(c, qaccel, c->qaccel));
+    return FB_OK;
+  }
   size_t bytes = sizeof(double) * (size_t)c->r;
   FB_TRY(upload(c, c->q, q, bytes));
   if (qvel) FB_TRY(upload(c, c->qvel, qvel, bytes));
@@ -453,6 +478,13 @@ int fb_set_state(fb_context *c, const double *q, const double *qvel, const doubl
 }
 int fb_get_state(fb_context *c, double *q, double *qvel, double *qaccel) {
   CHECK_CTX(c);
+  if (c->dist) {
+    // global-length outputs: this rank's owned entries, zeros elsewhere (sum over ranks = the full vector)
+    if (q) FB_TRY(fb_dist_download_owned(c, c->q, q));
+    if (qvel) FB_TRY(fb_dist_download_owned(c, c->qvel, qvel));
+    if (qaccel) FB_TRY(fb_dist_download_owned(c, c->qaccel, qaccel));
+    return FB_OK;
+  }
   size_t bytes = sizeof(double) * (size_t)c->r;
   if (bytes == 0) return FB_OK;
   if (q) FB_CUDA(cudaMemcpyAsync(q, c->q, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -130,6 +130,7 @@ int fb_deformable_contact_count(const fb_context *c) { return c ? c->contact_cou
 
 int fb_deformable_timestep(fb_context *c) {
   CHECK_CTX(c);
+  if (c->dist) { fb_set_error("fb_deformable_timestep on a partitioned context: build the force vector on the host and call fb_step"); return FB_ERR_NOT_SUPPORTED; }
   const size_t r = (size_t)c->r;
   if (!c->fext_host) FB_CUDA(cudaMallocHost(&c->fext_host, sizeof(double) * (r ? r : 1)));
   double *f = c->fext_host;

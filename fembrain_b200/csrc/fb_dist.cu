@@ -1,22 +1,371 @@
-// fb_dist.cu — partitioned (multi-GPU) contexts: NCCL halo exchange and scalar all-reduce.
-// (placeholder: filled in once the single-GPU path is parity-green)
+// fb_dist.cu — one big mesh over several GPUs (BASELINE.json config 5): row-block partition, NCCL halo exchange
+// of the PCG search direction and 1-element FP64 all-reduces for the two dot products.
+//
+// No reference counterpart (the reference is single-threaded CPU code).  Design:
+//  * Rows (vertices) are split into `world` contiguous ranges holding equal numbers of tet incidences (a proxy for
+//    matrix nonzeros) — row blocks, METIS-style objective without METIS (not in the image); for the benchmark
+//    cube the ranges are slabs along the slowest index with two neighbours each.
+//  * Each rank keeps the tets that touch one of its rows and all their vertices (owned + ghost), renumbered in
+//    ascending global order, and runs the ordinary single-GPU setup on that local mesh.  Cut tets are therefore
+//    assembled on both sides: assembly needs NO communication, and since contributions are still summed in
+//    ascending (global) element order the owned rows of K are bit-identical to the single-GPU matrix.
+//  * Ghost rows are masked in the solver (rowmask); ghost COLUMNS carry the neighbour's values of d, refreshed by
+//    a halo exchange after every direction update (pack kernel -> grouped ncclSend/ncclRecv -> unpack kernel).
+//    x, q, qvel at ghosts follow by the same arithmetic on the same bits, so the state needs no exchange.
+//  * d.q and sum r^2/diag are reduced per rank in fixed order, then summed across ranks by ncclAllReduce on the
+//    device scalar; every rank sees the same bits, so the loop flag is consistent without a host round trip.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 #include "fb_internal.h"
 
-int fb_dist_halo_exchange(fb_context *, double *) { return FB_ERR_NOT_SUPPORTED; }
-int fb_dist_allreduce_scalar(fb_context *, double *) { return FB_ERR_NOT_SUPPORTED; }
-void fb_dist_destroy(fb_context *) {}
+struct FbDist {
+  ncclComm_t comm;
+  int rank, world;
+  int nV_global, nT_global;
+  int vbeg, vend;            // owned global vertex range
+  std::vector<int> l2g;      // local vertex -> global vertex (ascending)
+  std::vector<unsigned char> owned;  // per local vertex
+  int nNbr;
+  std::vector<int> nbrRank, sendOff, recvOff;  // offsets in vertices, size nNbr + 1
+  int *sendIdx, *recvIdx;    // device: local vertex ids, concatenated per neighbour
+  double *sendBuf, *recvBuf; // device: 3 doubles per vertex
+  double *hostStage;         // pinned, local r doubles
+};
 
-extern "C" {
-int fb_comm_unique_id(void *) { fb_set_error("partitioned contexts not built yet"); return FB_ERR_NOT_SUPPORTED; }
-int fb_create_partitioned(fb_context **, int, const double *, int, const int *, int, const int *, const fb_params *, int, int,
-                          const void *) {
-  fb_set_error("partitioned contexts not built yet");
-  return FB_ERR_NOT_SUPPORTED;
+#define FB_NCCL(call)                                                                        \
+  do {                                                                                       \
+    ncclResult_t r__ = (call);                                                               \
+    if (r__ != ncclSuccess) {                                                                \
+      fb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__));   \
+      return FB_ERR_COMM;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+namespace {
+
+__global__ void k_pack(int n, const int *__restrict__ idx, const double *__restrict__ vec, double *__restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n) return;
+  int i = t / 3, k = t - 3 * i;
+  buf[t] = vec[3 * (size_t)idx[i] + k];
 }
-int fb_partition_range(const fb_context *c, int *b, int *e) {
-  if (!c) return FB_ERR_INVALID_ARGUMENT;
-  if (b) *b = 0;
-  if (e) *e = c->nV;
+__global__ void k_unpack(int n, const int *__restrict__ idx, const double *__restrict__ buf, double *__restrict__ vec) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n) return;
+  int i = t / 3, k = t - 3 * i;
+  vec[3 * (size_t)idx[i] + k] = buf[t];
+}
+__global__ void k_mask_ghost(int nV, const unsigned char *__restrict__ ownedV, const unsigned char *__restrict__ fixed,
+                             unsigned char *__restrict__ rowmask) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * nV) return;
+  rowmask[t] = (fixed[t] || !ownedV[t / 3]) ? 1 : 0;
+}
+
+// ---- the partition plan: pure host integer work, identical on every rank ------------------------------------
+struct Plan {
+  std::vector<int> bounds;       // world + 1 vertex boundaries
+  std::vector<int> localTets;    // global tet ids, ascending
+  std::vector<int> l2g;          // ascending global vertex ids of the local mesh
+  std::vector<int> nbr;          // neighbour ranks, ascending
+  std::vector<std::vector<int> > send, recv;  // global vertex ids per neighbour, ascending
+};
+
+int owner_of(const std::vector<int> &bounds, int v) {
+  return (int)(std::upper_bound(bounds.begin(), bounds.end(), v) - bounds.begin()) - 1;
+}
+
+void make_bounds(int nV, int nT, const int *tets, int world, std::vector<int> &bounds) {
+  std::vector<long long> w((size_t)nV + 1, 0);
+  for (size_t i = 0; i < 4 * (size_t)nT; i++) w[(size_t)tets[i] + 1]++;
+  for (int v = 0; v < nV; v++) w[(size_t)v + 1] += w[v];
+  const long long total = w[nV];
+  bounds.assign((size_t)world + 1, nV);
+  bounds[0] = 0;
+  for (int p = 1; p < world; p++) {
+    const long long target = total * p / world;
+    int v = (int)(std::lower_bound(w.begin(), w.end(), target) - w.begin());
+    if (v > nV) v = nV;
+    if (v < bounds[p - 1]) v = bounds[p - 1];
+    bounds[p] = v;
+  }
+  bounds[world] = nV;
+}
+
+void make_plan(int nV, int nT, const int *tets, int world, int rank, Plan &pl) {
+  make_bounds(nV, nT, tets, world, pl.bounds);
+  const int vb = pl.bounds[rank], ve = pl.bounds[rank + 1];
+  std::vector<unsigned char> mark((size_t)nV, 0);
+  pl.localTets.clear();
+  for (int el = 0; el < nT; el++) {
+    const int *t = tets + 4 * (size_t)el;
+    bool mine = false;
+    for (int i = 0; i < 4; i++) mine |= (t[i] >= vb && t[i] < ve);
+    if (!mine) continue;
+    pl.localTets.push_back(el);
+    for (int i = 0; i < 4; i++) mark[t[i]] = 1;
+  }
+  pl.l2g.clear();
+  for (int v = 0; v < nV; v++)
+    if (mark[v]) pl.l2g.push_back(v);
+  // halo lists from the local tets: a (mine) next to b (rank p) => a goes to p, b comes from p
+  std::vector<std::vector<int> > send((size_t)world), recv((size_t)world);
+  for (size_t k = 0; k < pl.localTets.size(); k++) {
+    const int *t = tets + 4 * (size_t)pl.localTets[k];
+    int own[4];
+    for (int i = 0; i < 4; i++) own[i] = owner_of(pl.bounds, t[i]);
+    for (int i = 0; i < 4; i++) {
+      if (own[i] != rank) continue;
+      for (int j = 0; j < 4; j++)
+        if (own[j] != rank) { send[own[j]].push_back(t[i]); recv[own[j]].push_back(t[j]); }
+    }
+  }
+  pl.nbr.clear(); pl.send.clear(); pl.recv.clear();
+  for (int p = 0; p < world; p++) {
+    if (send[p].empty() && recv[p].empty()) continue;
+    std::sort(send[p].begin(), send[p].end());
+    send[p].erase(std::unique(send[p].begin(), send[p].end()), send[p].end());
+    std::sort(recv[p].begin(), recv[p].end());
+    recv[p].erase(std::unique(recv[p].begin(), recv[p].end()), recv[p].end());
+    pl.nbr.push_back(p);
+    pl.send.push_back(send[p]);
+    pl.recv.push_back(recv[p]);
+  }
+}
+
+}  // namespace
+
+// ---- hooks used by the solver ---------------------------------------------------------------------------------
+int fb_dist_halo_exchange(fb_context *c, double *vec) {
+  FbDist *d = c->dist;
+  if (!d || d->nNbr == 0) return FB_OK;
+  const int nS = d->sendOff[d->nNbr], nR = d->recvOff[d->nNbr];
+  if (nS) { k_pack<<<(3 * nS + 255) / 256, 256, 0, c->stream>>>(nS, d->sendIdx, vec, d->sendBuf); c->launches++; }
+  FB_NCCL(ncclGroupStart());
+  for (int i = 0; i < d->nNbr; i++) {
+    const int ns = d->sendOff[i + 1] - d->sendOff[i], nr = d->recvOff[i + 1] - d->recvOff[i];
+    if (ns) FB_NCCL(ncclSend(d->sendBuf + 3 * (size_t)d->sendOff[i], 3 * (size_t)ns, ncclDouble, d->nbrRank[i], d->comm, c->stream));
+    if (nr) FB_NCCL(ncclRecv(d->recvBuf + 3 * (size_t)d->recvOff[i], 3 * (size_t)nr, ncclDouble, d->nbrRank[i], d->comm, c->stream));
+  }
+  FB_NCCL(ncclGroupEnd());
+  if (nR) { k_unpack<<<(3 * nR + 255) / 256, 256, 0, c->stream>>>(nR, d->recvIdx, d->recvBuf, vec); c->launches++; }
   return FB_OK;
 }
+
+int fb_dist_allreduce_scalar(fb_context *c, double *dev_scalar) {
+  FbDist *d = c->dist;
+  if (!d || d->world == 1) return FB_OK;
+  FB_NCCL(ncclAllReduce(dev_scalar, dev_scalar, 1, ncclDouble, ncclSum, d->comm, c->stream));
+  return FB_OK;
 }
+
+int fb_dist_refresh_rowmask(fb_context *c) {
+  FbDist *d = c->dist;
+  if (!d) return FB_OK;
+  unsigned char *ownedDev = nullptr;
+  FB_CUDA(cudaMalloc(&ownedDev, (size_t)(c->nV ? c->nV : 1)));
+  FB_CUDA(cudaMemcpyAsync(ownedDev, d->owned.data(), (size_t)c->nV, cudaMemcpyHostToDevice, c->stream));
+  if (c->nV) { k_mask_ghost<<<(3 * c->nV + 255) / 256, 256, 0, c->stream>>>(c->nV, ownedDev, c->fixed, c->rowmask); c->launches++; }
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(ownedDev);
+  return FB_OK;
+}
+
+int fb_dist_global_sizes(const fb_context *c, int *nV, int *nT) {
+  if (!c || !c->dist) return FB_ERR_NOT_SUPPORTED;
+  *nV = c->dist->nV_global;
+  *nT = c->dist->nT_global;
+  return FB_OK;
+}
+
+int fb_dist_upload_global(fb_context *c, const double *g, double *localDev) {
+  FbDist *d = c->dist;
+  double *h = d->hostStage;
+  for (int v = 0; v < c->nV; v++) {
+    const size_t gv = 3 * (size_t)d->l2g[v];
+    h[3 * (size_t)v] = g[gv]; h[3 * (size_t)v + 1] = g[gv + 1]; h[3 * (size_t)v + 2] = g[gv + 2];
+  }
+  if (c->r) FB_CUDA(cudaMemcpyAsync(localDev, h, sizeof(double) * (size_t)c->r, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+int fb_dist_download_owned(fb_context *c, const double *localDev, double *g) {
+  FbDist *d = c->dist;
+  double *h = d->hostStage;
+  if (c->r) FB_CUDA(cudaMemcpyAsync(h, localDev, sizeof(double) * (size_t)c->r, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  memset(g, 0, sizeof(double) * 3 * (size_t)d->nV_global);
+  for (int v = 0; v < c->nV; v++) {
+    if (!d->owned[v]) continue;
+    const size_t gv = 3 * (size_t)d->l2g[v];
+    g[gv] = h[3 * (size_t)v]; g[gv + 1] = h[3 * (size_t)v + 1]; g[gv + 2] = h[3 * (size_t)v + 2];
+  }
+  return FB_OK;
+}
+
+void fb_dist_destroy(fb_context *c) {
+  FbDist *d = c->dist;
+  if (!d) return;
+  if (d->sendIdx) cudaFree(d->sendIdx);
+  if (d->recvIdx) cudaFree(d->recvIdx);
+  if (d->sendBuf) cudaFree(d->sendBuf);
+  if (d->recvBuf) cudaFree(d->recvBuf);
+  if (d->hostStage) cudaFreeHost(d->hostStage);
+  if (c->rowmask && c->rowmask != c->fixed) { cudaFree(c->rowmask); c->rowmask = nullptr; }
+  if (d->comm) ncclCommDestroy(d->comm);
+  delete d;
+  c->dist = nullptr;
+}
+
+// ===================================================================================================================
+extern "C" {
+
+int fb_comm_unique_id(void *id128) {
+  if (!id128) return FB_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  FB_NCCL(ncclGetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return FB_OK;
+}
+
+// Host-only inspection of the partition (no GPU needed): what rank `rank` of `world` would own and exchange.
+// counts: [0] vertex_begin, [1] vertex_end, [2] local vertices, [3] local tets, [4] neighbours, [5] total send
+// vertices, [6] total recv vertices.  Optional outputs (NULL to skip) are sized from a first call:
+// l2g[counts[2]], local_tets[counts[3]], nbr_ranks[counts[4]], send_counts/recv_counts[counts[4]],
+// send_global[counts[5]], recv_global[counts[6]] (concatenated per neighbour, ascending global ids).
+int fb_plan_partition(int nV, int nT, const int *tets, int world, int rank, int *counts, int *l2g, int *local_tets,
+                      int *nbr_ranks, int *send_counts, int *recv_counts, int *send_global, int *recv_global) {
+  if (nV < 0 || nT < 0 || (nT > 0 && !tets) || world < 1 || rank < 0 || rank >= world || !counts) {
+    fb_set_error("bad arguments to fb_plan_partition");
+    return FB_ERR_INVALID_ARGUMENT;
+  }
+  for (size_t i = 0; i < 4 * (size_t)nT; i++)
+    if (tets[i] < 0 || tets[i] >= nV) { fb_set_error("tetrahedron %zu references a vertex outside [0, %d)", i / 4, nV); return FB_ERR_BAD_MESH; }
+  Plan pl;
+  make_plan(nV, nT, tets, world, rank, pl);
+  size_t ns = 0, nr = 0;
+  for (size_t i = 0; i < pl.nbr.size(); i++) { ns += pl.send[i].size(); nr += pl.recv[i].size(); }
+  counts[0] = pl.bounds[rank]; counts[1] = pl.bounds[rank + 1];
+  counts[2] = (int)pl.l2g.size(); counts[3] = (int)pl.localTets.size(); counts[4] = (int)pl.nbr.size();
+  counts[5] = (int)ns; counts[6] = (int)nr;
+  if (l2g) memcpy(l2g, pl.l2g.data(), sizeof(int) * pl.l2g.size());
+  if (local_tets) memcpy(local_tets, pl.localTets.data(), sizeof(int) * pl.localTets.size());
+  size_t so = 0, ro = 0;
+  for (size_t i = 0; i < pl.nbr.size(); i++) {
+    if (nbr_ranks) nbr_ranks[i] = pl.nbr[i];
+    if (send_counts) send_counts[i] = (int)pl.send[i].size();
+    if (recv_counts) recv_counts[i] = (int)pl.recv[i].size();
+    if (send_global) memcpy(send_global + so, pl.send[i].data(), sizeof(int) * pl.send[i].size());
+    if (recv_global) memcpy(recv_global + ro, pl.recv[i].data(), sizeof(int) * pl.recv[i].size());
+    so += pl.send[i].size();
+    ro += pl.recv[i].size();
+  }
+  return FB_OK;
+}
+
+int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, const int *tets, int nFixed, const int *fixedVerts,
+                          const fb_params *prm, int rank, int world, const void *comm_id128) {
+  if (!out) return FB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (nV < 0 || nT < 0 || (nV > 0 && !x0) || (nT > 0 && !tets) || world < 1 || rank < 0 || rank >= world || nFixed < 0 ||
+      (nFixed > 0 && !fixedVerts) || (world > 1 && !comm_id128)) {
+    fb_set_error("bad arguments to fb_create_partitioned");
+    return FB_ERR_INVALID_ARGUMENT;
+  }
+  for (size_t i = 0; i < 4 * (size_t)nT; i++)
+    if (tets[i] < 0 || tets[i] >= nV) { fb_set_error("tetrahedron %zu references a vertex outside [0, %d)", i / 4, nV); return FB_ERR_BAD_MESH; }
+  {  // a vertex in no tetrahedron is an error exactly as in fb_create (checked globally here)
+    std::vector<unsigned char> used((size_t)nV, 0);
+    for (size_t i = 0; i < 4 * (size_t)nT; i++) used[tets[i]] = 1;
+    for (int v = 0; v < nV; v++)
+      if (!used[v]) { fb_set_error("vertex %d belongs to no tetrahedron", v); return FB_ERR_BAD_MESH; }
+  }
+  Plan pl;
+  make_plan(nV, nT, tets, world, rank, pl);
+  const int nLV = (int)pl.l2g.size(), nLT = (int)pl.localTets.size();
+  std::vector<int> g2l((size_t)nV, -1);
+  for (int i = 0; i < nLV; i++) g2l[pl.l2g[i]] = i;
+  std::vector<double> lx(3 * (size_t)nLV);
+  for (int i = 0; i < nLV; i++)
+    for (int k = 0; k < 3; k++) lx[3 * (size_t)i + k] = x0[3 * (size_t)pl.l2g[i] + k];
+  std::vector<int> lt(4 * (size_t)nLT);
+  for (int e = 0; e < nLT; e++)
+    for (int k = 0; k < 4; k++) lt[4 * (size_t)e + k] = g2l[tets[4 * (size_t)pl.localTets[e] + k]];
+  std::vector<int> fv(fixedVerts, fixedVerts + nFixed);
+  std::sort(fv.begin(), fv.end());
+  std::vector<int> cd;
+  for (int i = 0; i < nFixed; i++) {
+    if (fv[i] < 0 || fv[i] >= nV) { fb_set_error("fixed vertex %d out of range [0, %d)", fv[i], nV); return FB_ERR_INVALID_ARGUMENT; }
+    if (i && fv[i] == fv[i - 1]) { fb_set_error("fixed vertex %d listed twice", fv[i]); return FB_ERR_INVALID_ARGUMENT; }
+    const int l = g2l[fv[i]];
+    if (l < 0) continue;
+    cd.push_back(3 * l); cd.push_back(3 * l + 1); cd.push_back(3 * l + 2);
+  }
+  fb_context *c = nullptr;
+  FB_TRY(fb_create_local(&c, nLV, lx.data(), nLT, lt.data(), (int)cd.size(), cd.data(), nullptr, nullptr, nullptr, prm));
+  FbDist *d = new FbDist();
+  d->comm = nullptr; d->sendIdx = d->recvIdx = nullptr; d->sendBuf = d->recvBuf = nullptr; d->hostStage = nullptr;
+  d->rank = rank; d->world = world; d->nV_global = nV; d->nT_global = nT;
+  d->vbeg = pl.bounds[rank]; d->vend = pl.bounds[rank + 1];
+  d->l2g = pl.l2g;
+  d->owned.resize((size_t)nLV);
+  for (int i = 0; i < nLV; i++) d->owned[i] = (pl.l2g[i] >= d->vbeg && pl.l2g[i] < d->vend) ? 1 : 0;
+  d->nNbr = (int)pl.nbr.size();
+  d->nbrRank = pl.nbr;
+  d->sendOff.assign((size_t)d->nNbr + 1, 0);
+  d->recvOff.assign((size_t)d->nNbr + 1, 0);
+  std::vector<int> sIdx, rIdx;
+  for (int i = 0; i < d->nNbr; i++) {
+    for (size_t k = 0; k < pl.send[i].size(); k++) sIdx.push_back(g2l[pl.send[i][k]]);
+    for (size_t k = 0; k < pl.recv[i].size(); k++) rIdx.push_back(g2l[pl.recv[i][k]]);
+    d->sendOff[i + 1] = (int)sIdx.size();
+    d->recvOff[i + 1] = (int)rIdx.size();
+  }
+  c->dist = d;
+  int st = FB_OK;
+#define DCHK(call) do { st = (call); if (st != FB_OK) { fb_destroy(c); return st; } } while (0)
+#define DCUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fb_set_error("%s -> %s", #call, cudaGetErrorString(e__)); fb_destroy(c); return FB_ERR_CUDA; } } while (0)
+  DCHK(fb_dev_alloc(c, &d->sendIdx, sIdx.size()));
+  DCHK(fb_dev_alloc(c, &d->recvIdx, rIdx.size()));
+  DCHK(fb_dev_alloc(c, &d->sendBuf, 3 * sIdx.size()));
+  DCHK(fb_dev_alloc(c, &d->recvBuf, 3 * rIdx.size()));
+  if (!sIdx.empty()) DCUDA(cudaMemcpyAsync(d->sendIdx, sIdx.data(), sizeof(int) * sIdx.size(), cudaMemcpyHostToDevice, c->stream));
+  if (!rIdx.empty()) DCUDA(cudaMemcpyAsync(d->recvIdx, rIdx.data(), sizeof(int) * rIdx.size(), cudaMemcpyHostToDevice, c->stream));
+  DCUDA(cudaStreamSynchronize(c->stream));
+  DCUDA(cudaMallocHost(&d->hostStage, sizeof(double) * (size_t)(c->r ? c->r : 1)));
+  unsigned char *mask = nullptr;
+  DCHK(fb_dev_alloc(c, &mask, (size_t)c->r));
+  c->rowmask = mask;
+  DCHK(fb_dist_refresh_rowmask(c));
+  if (world > 1) {
+    ncclUniqueId id;
+    memcpy(&id, comm_id128, sizeof(id));
+    ncclResult_t r = ncclCommInitRank(&d->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      fb_set_error("ncclCommInitRank -> %s", ncclGetErrorString(r));
+      d->comm = nullptr;
+      fb_destroy(c);
+      return FB_ERR_COMM;
+    }
+  }
+#undef DCHK
+#undef DCUDA
+  *out = c;
+  return FB_OK;
+}
+
+int fb_partition_range(const fb_context *c, int *b, int *e) {
+  if (!c) return FB_ERR_INVALID_ARGUMENT;
+  if (b) *b = c->dist ? c->dist->vbeg : 0;
+  if (e) *e = c->dist ? c->dist->vend : c->nV;
+  return FB_OK;
+}
+
+}  // extern "C"

@@ -302,7 +302,7 @@ int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effect
   p.dampK = c->prm.damping_stiffness; p.dampM = c->prm.damping_mass;
   p.effective = effective;
   k_reduce_K<<<grid_for((size_t)c->nB * 9, 256), 256, 0, c->stream>>>(p, c->seg, c->src, c->scrK, c->brow, c->bp, c->diag, c->mblk,
-                                                                     c->fixed, Kraw, c->T, c->Keff, c->invD);
+                                                                     c->rowmask, Kraw, c->T, c->Keff, c->invD);
   k_reduce_f<<<grid_for((size_t)c->r, 256), 256, 0, c->stream>>>(c->nV, c->nT, c->prm.internal_force_scaling, c->diag, c->seg,
                                                                  c->src, c->scrF, c->fint);
   c->launches += 3;
@@ -320,7 +320,7 @@ int fb_launch_spmv_exact(fb_context *c, const double *A, const double *x, double
 
 int fb_launch_rhs(fb_context *c) {
   if (c->r == 0) return FB_OK;
-  k_rhs<<<grid_for((size_t)c->r, 256), 256, 0, c->stream>>>(c->r, c->prm.timestep, c->tmp, c->fint, c->fext, c->fixed, c->qres, c->rhs);
+  k_rhs<<<grid_for((size_t)c->r, 256), 256, 0, c->stream>>>(c->r, c->prm.timestep, c->tmp, c->fint, c->fext, c->rowmask, c->qres, c->rhs);
   c->launches++;
   FB_CUDA(cudaGetLastError());
   return FB_OK;

@@ -74,7 +74,8 @@ struct fb_context {
   unsigned int *src;   // [16 nT]
   int *colIdx;         // [16 nT] element -> block position inside row (reference's columnIndices)
   double *mblk;        // [nB] mass scalar of each block (M = mblk (x) I3)
-  unsigned char *fixed;  // [r] 1 = constrained DOF (or, in partitioned contexts, a row this rank does not own)
+  unsigned char *fixed;    // [r] 1 = constrained DOF (state is pinned to zero there)
+  unsigned char *rowmask;  // [r] rows the solver skips: == fixed, or fixed + ghost rows in partitioned contexts
   int *cdofs;            // [nC] sorted constrained DOFs (device)
   int *cdofs_host;
 
@@ -126,6 +127,9 @@ struct fb_context {
 
 // ---- fb_api.cu -----------------------------------------------------------------------------------
 int fb_do_step(fb_context *c);
+int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const int *tets, int nC, const int *cdofs,
+                    const double *E, const double *nu, const double *rho, const fb_params *prm);
+int fb_apply_constraints(fb_context *c, int nC, const int *cdofs_sorted);
 #ifdef __cplusplus
 #include <vector>
 int fb_fetch_structure(fb_context *c, std::vector<int> &bp, std::vector<int> &bc);
@@ -149,6 +153,11 @@ int fb_spmv_plan(fb_context *c);  // call once after the block structure exists
 int fb_dist_halo_exchange(fb_context *c, double *vec);
 int fb_dist_allreduce_scalar(fb_context *c, double *dev_scalar);
 void fb_dist_destroy(fb_context *c);
+int fb_dist_refresh_rowmask(fb_context *c);  // rowmask = fixed + ghost rows (after constraints change)
+// global-length host vector <-> this rank's local device vector
+int fb_dist_upload_global(fb_context *c, const double *global_host, double *local_dev);
+int fb_dist_download_owned(fb_context *c, const double *local_dev, double *global_host);
+int fb_dist_global_sizes(const fb_context *c, int *nV, int *nT);
 
 template <typename T>
 static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {

@@ -274,14 +274,14 @@ void launch_rows3(fb_context *c, const double *A, const double *x, double *y, in
   size_t cap = (size_t)c->sm_count * (size_t)perSM;
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  k_spmv_rows3<MODE, MINB><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc, c->partials, it);
+  k_spmv_rows3<MODE, MINB><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, c->rhs, c->invD, c->sc, c->partials, it);
   c->launches++;
 }
 
 // r = b (x0 = 0), d = invD r, x = 0, rho0 = sum r^2 invD           (CGSolver.cpp:139-147)
 __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restrict__ b, const double *__restrict__ invD,
                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
-                                                    FbScalars *sc, double *slots, double eps, int maxIt) {
+                                                    FbScalars *sc, double *slots) {
   double part = 0.0;
   for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB) {
     const double bi = b[i], di = invD[i];
@@ -291,16 +291,19 @@ __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restr
     part += (bi * bi) * di;
   }
   double total;
-  if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) {
-    sc->rho[0] = total;
-    sc->rho0 = total;
-    sc->eps2 = eps * eps;
-    sc->max_it = maxIt;
-    sc->iters = 0;
-    sc->dq = 0.0;
-    // while ((residualNorm2 > eps*eps*initialResidualNorm2) && (iteration <= maxIterations)), iteration = 1
-    sc->done = !((total > eps * eps * total) && (1 <= maxIt));
-  }
+  if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) sc->rho[0] = total;
+}
+
+// after rho[0] is final (all-reduced in partitioned contexts): initial residual, loop condition at iteration 1
+__global__ void k_cg_begin(FbScalars *sc, double eps, int maxIt) {
+  const double total = sc->rho[0];
+  sc->rho0 = total;
+  sc->eps2 = eps * eps;
+  sc->max_it = maxIt;
+  sc->iters = 0;
+  sc->dq = 0.0;
+  // while ((residualNorm2 > eps*eps*initialResidualNorm2) && (iteration <= maxIterations)), iteration = 1
+  sc->done = !((total > eps * eps * total) && (1 <= maxIt));
 }
 
 // x += alpha d; REFRESH ? nothing more : (r -= alpha q; rho' = sum r^2 invD)     (CGSolver.cpp:155-174)
@@ -374,7 +377,7 @@ void launch_spmv_g(fb_context *c, const double *A, const double *x, double *y, i
   size_t cap = (size_t)c->sm_count * (size_t)perSM;
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  k_spmv<G, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->fixed, c->rhs, c->invD, c->sc,
+  k_spmv<G, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, c->rhs, c->invD, c->sc,
                                                            c->partials, it);
   c->launches++;
 }
@@ -439,12 +442,11 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
   cudaStream_t st = c->stream;
   if (n == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
   const int vg = vec_grid(c, (size_t)n);
-  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, eps, maxIt);
-  c->launches++;
-  if (c->dist) {
-    // rho0 is a global sum: reduce, then recompute the loop condition on every rank identically
-    return FB_ERR_NOT_SUPPORTED;
-  }
+  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS);
+  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho[0]));  // rho0 is a global sum
+  k_cg_begin<<<1, 1, 0, st>>>(c->sc, eps, maxIt);
+  c->launches += 2;
+  if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));  // ghost entries of d = invD r live on the neighbours
   // Iterations are enqueued in chunks; the loop condition lives on the device (kernels turn into
   // no-ops once `done` is set).  The host looks at the flag of chunk k-1 while chunk k runs.
   const int CH = 32;
@@ -487,8 +489,11 @@ int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
   if (n == 0 || repeats <= 0) { *sec = 0.0; return FB_OK; }
   cudaStream_t st = c->stream;
   const int vg = vec_grid(c, (size_t)n);
-  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, 0.0, 1 << 30);
-  c->launches++;
+  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS);
+  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho[0]));
+  k_cg_begin<<<1, 1, 0, st>>>(c->sc, 0.0, 1 << 30);
+  c->launches += 2;
+  if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));
   for (int it = 1; it <= 3; it++) enqueue_iteration(c, it);
   FB_CUDA(cudaEventRecord(c->ev[3], st));
   for (int it = 4; it < 4 + repeats; it++) enqueue_iteration(c, it);

@@ -212,6 +212,18 @@ int fb_create_partitioned(fb_context **out, int num_vertices, const double *rest
                           const int *fixed_vertices, const fb_params *params, int rank, int world,
                           const void *comm_id128);
 int fb_partition_range(const fb_context *ctx, int *vertex_begin, int *vertex_end);
+/* On a partitioned context every vector argument of the force/state calls is GLOBAL length (3*num_vertices of the whole
+ * mesh): setters take the global vector and keep this rank's part; getters write this rank's OWNED entries and zeros
+ * elsewhere, so the sum over ranks is the full vector.  fb_num_vertices/_tets/_dofs report the global mesh; the
+ * inspection hooks (CSR, maps, rhs, ...) describe the rank's LOCAL system. */
+/* Host-only view of the partition (runs without a GPU): what rank `rank` of `world` owns and exchanges.
+ * counts[7] = {vertex_begin, vertex_end, local vertices, local tets, neighbours, total send vertices, total recv vertices};
+ * every other output may be NULL; sizes come from a first call: l2g[counts[2]] (ascending global vertex ids of the local
+ * mesh), local_tets[counts[3]], nbr_ranks/send_counts/recv_counts[counts[4]], send_global[counts[5]],
+ * recv_global[counts[6]] (concatenated per neighbour, ascending global ids). */
+int fb_plan_partition(int num_vertices, int num_tets, const int *tets, int world, int rank, int *counts, int *l2g,
+                      int *local_tets, int *nbr_ranks, int *send_counts, int *recv_counts, int *send_global,
+                      int *recv_global);
 
 #ifdef __cplusplus
 }

@@ -157,10 +157,14 @@ int fb_dist_halo_exchange(fb_context *c, double *vec) {
   return FB_OK;
 }
 
-int fb_dist_allreduce_scalar(fb_context *c, double *dev_scalar) {
+int fb_dist_allreduce_scalar(fb_context *c, const double *dev_part, double *dev_total) {
   FbDist *d = c->dist;
-  if (!d || d->world == 1) return FB_OK;
-  FB_NCCL(ncclAllReduce(dev_scalar, dev_scalar, 1, ncclDouble, ncclSum, d->comm, c->stream));
+  if (!d) return FB_OK;
+  if (d->world == 1) {
+    FB_CUDA(cudaMemcpyAsync(dev_total, dev_part, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return FB_OK;
+  }
+  FB_NCCL(ncclAllReduce(dev_part, dev_total, 1, ncclDouble, ncclSum, d->comm, c->stream));
   return FB_OK;
 }
 

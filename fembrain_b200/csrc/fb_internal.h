@@ -37,6 +37,9 @@ struct FbScalars {
   unsigned int ticket_a;  // last-block tickets (reset by the last block)
   unsigned int ticket_b;
   int pad[3];
+  // partitioned contexts: this rank's partial sums; ncclAllReduce(part -> dq / rho[it&1]).  Kept apart from the
+  // reduced values so that the all-reduces that still run after `done` cannot compound stale numbers.
+  double dq_part, rho_part;
 };
 
 #define FB_MAX_PARTIALS 4096
@@ -151,7 +154,7 @@ int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec);
 int fb_spmv_plan(fb_context *c);  // call once after the block structure exists
 // ---- fb_dist.cu ------------------------------------------------------------------------------------
 int fb_dist_halo_exchange(fb_context *c, double *vec);
-int fb_dist_allreduce_scalar(fb_context *c, double *dev_scalar);
+int fb_dist_allreduce_scalar(fb_context *c, const double *dev_part, double *dev_total);
 void fb_dist_destroy(fb_context *c);
 int fb_dist_refresh_rowmask(fb_context *c);  // rowmask = fixed + ghost rows (after constraints change)
 // global-length host vector <-> this rank's local device vector

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
                                                   const double *__restrict__ A, const double *__restrict__ x,
                                                   double *__restrict__ y, const unsigned char *__restrict__ fixed,
                                                   const double *__restrict__ b, const double *__restrict__ invD,
-                                                  FbScalars *sc, double *slots, int it) {
+                                                  FbScalars *sc, double *slots, double *outp) {
   if (MODE != 0) {
     if (sc->done) return;
   }
@@ -159,10 +159,10 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
   }
   if (MODE == 1) {
     double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->dq = total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
   } else if (MODE == 2) {
     double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->rho[it & 1] = total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
   }
 }
 
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
                                                               const double *__restrict__ A, const double *__restrict__ x,
                                                               double *__restrict__ y, const unsigned char *__restrict__ fixed,
                                                               const double *__restrict__ b, const double *__restrict__ invD,
-                                                              FbScalars *sc, double *slots, int it) {
+                                                              FbScalars *sc, double *slots, double *outp) {
   if (MODE != 0) {
     if (sc->done) return;
   }
@@ -256,15 +256,15 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
   }
   if (MODE == 1) {
     double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->dq = total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
   } else if (MODE == 2) {
     double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) sc->rho[it & 1] = total;
+    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
   }
 }
 
 template <int MODE, int MINB>
-void launch_rows3(fb_context *c, const double *A, const double *x, double *y, int it) {
+void launch_rows3(fb_context *c, const double *A, const double *x, double *y, double *outp) {
   static int perSM = 0;
   if (!perSM) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_rows3<MODE, MINB>, SPMV_TB, 0) != cudaSuccess || perSM < 1) perSM = 1;
@@ -274,14 +274,14 @@ void launch_rows3(fb_context *c, const double *A, const double *x, double *y, in
   size_t cap = (size_t)c->sm_count * (size_t)perSM;
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  k_spmv_rows3<MODE, MINB><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, c->rhs, c->invD, c->sc, c->partials, it);
+  k_spmv_rows3<MODE, MINB><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, c->rhs, c->invD, c->sc, c->partials, outp);
   c->launches++;
 }
 
 // r = b (x0 = 0), d = invD r, x = 0, rho0 = sum r^2 invD           (CGSolver.cpp:139-147)
 __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restrict__ b, const double *__restrict__ invD,
                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
-                                                    FbScalars *sc, double *slots) {
+                                                    FbScalars *sc, double *slots, double *outp) {
   double part = 0.0;
   for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB) {
     const double bi = b[i], di = invD[i];
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restr
     part += (bi * bi) * di;
   }
   double total;
-  if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) sc->rho[0] = total;
+  if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) *outp = total;
 }
 
 // after rho[0] is final (all-reduced in partitioned contexts): initial residual, loop condition at iteration 1
@@ -310,7 +310,7 @@ __global__ void k_cg_begin(FbScalars *sc, double eps, int maxIt) {
 template <bool REFRESH>
 __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restrict__ d, const double *__restrict__ q,
                                                    const double *__restrict__ invD, double *__restrict__ x,
-                                                   double *__restrict__ r, FbScalars *sc, double *slots, int it) {
+                                                   double *__restrict__ r, FbScalars *sc, double *slots, int it, double *outp) {
   if (sc->done) return;
   const double alpha = sc->rho[(it - 1) & 1] / sc->dq;
   double part = 0.0;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restri
   }
   if (!REFRESH) {
     double total;
-    if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) sc->rho[it & 1] = total;
+    if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) *outp = total;
   }
 }
 
@@ -367,7 +367,7 @@ int vec_grid(const fb_context *c, size_t n) {
 }
 
 template <int G, int MODE>
-void launch_spmv_g(fb_context *c, const double *A, const double *x, double *y, int it) {
+void launch_spmv_g(fb_context *c, const double *A, const double *x, double *y, double *outp) {
   static int perSM = 0;  // resident CTAs of this instantiation per SM (same for every B200)
   if (!perSM) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv<G, MODE>, SPMV_TB, 0) != cudaSuccess || perSM < 1) perSM = 1;
@@ -378,17 +378,17 @@ void launch_spmv_g(fb_context *c, const double *A, const double *x, double *y, i
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
   k_spmv<G, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, c->rhs, c->invD, c->sc,
-                                                           c->partials, it);
+                                                           c->partials, outp);
   c->launches++;
 }
 
 template <int MODE>
-void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, int it) {
-  if (c->use_tiled) { launch_rows3<MODE, 5>(c, A, x, y, it); return; }
+void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, double *outp) {
+  if (c->use_tiled) { launch_rows3<MODE, 5>(c, A, x, y, outp); return; }
   switch (c->spmv_group) {
-    case 8: launch_spmv_g<8, MODE>(c, A, x, y, it); break;
-    case 32: launch_spmv_g<32, MODE>(c, A, x, y, it); break;
-    default: launch_spmv_g<16, MODE>(c, A, x, y, it); break;
+    case 8: launch_spmv_g<8, MODE>(c, A, x, y, outp); break;
+    case 32: launch_spmv_g<32, MODE>(c, A, x, y, outp); break;
+    default: launch_spmv_g<16, MODE>(c, A, x, y, outp); break;
   }
 }
 
@@ -398,18 +398,20 @@ void enqueue_iteration(fb_context *c, int it) {
   double *slotsB = c->partials + FB_MAX_PARTIALS;
   const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64;
   if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
-  launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, it);
+  double *dqOut = c->dist ? &c->sc->dq_part : &c->sc->dq;
+  double *rhoOut = c->dist ? &c->sc->rho_part : &c->sc->rho[it & 1];
+  launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, dqOut);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
-  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq);
+  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it);
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it, rhoOut);
     c->launches++;
-    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, it);
+    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, rhoOut);
   } else {
-    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it);
+    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it, rhoOut);
     c->launches++;
   }
-  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho[it & 1]);
+  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
   k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it);
   c->launches++;
   if (c->dist) fb_dist_halo_exchange(c, c->dir);
@@ -430,7 +432,7 @@ int fb_spmv_plan(fb_context *c) {
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked) {
   (void)masked;
   if (c->nV == 0) return FB_OK;
-  launch_spmv_mode<0>(c, A, x, y, 0);
+  launch_spmv_mode<0>(c, A, x, y, nullptr);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
@@ -442,8 +444,9 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
   cudaStream_t st = c->stream;
   if (n == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
   const int vg = vec_grid(c, (size_t)n);
-  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS);
-  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho[0]));  // rho0 is a global sum
+  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS,
+                                   c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
+  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));  // rho0 is a global sum
   k_cg_begin<<<1, 1, 0, st>>>(c->sc, eps, maxIt);
   c->launches += 2;
   if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));  // ghost entries of d = invD r live on the neighbours
@@ -489,8 +492,9 @@ int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
   if (n == 0 || repeats <= 0) { *sec = 0.0; return FB_OK; }
   cudaStream_t st = c->stream;
   const int vg = vec_grid(c, (size_t)n);
-  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS);
-  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho[0]));
+  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS,
+                                   c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
+  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));
   k_cg_begin<<<1, 1, 0, st>>>(c->sc, 0.0, 1 << 30);
   c->launches += 2;
   if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));

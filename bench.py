@@ -163,6 +163,16 @@ def cpu_reference_sample(nx, cg_sample_iters, iters_per_step, steps, warmup, log
 # committed iteration counts of the bench workload (from rest, steps 1..): measured on B200 by this
 # bench (matches the CPU oracle to +-1 where the oracle is affordable); used by --impl reference to
 # extrapolate its bounded PCG sample without touching the GPU arm
+def ncu_traffic(nx):
+    """dram__bytes_read.sum + dram__bytes_write.sum per SpMV launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json), or None when no capture exists for this size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh).get(str(nx), {}).get("spmv_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def known_iterations(nx):
     try:
         with open(os.path.join(ROOT, "profiles", "bench_iterations.json")) as fh:
@@ -312,9 +322,9 @@ def run_ours(args):
                     "ms_per_step": 1e3 * sec_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": {
-                "kernel": "k_spmv<16,1> (q = Keff d fused with d.q), sampled every 16th PCG iteration inside the timed steps",
+                "kernel": "k_spmv_rows3<1> (q = Keff d fused with d.q), CUDA-event pairs around every 16th PCG iteration's launch inside the timed steps",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(nx),
                 "algorithmic_bytes_per_launch": spmv_bytes, "mean_launch_seconds": spmv_mean, "samples": spmv_samples,
                 "bytes_model": "8 B/nnz values + 4 B per 3x3 block column + 52 B per block row (rowptr, x read, y write)",
                 "reference_layout_equiv_gbs": ((12.0 * nnz + 20.0 * rows) / spmv_mean / 1e9) if spmv_mean > 0 else None,

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <set>
@@ -278,6 +279,32 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   double avg3 = nV ? 3.0 * (double)c->nB / (double)nV : 0.0;
   c->spmv_group = avg3 <= 12.0 ? 8 : (avg3 <= 72.0 ? 16 : 32);
   CR(fb_spmv_plan(c));
+  // Optional L2 policy for the solver's matrix stream (FEMBRAIN_B200_L2PIN=f, default off): a fraction f of the
+  // persisting carve-out is given to a window over Keff (hit = persisting, miss = streaming).  Measured on B200
+  // (profiles/r01_l2pin.txt): no gain at f = 0.5 and a LOSS at f = 1 (PCG iteration 55.8 -> 68 us at 1M tets,
+  // 523 -> 620 us at 10M) because the vectors lose their share of L2 — so it stays off.
+  {
+    const char *env = getenv("FEMBRAIN_B200_L2PIN");
+    const double frac = env ? atof(env) : 0.0;
+    if (frac > 0.0 && c->nnzK > 0 && dp.persistingL2CacheMaxSize > 0 && dp.accessPolicyMaxWindowSize > 0) {
+      size_t persist = (size_t)(frac * (double)dp.persistingL2CacheMaxSize);
+      if (persist > (size_t)dp.persistingL2CacheMaxSize) persist = (size_t)dp.persistingL2CacheMaxSize;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+        size_t win = sizeof(double) * (size_t)c->nnzK;
+        if (win > (size_t)dp.accessPolicyMaxWindowSize) win = (size_t)dp.accessPolicyMaxWindowSize;
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = c->Keff;
+        attr.accessPolicyWindow.num_bytes = win;
+        double ratio = 0.95 * (double)persist / (double)win;
+        attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) c->l2_pinned_bytes = (size_t)(attr.accessPolicyWindow.hitRatio * (double)win);
+      }
+      cudaGetLastError();
+    }
+  }
   CRC(cudaStreamSynchronize(c->stream));
   CRC(cudaGetLastError());
 #undef CR

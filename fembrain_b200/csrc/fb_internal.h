@@ -59,6 +59,7 @@ struct fb_context {
   int nC;         // constrained DOFs
   long long nnzK;  // 9 * nB
   size_t bytes;   // device bytes held
+  size_t l2_pinned_bytes;  // bytes of Keff covered by the persisting-L2 access policy window
 
   // mesh
   double *x0;  // [3 nV] rest positions

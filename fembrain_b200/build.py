@@ -24,10 +24,11 @@ UNITS = {
     "fb_setup.cu": [],
     "fb_fem.cu": ["-fmad=false"],
     "fb_pcg.cu": [],
+    "fb_pcg_persistent.cu": [],
     "fb_dist.cu": [],
     "fb_deformable.cu": ["-fmad=false"],
 }
-HEADERS = ["fb_internal.h", "fb_element_math.h", os.path.join("..", "..", "include", "fembrain_b200.h")]
+HEADERS = ["fb_internal.h", "fb_element_math.h", "fb_pcg_common.cuh", os.path.join("..", "..", "include", "fembrain_b200.h")]
 
 
 def _nvcc() -> str:

@@ -104,7 +104,7 @@ void free_all(fb_context *c) {
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,
-                  c->contact_dev, c->ctaRows};
+                  c->contact_dev, c->ctaRows, c->pers_prof};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -790,12 +790,23 @@ int fb_set_profiling(fb_context *c, int enabled) {
   c->profiling = enabled != 0;
   c->prof_sum_s = 0.0;
   c->prof_samples = 0;
+  if (c->pers_prof) FB_CUDA(cudaMemsetAsync(c->pers_prof, 0, 2 * sizeof(unsigned long long), c->stream));
   return FB_OK;
 }
 int fb_get_spmv_profile(fb_context *c, double *mean, int *samples, double *bytes) {
   if (!c) return FB_ERR_INVALID_ARGUMENT;
-  if (mean) *mean = c->prof_samples ? c->prof_sum_s / c->prof_samples : 0.0;
-  if (samples) *samples = c->prof_samples;
+  if (c->pers_grid > 0 && c->pers_prof && !c->dist) {
+    // persistent kernel: %globaltimer around the SpMV phase including its grid barrier, sampled by CTA 0
+    unsigned long long h[2] = {0, 0};
+    cudaSetDevice(c->device);
+    FB_CUDA(cudaMemcpyAsync(h, c->pers_prof, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    if (mean) *mean = h[1] ? 1e-9 * (double)h[0] / (double)h[1] : 0.0;
+    if (samples) *samples = (int)h[1];
+  } else {
+    if (mean) *mean = c->prof_samples ? c->prof_sum_s / c->prof_samples : 0.0;
+    if (samples) *samples = c->prof_samples;
+  }
   // 8 B value per scalar nonzero + 4 B block column per 3x3 block + per block row: 4 B row pointer,
   // 24 B of x (compulsory read), 24 B of y (write) [+ 3 B mask + 24 B d re-read for the fused dot]
   if (bytes) *bytes = 8.0 * (double)c->nnzK + 4.0 * (double)c->nB + 52.0 * (double)c->nV;

@@ -119,7 +119,10 @@ struct fb_context {
   long long launches;
   int spmv_group;        // lanes per block row chosen at setup
   int use_tiled;         // 1: k_spmv_rows3 (16 lanes per row, all loads of a row in flight), 0: k_spmv<G>
-  int *ctaRows;          // reserved
+  // persistent cooperative PCG kernel (fb_pcg_persistent.cu): contiguous row range per CTA, equal block counts
+  int *ctaRows;          // [pers_grid + 1] device
+  int pers_grid;         // 0 = use the three-kernels-per-iteration path
+  unsigned long long *pers_prof;  // device [2]: summed ns of sampled SpMV phases, sample count
   // optional sampling of SpMV launch durations inside fb_step
   int profiling, nprof;
   cudaEvent_t evProf[128];
@@ -153,6 +156,9 @@ int fb_pcg_solve(fb_context *c, double eps, int max_it);  // solves Keff x = rhs
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked);
 int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec);
 int fb_spmv_plan(fb_context *c);  // call once after the block structure exists
+// ---- fb_pcg_persistent.cu --------------------------------------------------------------------------
+int fb_pcg_plan_persistent(fb_context *c);
+int fb_pcg_launch_persistent(fb_context *c);
 // ---- fb_dist.cu ------------------------------------------------------------------------------------
 int fb_dist_halo_exchange(fb_context *c, double *vec);
 int fb_dist_allreduce_scalar(fb_context *c, const double *dev_part, double *dev_total);

@@ -31,17 +31,12 @@
 #include <cstring>
 
 #include "fb_internal.h"
+#include "fb_pcg_common.cuh"
 
 namespace {
 
 constexpr int SPMV_TB = 256;
 constexpr int VEC_TB = 256;
-
-__device__ __forceinline__ double ld_stream(const double *p) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
 
 // Deterministic block reduction followed by the "last block adds all slots in order" pattern.
 // Returns true in every thread of the last block; *total is then valid in thread 0.
@@ -163,27 +158,6 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
   } else if (MODE == 2) {
     double total;
     if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
-  }
-}
-
-// lanes per block row and scalars covered by the three unrolled passes of k_spmv_rows3
-constexpr int TILE_G = 16;
-constexpr int TILE_CHUNK = 3 * TILE_G;
-
-struct RowVals {
-  double v[3][3];  // [pass][k]
-};
-
-__device__ __forceinline__ void load_row_chunk(const double *__restrict__ A, int rs, int n3, int base, int lane, RowVals &o) {
-  const double *a0 = A + 9 * (size_t)rs + base;
-#pragma unroll
-  for (int p = 0; p < 3; p++) {
-    const int t = base + lane + TILE_G * p;
-    const bool ok = t < n3;
-    const double *q = a0 + lane + TILE_G * p;
-    o.v[p][0] = ok ? ld_stream(q) : 0.0;
-    o.v[p][1] = ok ? ld_stream(q + n3) : 0.0;
-    o.v[p][2] = ok ? ld_stream(q + 2 * (size_t)n3) : 0.0;
   }
 }
 
@@ -426,7 +400,7 @@ void enqueue_iteration(fb_context *c, int it) {
 int fb_spmv_plan(fb_context *c) {
   const char *env = getenv("FEMBRAIN_B200_SPMV");
   c->use_tiled = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
-  return FB_OK;
+  return fb_pcg_plan_persistent(c);
 }
 
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked) {
@@ -444,6 +418,22 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
   cudaStream_t st = c->stream;
   if (n == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
   const int vg = vec_grid(c, (size_t)n);
+  if (c->pers_grid > 0 && !c->dist) {
+    // one cooperative kernel runs the whole loop (fb_pcg_persistent.cu)
+    k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, &c->sc->rho[0]);
+    k_cg_begin<<<1, 1, 0, st>>>(c->sc, eps, maxIt);
+    c->launches += 2;
+    FB_TRY(fb_pcg_launch_persistent(c));
+    FB_CUDA(cudaMemcpyAsync(&c->sc_host[2], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    FB_CUDA(cudaGetLastError());
+    const FbScalars &s = c->sc_host[2];
+    const double rhoFinal = s.rho[s.iters & 1];
+    const bool notConverged = rhoFinal > s.eps2 * s.rho0;
+    c->last_iters = s.iters * (notConverged ? -1 : 1);
+    c->last_ratio = (s.rho0 != 0.0) ? rhoFinal / s.rho0 : 0.0;
+    return FB_OK;
+  }
   k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS,
                                    c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
   if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));  // rho0 is a global sum
@@ -492,6 +482,19 @@ int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
   if (n == 0 || repeats <= 0) { *sec = 0.0; return FB_OK; }
   cudaStream_t st = c->stream;
   const int vg = vec_grid(c, (size_t)n);
+  if (c->pers_grid > 0 && !c->dist) {
+    k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, &c->sc->rho[0]);
+    k_cg_begin<<<1, 1, 0, st>>>(c->sc, 0.0, repeats);
+    c->launches += 2;
+    FB_CUDA(cudaEventRecord(c->ev[3], st));
+    FB_TRY(fb_pcg_launch_persistent(c));
+    FB_CUDA(cudaEventRecord(c->ev[7], st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    FB_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]));
+    *sec = 1e-3 * ms / repeats;
+    return FB_OK;
+  }
   k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS,
                                    c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
   if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));

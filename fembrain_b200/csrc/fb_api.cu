@@ -100,6 +100,7 @@ int download(fb_context *c, void *dst, const void *src, size_t bytes) {
 void free_all(fb_context *c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  fb_pcg_release(c);
   fb_dist_destroy(c);
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
@@ -271,7 +272,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   }
   CR(fb_dev_alloc(c, &c->sc, 1));
   CRC(cudaMemsetAsync(c->sc, 0, sizeof(FbScalars), c->stream));
-  CR(fb_dev_alloc(c, &c->partials, 2 * (size_t)FB_MAX_PARTIALS));
+  CR(fb_dev_alloc(c, &c->partials, 4 * (size_t)FB_MAX_PARTIALS));
   CR(fb_dev_alloc(c, &c->contact_dev, 1));
   CRC(cudaMallocHost(&c->sc_host, sizeof(FbScalars) * 4));
   memset(c->sc_host, 0, sizeof(FbScalars) * 4);

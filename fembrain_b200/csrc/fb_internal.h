@@ -30,6 +30,7 @@ struct FbScalars {
   double rho[2];
   double rho0;
   double dq;        // d . (A d) of the current iteration
+  double rq, qq;    // (r, q)_D and (q, q)_D of the current iteration (fused schedule)
   double eps2;      // epsilon^2
   int max_it;
   int iters;        // iterations completed
@@ -118,7 +119,12 @@ struct fb_context {
   double last_ratio;
   long long launches;
   int spmv_group;        // lanes per block row chosen at setup
-  int use_tiled;         // 1: k_spmv_rows3 (16 lanes per row, all loads of a row in flight), 0: k_spmv<G>
+  int use_rows3;         // 1: k_spmv_rows3 (16 lanes per row, all loads of a row in flight), 0: k_spmv<G>
+  int rows3_minb;        // resident CTAs/SM requested for k_spmv_rows3 modes 0-2 (4 or 5)
+  int grid_spmv[4], grid_vec;  // one-resident-wave launch shapes per SpMV mode and for the vector kernels
+  int pcg_fused, pcg_graph;    // two-kernel schedule / CUDA-graph replay of a 30-iteration period
+  void *graph_exec;            // cudaGraphExec_t
+  int graph_kernels, graph_failed;
   // persistent cooperative PCG kernel (fb_pcg_persistent.cu): contiguous row range per CTA, equal block counts
   int *ctaRows;          // [pers_grid + 1] device
   int pers_grid;         // 0 = use the three-kernels-per-iteration path
@@ -156,6 +162,7 @@ int fb_pcg_solve(fb_context *c, double eps, int max_it);  // solves Keff x = rhs
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked);
 int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec);
 int fb_spmv_plan(fb_context *c);  // call once after the block structure exists
+void fb_pcg_release(fb_context *c);
 // ---- fb_pcg_persistent.cu --------------------------------------------------------------------------
 int fb_pcg_plan_persistent(fb_context *c);
 int fb_pcg_launch_persistent(fb_context *c);

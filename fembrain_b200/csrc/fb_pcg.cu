@@ -7,26 +7,32 @@
 //     q = A d; alpha = rho / (d.q); x += alpha d
 //     it % 30 == 0 ? r = b - A x : r -= alpha q
 //     rho' = sum r^2 invD; beta = rho'/rho; d = invD r + beta d
-// Same recurrences, same refresh period, same stopping rule; sums are parallel reductions with a
-// FIXED association order (deterministic run to run), so iterates agree with the reference's
-// sequential sums to rounding, not bitwise.
+// Same recurrences for x, r, d, same refresh period, same stopping rule (tested on the directly summed
+// rho'); sums are parallel reductions with a FIXED association order (deterministic run to run), so iterates
+// agree with the reference's sequential sums to rounding, not bitwise.
 //
-// The constrained system (fixed rows/columns removed, CGSolver on systemMatrix) is solved IN PLACE
-// on full-length vectors: rows of constrained DOFs produce 0 and their entries of d, r, x stay 0,
-// which contributes exact zeros to every sum — arithmetically the compacted system, without the
-// per-step gather of AssignSuperMatrix (sparseMatrix.cpp:993-1002).
+// The constrained system (fixed rows/columns removed, CGSolver on systemMatrix) is solved IN PLACE on
+// full-length vectors: rows of constrained DOFs produce 0 and their entries of d, r, x stay 0, which
+// contributes exact zeros to every sum — arithmetically the compacted system, without the per-step gather of
+// AssignSuperMatrix (sparseMatrix.cpp:993-1002).
 //
-// Three kernels per iteration, all HBM-streaming, scalars (alpha, beta, rho, loop condition)
-// stay on the device:
-//   k_spmv_cg     q = A d  (+ d.q)            A values + block columns streamed once, d gathered
-//   k_update      x += alpha d; r -= alpha q  (+ rho')
-//   k_direction   d = invD r + beta d         (+ loop bookkeeping)
-// Block-level partial sums go to a fixed slot per CTA; the last CTA to finish (integer ticket)
-// adds the slots in index order.
+// Two schedules, both with alpha/beta/rho and the loop flag resident on the device:
+//  * fused (default on one GPU), TWO kernels per iteration:
+//      k_spmv_rows3<3>   q = A d, and the three sums d.q, (r,q)_D, (q,q)_D  ((u,v)_D = sum u v / diag)
+//      k_fused_update    alpha = rho/d.q; x += alpha d; r -= alpha q; d = invD r + beta d; rho' = sum r^2 invD
+//    beta needs rho' before r is updated; it is taken from the identity rho' = rho - 2 alpha (r,q)_D +
+//    alpha^2 (q,q)_D (exact in exact arithmetic, differs from the direct sum by rounding), while the rho used
+//    for the next alpha and for the stopping test is the DIRECT sum accumulated in the same pass.  This removes one
+//    launch and 24 B/row of vector traffic per iteration.  Every 30th iteration runs the reference's refresh
+//    unfused (x update, r = b - A x with the direct rho', direction update).
+//    A CUDA graph replays one 30-iteration period (58 + 4 kernels) per launch.
+//  * kernels (partitioned contexts; FEMBRAIN_B200_PCG=kernels), THREE kernels per iteration in the reference's
+//    literal order: k_spmv<1> (q, d.q), k_update (x, r, rho'), k_direction (beta, d), with NCCL calls between.
+// Per-CTA partial sums go to a fixed slot; the last CTA to finish (integer ticket) adds the slots in index order.
 //
-// Matrix layout: the reference's CSR value order with 3x3-block-compressed column indices:
-// block row v owns 9*nb doubles at 9*bp[v]: three scalar rows of 3*nb values each; column of entry
-// t of a scalar row is 3*bc[bp[v] + t/3] + t%3.  8.44 bytes per nonzero instead of CSR's 12.
+// Matrix layout: the reference's CSR value order with 3x3-block-compressed column indices: block row v owns
+// 9*nb doubles at 9*bp[v]: three scalar rows of 3*nb values each; column of entry t of a scalar row is
+// 3*bc[bp[v] + t/3] + t%3.  8.44 bytes per nonzero instead of CSR's 12.
 #include <cstdlib>
 #include <cstring>
 
@@ -38,23 +44,31 @@ namespace {
 constexpr int SPMV_TB = 256;
 constexpr int VEC_TB = 256;
 
-// Deterministic block reduction followed by the "last block adds all slots in order" pattern.
-// Returns true in every thread of the last block; *total is then valid in thread 0.
-template <int TB>
-__device__ __forceinline__ bool block_reduce_to_total(double v, double *slots, unsigned int *ticket, double *total) {
-  __shared__ double wsum[TB / 32];
+// Deterministic block reduction of N values followed by the "last block adds all slots in order" pattern.
+// Value k of CTA b goes to slots[k * FB_MAX_PARTIALS + b].  Returns true in every thread of the last block;
+// total[] is then valid in thread 0.
+template <int TB, int N>
+__device__ __forceinline__ bool block_reduce_to_total(double (&v)[N], double *slots, unsigned int *ticket, double (&total)[N]) {
+  __shared__ double wsum[N][TB / 32];
   __shared__ bool isLast;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if (lane == 0) wsum[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    double s = (lane < TB / 32) ? wsum[lane] : 0.0;
+  for (int k = 0; k < N; k++) {
+    double s = v[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) wsum[k][warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      double s = (lane < TB / 32) ? wsum[k][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) slots[(size_t)k * FB_MAX_PARTIALS + blockIdx.x] = s;
+    }
     if (lane == 0) {
-      slots[blockIdx.x] = s;
       __threadfence();
       unsigned int tk = atomicAdd(ticket, 1u);
       isLast = (tk == gridDim.x - 1);
@@ -64,32 +78,76 @@ __device__ __forceinline__ bool block_reduce_to_total(double v, double *slots, u
   if (!isLast) return false;
   __threadfence();
   // fixed-order final sum: thread t adds slots t, t+TB, ...; then the same block tree
-  double s = 0.0;
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += TB) s += ((volatile double *)slots)[i];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  __syncthreads();
-  if (lane == 0) wsum[warp] = s;
-  __syncthreads();
-  if (warp == 0) {
-    double z = (lane < TB / 32) ? wsum[lane] : 0.0;
+  for (int k = 0; k < N; k++) {
+    double s = 0.0;
+    const volatile double *sl = slots + (size_t)k * FB_MAX_PARTIALS;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += TB) s += sl[i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) z += __shfl_down_sync(0xffffffffu, z, o);
-    if (lane == 0) {
-      *total = z;
-      *ticket = 0u;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if (lane == 0) wsum[k][warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double z = (lane < TB / 32) ? wsum[k][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) z += __shfl_down_sync(0xffffffffu, z, o);
+      if (lane == 0) total[k] = z;
     }
   }
+  if (threadIdx.x == 0) *ticket = 0u;
   return true;
 }
 
-// MODE 0: y = A x                     (no mask, no reduction)       — generic product
-// MODE 1: y = mask(A x), sum x.y      (x = d, y = q)                — CG iteration
-// MODE 2: y = mask(b - A x), sum y^2 invD   (x = x, y = r)          — exact-residual refresh
+// what the lanes holding a finished row do with it, per MODE:
+// 0: y = A x                                   generic product (no mask, no sums)
+// 1: y = mask(A x); sum x.y                    q = A d with d.q                 (kernels schedule)
+// 2: y = mask(b - A x); sum y^2 invD           exact-residual refresh
+// 3: y = mask(A x); sums x.y, (rv,y)_D, (y,y)_D   q = A d with the three sums   (fused schedule; rv = r)
+template <int MODE>
+__device__ __forceinline__ void finish_row(double s, size_t row, const double *__restrict__ x, double *__restrict__ y,
+                                           const unsigned char *__restrict__ mask, const double *__restrict__ b,
+                                           const double *__restrict__ invD, double (&part)[3]) {
+  if (MODE == 0) {
+    y[row] = s;
+  } else if (MODE == 1) {
+    if (mask[row]) s = 0.0;
+    y[row] = s;
+    part[0] = fma(x[row], s, part[0]);
+  } else if (MODE == 2) {
+    const double rres = mask[row] ? 0.0 : (b[row] - s);
+    y[row] = rres;
+    part[0] += (rres * rres) * invD[row];
+  } else {
+    if (mask[row]) s = 0.0;
+    y[row] = s;
+    const double wi = invD[row];
+    part[0] = fma(x[row], s, part[0]);
+    part[1] += (b[row] * s) * wi;  // b carries r in this mode
+    part[2] += (s * s) * wi;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void finish_kernel(double (&part)[3], FbScalars *sc, double *slots, double *outp) {
+  if (MODE == 1 || MODE == 2) {
+    double p1[1] = {part[0]}, t1[1];
+    if (block_reduce_to_total<SPMV_TB, 1>(p1, slots, &sc->ticket_a, t1) && threadIdx.x == 0) *outp = t1[0];
+  } else if (MODE == 3) {
+    double t3[3];
+    if (block_reduce_to_total<SPMV_TB, 3>(part, slots, &sc->ticket_a, t3) && threadIdx.x == 0) {
+      sc->dq = t3[0];
+      sc->rq = t3[1];
+      sc->qq = t3[2];
+    }
+  }
+}
+
+// ---- generic row-per-G-lanes SpMV (G = 8 or 32: meshes with very short or very long rows) -------------------
 template <int G, int MODE>
 __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
                                                   const double *__restrict__ A, const double *__restrict__ x,
-                                                  double *__restrict__ y, const unsigned char *__restrict__ fixed,
+                                                  double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                   const double *__restrict__ b, const double *__restrict__ invD,
                                                   FbScalars *sc, double *slots, double *outp) {
   if (MODE != 0) {
@@ -98,11 +156,11 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
   const int lane = threadIdx.x & (G - 1);
   // the G lanes of a group always take the same trips through the row loop; other groups of the warp may
   // not, so shuffles name only the group's own lanes
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   const int groupsPerBlock = SPMV_TB / G;
   const int group = blockIdx.x * groupsPerBlock + threadIdx.x / G;
   const int nGroups = gridDim.x * groupsPerBlock;
-  double part = 0.0;
+  double part[3] = {0.0, 0.0, 0.0};
   for (int v = group; v < nV; v += nGroups) {
     const int rs = __ldg(bp + v), re = __ldg(bp + v + 1);
     const int n3 = 3 * (re - rs);
@@ -111,8 +169,7 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
     const double *a2 = a1 + n3;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     int t = lane;
-    // two passes per trip: six independent streaming loads in flight per lane
-    for (; t + G < n3; t += 2 * G) {
+    for (; t + G < n3; t += 2 * G) {  // two passes per trip: six independent streaming loads in flight per lane
       const int jb0 = t / 3, l0 = t - 3 * jb0;
       const int t1 = t + G;
       const int jb1 = t1 / 3, l1 = t1 - 3 * jb1;
@@ -136,39 +193,19 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
       acc1 += __shfl_xor_sync(gmask, acc1, o, G);
       acc2 += __shfl_xor_sync(gmask, acc2, o, G);
     }
-    if (lane < 3) {
-      double s = (lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2);
-      const size_t row = 3 * (size_t)v + lane;
-      if (MODE == 0) {
-        y[row] = s;
-      } else if (MODE == 1) {
-        if (fixed[row]) s = 0.0;
-        y[row] = s;
-        part = fma(x[row], s, part);
-      } else {
-        double rr = fixed[row] ? 0.0 : (b[row] - s);
-        y[row] = rr;
-        part += (rr * rr) * invD[row];
-      }
-    }
+    if (lane < 3) finish_row<MODE>((lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2), 3 * (size_t)v + lane, x, y, mask, b, invD, part);
   }
-  if (MODE == 1) {
-    double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
-  } else if (MODE == 2) {
-    double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
-  }
+  finish_kernel<MODE>(part, sc, slots, outp);
 }
 
 // ---- row-per-16-lanes SpMV with every load of a row in flight at once (no shared memory, no block syncs) ----
-// Same mapping as k_spmv<16,*>, but the three 16-wide passes over a row are fully unrolled and predicated, so a
-// lane has 9 streaming value loads + 3 column loads outstanding before the first multiply, and the row pointers
-// of the group's next row are fetched one row ahead.  MINB = resident CTAs per SM requested from the compiler.
+// The three 16-wide passes over a row are fully unrolled and predicated, so a lane has 9 streaming value loads +
+// 3 column loads outstanding before the first multiply, and the row pointers of the group's next row are fetched
+// one row ahead.  MINB = resident CTAs per SM requested from the compiler (5 -> 48 registers, no spills).
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
                                                               const double *__restrict__ A, const double *__restrict__ x,
-                                                              double *__restrict__ y, const unsigned char *__restrict__ fixed,
+                                                              double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                               const double *__restrict__ b, const double *__restrict__ invD,
                                                               FbScalars *sc, double *slots, double *outp) {
   if (MODE != 0) {
@@ -179,7 +216,7 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
   const int groupsPerBlock = SPMV_TB / TILE_G;
   const int group = blockIdx.x * groupsPerBlock + threadIdx.x / TILE_G;
   const int nGroups = gridDim.x * groupsPerBlock;
-  double part = 0.0;
+  double part[3] = {0.0, 0.0, 0.0};
   int v = group;
   int rs = 0, re = 0;
   if (v < nV) { rs = __ldg(bp + v); re = __ldg(bp + v + 1); }
@@ -188,6 +225,15 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
     int rsn = 0, ren = 0;
     if (vn < nV) { rsn = __ldg(bp + vn); ren = __ldg(bp + vn + 1); }
     const int n3 = 3 * (re - rs);
+    // the lanes that will own the finished row fetch its vector entries now, so the loads fly with the row's values
+    const size_t row = 3 * (size_t)v + (lane < 3 ? lane : 0);
+    double xr = 0.0, br = 0.0, wr = 0.0;
+    unsigned char mk = 0;
+    if (lane < 3) {
+      if (MODE != 0) mk = __ldg(mask + row);
+      if (MODE == 1 || MODE == 3) xr = __ldg(x + row);
+      if (MODE == 2 || MODE == 3) { br = __ldg(b + row); wr = __ldg(invD + row); }
+    }
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     for (int base = 0; base < n3; base += TILE_CHUNK) {
       RowVals val;
@@ -213,59 +259,43 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
     }
     if (lane < 3) {
       double s = (lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2);
-      const size_t row = 3 * (size_t)v + lane;
       if (MODE == 0) {
         y[row] = s;
       } else if (MODE == 1) {
-        if (fixed[row]) s = 0.0;
+        if (mk) s = 0.0;
         y[row] = s;
-        part = fma(x[row], s, part);
-      } else {
-        const double rres = fixed[row] ? 0.0 : (b[row] - s);
+        part[0] = fma(xr, s, part[0]);
+      } else if (MODE == 2) {
+        const double rres = mk ? 0.0 : (br - s);
         y[row] = rres;
-        part += (rres * rres) * invD[row];
+        part[0] += (rres * rres) * wr;
+      } else {
+        if (mk) s = 0.0;
+        y[row] = s;
+        part[0] = fma(xr, s, part[0]);
+        part[1] += (br * s) * wr;  // b carries r in this mode
+        part[2] += (s * s) * wr;
       }
     }
     v = vn; rs = rsn; re = ren;
   }
-  if (MODE == 1) {
-    double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
-  } else if (MODE == 2) {
-    double total;
-    if (block_reduce_to_total<SPMV_TB>(part, slots, &sc->ticket_a, &total) && threadIdx.x == 0) *outp = total;
-  }
-}
-
-template <int MODE, int MINB>
-void launch_rows3(fb_context *c, const double *A, const double *x, double *y, double *outp) {
-  static int perSM = 0;
-  if (!perSM) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_rows3<MODE, MINB>, SPMV_TB, 0) != cudaSuccess || perSM < 1) perSM = 1;
-  }
-  const size_t groupsPerBlock = SPMV_TB / TILE_G;
-  size_t want = ((size_t)c->nV + groupsPerBlock - 1) / groupsPerBlock;
-  size_t cap = (size_t)c->sm_count * (size_t)perSM;
-  if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
-  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  k_spmv_rows3<MODE, MINB><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, c->rhs, c->invD, c->sc, c->partials, outp);
-  c->launches++;
+  finish_kernel<MODE>(part, sc, slots, outp);
 }
 
 // r = b (x0 = 0), d = invD r, x = 0, rho0 = sum r^2 invD           (CGSolver.cpp:139-147)
 __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restrict__ b, const double *__restrict__ invD,
                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
                                                     FbScalars *sc, double *slots, double *outp) {
-  double part = 0.0;
+  double part[1] = {0.0};
   for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB) {
     const double bi = b[i], di = invD[i];
     x[i] = 0.0;
     r[i] = bi;
     d[i] = di * bi;
-    part += (bi * bi) * di;
+    part[0] += (bi * bi) * di;
   }
-  double total;
-  if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) *outp = total;
+  double total[1];
+  if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) *outp = total[0];
 }
 
 // after rho[0] is final (all-reduced in partitioned contexts): initial residual, loop condition at iteration 1
@@ -275,114 +305,191 @@ __global__ void k_cg_begin(FbScalars *sc, double eps, int maxIt) {
   sc->eps2 = eps * eps;
   sc->max_it = maxIt;
   sc->iters = 0;
-  sc->dq = 0.0;
+  sc->dq = sc->rq = sc->qq = 0.0;
   // while ((residualNorm2 > eps*eps*initialResidualNorm2) && (iteration <= maxIterations)), iteration = 1
   sc->done = !((total > eps * eps * total) && (1 <= maxIt));
 }
 
 // x += alpha d; REFRESH ? nothing more : (r -= alpha q; rho' = sum r^2 invD)     (CGSolver.cpp:155-174)
+// itArg > 0: iteration number from the host; itArg <= 0: from the device counter (graph replay)
 template <bool REFRESH>
 __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restrict__ d, const double *__restrict__ q,
                                                    const double *__restrict__ invD, double *__restrict__ x,
-                                                   double *__restrict__ r, FbScalars *sc, double *slots, int it, double *outp) {
+                                                   double *__restrict__ r, FbScalars *sc, double *slots, int itArg, double *outp) {
   if (sc->done) return;
+  const int it = itArg > 0 ? itArg : sc->iters + 1;
   const double alpha = sc->rho[(it - 1) & 1] / sc->dq;
-  double part = 0.0;
-  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB) {
-    const double di = d[i];
-    x[i] = fma(alpha, di, x[i]);
+  double part[1] = {0.0};
+  // two doubles per thread per trip (128-bit loads/stores); element n-1 of an odd-length vector is handled last
+  const size_t n2 = (size_t)n >> 1;
+  const double2 *d2 = reinterpret_cast<const double2 *>(d), *q2 = reinterpret_cast<const double2 *>(q);
+  const double2 *w2 = reinterpret_cast<const double2 *>(invD);
+  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
+    const double2 dv = d2[i];
+    double2 xv = x2[i];
+    xv.x = fma(alpha, dv.x, xv.x); xv.y = fma(alpha, dv.y, xv.y);
+    x2[i] = xv;
+    if (!REFRESH) {
+      const double2 qv = q2[i], wv = w2[i];
+      double2 rv = r2[i];
+      rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
+      r2[i] = rv;
+      part[0] += (rv.x * rv.x) * wv.x;
+      part[0] += (rv.y * rv.y) * wv.y;
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const size_t i = (size_t)n - 1;
+    x[i] = fma(alpha, d[i], x[i]);
     if (!REFRESH) {
       const double ri = fma(-alpha, q[i], r[i]);
       r[i] = ri;
-      part += (ri * ri) * invD[i];
+      part[0] += (ri * ri) * invD[i];
     }
   }
   if (!REFRESH) {
-    double total;
-    if (block_reduce_to_total<VEC_TB>(part, slots, &sc->ticket_b, &total) && threadIdx.x == 0) *outp = total;
+    double total[1];
+    if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) *outp = total[0];
   }
 }
 
 // beta = rho'/rho; d = invD r + beta d; iteration++ and loop condition            (CGSolver.cpp:176-183, 150)
 __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__restrict__ r, const double *__restrict__ invD,
-                                                      double *__restrict__ d, FbScalars *sc, int it) {
+                                                      double *__restrict__ d, FbScalars *sc, int itArg) {
   if (sc->done) return;
+  const int it = itArg > 0 ? itArg : sc->iters + 1;
   const double rhoNew = sc->rho[it & 1], rhoOld = sc->rho[(it - 1) & 1];
+  const double eps2 = sc->eps2, rho0 = sc->rho0;
+  const int maxIt = sc->max_it;
   const double beta = rhoNew / rhoOld;
-  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB)
-    d[i] = fma(invD[i], r[i], beta * d[i]);
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+  const size_t n2 = (size_t)n >> 1;
+  const double2 *r2 = reinterpret_cast<const double2 *>(r), *w2 = reinterpret_cast<const double2 *>(invD);
+  double2 *d2 = reinterpret_cast<double2 *>(d);
+  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
+    const double2 rv = r2[i], wv = w2[i];
+    double2 dv = d2[i];
+    dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
+    d2[i] = dv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
+  // bookkeeping by the last CTA to finish, so that no CTA of this launch can still be reading sc->iters / done
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(&sc->ticket_b, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    sc->ticket_b = 0u;
     sc->iters = it;
-    // `done` is read at kernel entry by this kernel's other blocks too; a block that sees the new value
-    // early only skips a direction update nobody will use.
-    if (!((rhoNew > sc->eps2 * sc->rho0) && (it + 1 <= sc->max_it))) sc->done = 1;
+    if (!((rhoNew > eps2 * rho0) && (it + 1 <= maxIt))) sc->done = 1;
   }
 }
 
-// Grids are sized to ONE resident wave: sm_count x (blocks of this kernel that fit on an SM), so the
-// grid-stride loops see every SM equally loaded (no partial second wave) and the number of per-CTA
-// partial sums stays small and fixed.
-int vec_grid(const fb_context *c, size_t n) {
-  static int perSM = 0;
-  if (!perSM) {
-    int a = 1, b = 1, d = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_update<false>, VEC_TB, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_direction, VEC_TB, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_cg_init, VEC_TB, 0);
-    perSM = a < b ? a : b;
-    if (d < perSM) perSM = d;
-    if (perSM < 1) perSM = 1;
+// The fused vector kernel of the two-kernel schedule (see the header comment).
+__global__ void __launch_bounds__(VEC_TB) k_fused_update(int n, const double *__restrict__ q, const double *__restrict__ invD,
+                                                         double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
+                                                         FbScalars *sc, double *slots) {
+  if (sc->done) return;
+  const int it = sc->iters + 1;
+  const double rho = sc->rho[(it - 1) & 1];
+  const double alpha = rho / sc->dq;
+  // rho' = (r - alpha q, r - alpha q)_D = rho - 2 alpha (r,q)_D + alpha^2 (q,q)_D
+  const double rhoF = fma(alpha, fma(alpha, sc->qq, -2.0 * sc->rq), rho);
+  const double beta = rhoF / rho;
+  const double eps2 = sc->eps2, rho0 = sc->rho0;
+  const int maxIt = sc->max_it;
+  double part[1] = {0.0};
+  const size_t n2 = (size_t)n >> 1;
+  const double2 *q2 = reinterpret_cast<const double2 *>(q), *w2 = reinterpret_cast<const double2 *>(invD);
+  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r), *d2 = reinterpret_cast<double2 *>(d);
+  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
+    const double2 qv = q2[i], wv = w2[i];
+    double2 dv = d2[i], xv = x2[i], rv = r2[i];
+    xv.x = fma(alpha, dv.x, xv.x); xv.y = fma(alpha, dv.y, xv.y);
+    rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
+    dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
+    x2[i] = xv; r2[i] = rv; d2[i] = dv;
+    part[0] += (rv.x * rv.x) * wv.x;
+    part[0] += (rv.y * rv.y) * wv.y;
   }
-  size_t want = (n + VEC_TB - 1) / VEC_TB;
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const size_t i = (size_t)n - 1;
+    const double di = d[i], wi = invD[i];
+    x[i] = fma(alpha, di, x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    d[i] = fma(wi, ri, beta * di);
+    part[0] += (ri * ri) * wi;
+  }
+  double total[1];
+  if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) {
+    sc->rho[it & 1] = total[0];  // the directly summed rho': next alpha and the stopping rule use this one
+    sc->iters = it;
+    if (!((total[0] > eps2 * rho0) && (it + 1 <= maxIt))) sc->done = 1;
+  }
+}
+
+// ---- launch shapes: ONE resident wave per kernel (sm_count x CTAs/SM from the occupancy API), so grid-stride
+// loops load every SM equally (no partial second wave) and the number of per-CTA partial sums stays small.
+template <typename K>
+int one_wave(const fb_context *c, K kernel, int tb, size_t want) {
+  int perSM = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, tb, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
   size_t cap = (size_t)c->sm_count * (size_t)perSM;
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
 }
 
-template <int G, int MODE>
-void launch_spmv_g(fb_context *c, const double *A, const double *x, double *y, double *outp) {
-  static int perSM = 0;  // resident CTAs of this instantiation per SM (same for every B200)
-  if (!perSM) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv<G, MODE>, SPMV_TB, 0) != cudaSuccess || perSM < 1) perSM = 1;
-  }
-  const size_t groupsPerBlock = SPMV_TB / G;
-  size_t want = ((size_t)c->nV + groupsPerBlock - 1) / groupsPerBlock;
-  size_t cap = (size_t)c->sm_count * (size_t)perSM;
-  if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
-  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  k_spmv<G, MODE><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, c->rhs, c->invD, c->sc,
-                                                           c->partials, outp);
-  c->launches++;
+template <int G>
+void plan_generic(fb_context *c) {
+  const size_t gpb = SPMV_TB / G;
+  const size_t want = ((size_t)c->nV + gpb - 1) / gpb;
+  c->grid_spmv[0] = one_wave(c, k_spmv<G, 0>, SPMV_TB, want);
+  c->grid_spmv[1] = one_wave(c, k_spmv<G, 1>, SPMV_TB, want);
+  c->grid_spmv[2] = one_wave(c, k_spmv<G, 2>, SPMV_TB, want);
+  c->grid_spmv[3] = 0;
 }
 
 template <int MODE>
-void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, double *outp) {
-  if (c->use_tiled) { launch_rows3<MODE, 5>(c, A, x, y, outp); return; }
-  switch (c->spmv_group) {
-    case 8: launch_spmv_g<8, MODE>(c, A, x, y, outp); break;
-    case 32: launch_spmv_g<32, MODE>(c, A, x, y, outp); break;
-    default: launch_spmv_g<16, MODE>(c, A, x, y, outp); break;
+void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, const double *b, double *outp) {
+  const int grid = c->grid_spmv[MODE];
+  if (c->use_rows3) {
+    if (MODE == 3 || c->rows3_minb == 4)
+      k_spmv_rows3<MODE, 4><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp);
+    else
+      k_spmv_rows3<MODE, 5><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp);
+  } else if (MODE != 3) {
+    constexpr int M = MODE == 3 ? 1 : MODE;
+    switch (c->spmv_group) {
+      case 8: k_spmv<8, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp); break;
+      case 32: k_spmv<32, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp); break;
+      default: k_spmv<16, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp); break;
+    }
   }
+  c->launches++;
 }
 
-void enqueue_iteration(fb_context *c, int it) {
-  const int n = c->r;
-  const int vg = vec_grid(c, (size_t)n);
-  double *slotsB = c->partials + FB_MAX_PARTIALS;
+// the reference's literal order, three kernels (+ NCCL in partitioned contexts)
+void enqueue_iteration_kernels(fb_context *c, int it) {
+  const int n = c->r, vg = c->grid_vec;
+  double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
   const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64;
   if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
   double *dqOut = c->dist ? &c->sc->dq_part : &c->sc->dq;
   double *rhoOut = c->dist ? &c->sc->rho_part : &c->sc->rho[it & 1];
-  launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, dqOut);
+  launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, dqOut);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it, rhoOut);
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut);
     c->launches++;
-    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, rhoOut);
+    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
   } else {
-    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsB, it, rhoOut);
+    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut);
     c->launches++;
   }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
@@ -391,75 +498,30 @@ void enqueue_iteration(fb_context *c, int it) {
   if (c->dist) fb_dist_halo_exchange(c, c->dir);
 }
 
-}  // namespace
-
-// Chooses the SpMV variant for this mesh.  Measured on B200, 998,250-tet cube (profiles/r01_spmv_variants.txt):
-// k_spmv<16> 45.0 us in step / 36.8 us isolated; k_spmv_rows3 at 48 registers (5 CTAs/SM) 42.8 / 36.6 us; forcing
-// 40 or 32 registers spills and is slower (54 / 66 us); a shared-memory-tiled variant with x staged per 64-row tile
-// was slower too (60 us: three block-wide barriers per tile, 3 CTAs/SM) and was removed.
-int fb_spmv_plan(fb_context *c) {
-  const char *env = getenv("FEMBRAIN_B200_SPMV");
-  c->use_tiled = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
-  return fb_pcg_plan_persistent(c);
+// two kernels; `it` is only used to place the refresh (the kernels read the iteration from the device counter,
+// so a captured period can be replayed).  Returns the number of kernels enqueued.
+int enqueue_iteration_fused(fb_context *c, int it, bool allowSample) {
+  const int n = c->r, vg = c->grid_vec;
+  double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
+  const bool sample = allowSample && c->profiling && (it % 16 == 1) && c->nprof < 64;
+  if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
+  launch_spmv_mode<3>(c, c->Keff, c->dir, c->Ad, c->res, nullptr);
+  if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
+  if (it % 30 == 0) {
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr);
+    c->launches++;
+    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, &c->sc->rho[0]);  // it is even: rho[it & 1] = rho[0]
+    k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, 0);
+    c->launches++;
+    return 4;
+  }
+  k_fused_update<<<vg, VEC_TB, 0, c->stream>>>(n, c->Ad, c->invD, c->x, c->res, c->dir, c->sc, slotsV);
+  c->launches++;
+  return 2;
 }
 
-int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked) {
-  (void)masked;
-  if (c->nV == 0) return FB_OK;
-  launch_spmv_mode<0>(c, A, x, y, nullptr);
-  FB_CUDA(cudaGetLastError());
-  return FB_OK;
-}
-
-// Solves Keff x = rhs on the constrained DOFs, x0 = 0.  On return c->last_iters holds the
-// reference's return value: +iterations if converged, -iterations otherwise (CGSolver.cpp:189).
-int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
-  const int n = c->r;
+int finish_solve(fb_context *c) {
   cudaStream_t st = c->stream;
-  if (n == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
-  const int vg = vec_grid(c, (size_t)n);
-  if (c->pers_grid > 0 && !c->dist) {
-    // one cooperative kernel runs the whole loop (fb_pcg_persistent.cu)
-    k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, &c->sc->rho[0]);
-    k_cg_begin<<<1, 1, 0, st>>>(c->sc, eps, maxIt);
-    c->launches += 2;
-    FB_TRY(fb_pcg_launch_persistent(c));
-    FB_CUDA(cudaMemcpyAsync(&c->sc_host[2], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
-    FB_CUDA(cudaStreamSynchronize(st));
-    FB_CUDA(cudaGetLastError());
-    const FbScalars &s = c->sc_host[2];
-    const double rhoFinal = s.rho[s.iters & 1];
-    const bool notConverged = rhoFinal > s.eps2 * s.rho0;
-    c->last_iters = s.iters * (notConverged ? -1 : 1);
-    c->last_ratio = (s.rho0 != 0.0) ? rhoFinal / s.rho0 : 0.0;
-    return FB_OK;
-  }
-  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS,
-                                   c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
-  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));  // rho0 is a global sum
-  k_cg_begin<<<1, 1, 0, st>>>(c->sc, eps, maxIt);
-  c->launches += 2;
-  if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));  // ghost entries of d = invD r live on the neighbours
-  // Iterations are enqueued in chunks; the loop condition lives on the device (kernels turn into
-  // no-ops once `done` is set).  The host looks at the flag of chunk k-1 while chunk k runs.
-  const int CH = 32;
-  c->nprof = 0;
-  int it = 1, slot = 0, pending = 0;
-  bool finished = false;
-  while (!finished && it <= maxIt) {
-    const int end = (it + CH - 1 < maxIt) ? it + CH - 1 : maxIt;
-    for (; it <= end; it++) enqueue_iteration(c, it);
-    FB_CUDA(cudaMemcpyAsync(&c->sc_host[slot], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
-    FB_CUDA(cudaEventRecord(c->evChunk[slot], st));
-    pending++;
-    if (pending == 2) {
-      const int prev = slot ^ 1;
-      FB_CUDA(cudaEventSynchronize(c->evChunk[prev]));
-      if (c->sc_host[prev].done) finished = true;
-      pending--;
-    }
-    slot ^= 1;
-  }
   FB_CUDA(cudaMemcpyAsync(&c->sc_host[2], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   FB_CUDA(cudaGetLastError());
@@ -476,36 +538,179 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
   return FB_OK;
 }
 
-int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
-  // time `repeats` full CG iterations on the current system without the stopping rule
-  const int n = c->r;
-  if (n == 0 || repeats <= 0) { *sec = 0.0; return FB_OK; }
+int start_solve(fb_context *c, double eps, int maxIt) {
   cudaStream_t st = c->stream;
-  const int vg = vec_grid(c, (size_t)n);
+  k_cg_init<<<c->grid_vec, VEC_TB, 0, st>>>(c->r, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + 3 * (size_t)FB_MAX_PARTIALS,
+                                            c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
+  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));  // rho0 is a global sum
+  k_cg_begin<<<1, 1, 0, st>>>(c->sc, eps, maxIt);
+  c->launches += 2;
+  if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));  // ghost entries of d = invD r live on the neighbours
+  return FB_OK;
+}
+
+// one 30-iteration period of the fused schedule as a CUDA graph (built lazily, once per context)
+int ensure_period_graph(fb_context *c) {
+  if (c->graph_exec || c->graph_failed) return FB_OK;
+  cudaStream_t st = c->stream;
+  cudaGraph_t graph = nullptr;
+  const long long before = c->launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_failed = 1; return FB_OK; }
+  int kernels = 0;
+  for (int k = 1; k <= 30; k++) kernels += enqueue_iteration_fused(c, k, false);
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  c->launches = before;  // captured, not launched
+  if (e != cudaSuccess || !graph) { cudaGetLastError(); c->graph_failed = 1; return FB_OK; }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { cudaGetLastError(); c->graph_failed = 1; return FB_OK; }
+  c->graph_exec = exec;
+  c->graph_kernels = kernels;
+  return FB_OK;
+}
+
+}  // namespace
+
+// Chooses the SpMV variant and the launch shapes for this mesh.  Measured on B200, 998,250-tet cube
+// (profiles/r01_spmv_variants.txt): k_spmv<16> 45.0 us in step / 36.8 us isolated; k_spmv_rows3 at 48 registers
+// (5 CTAs/SM) 42.8 / 36.6 us; forcing 40 or 32 registers spills and is slower (54 / 66 us); a shared-memory-tiled
+// variant with x staged per 64-row tile was slower too (60 us: three block-wide barriers per tile, 3 CTAs/SM) and
+// was removed.
+int fb_spmv_plan(fb_context *c) {
+  const char *env = getenv("FEMBRAIN_B200_SPMV");
+  c->use_rows3 = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
+  const size_t n = (size_t)c->r;
+  int gv = one_wave(c, k_fused_update, VEC_TB, (n + VEC_TB - 1) / VEC_TB);
+  gv = min(gv, one_wave(c, k_update<false>, VEC_TB, (n + VEC_TB - 1) / VEC_TB));
+  gv = min(gv, one_wave(c, k_direction, VEC_TB, (n + VEC_TB - 1) / VEC_TB));
+  gv = min(gv, one_wave(c, k_cg_init, VEC_TB, (n + VEC_TB - 1) / VEC_TB));
+  c->grid_vec = gv;
+  if (c->use_rows3) {
+    const size_t gpb = SPMV_TB / TILE_G;
+    const size_t want = ((size_t)c->nV + gpb - 1) / gpb;
+    const char *mb = getenv("FEMBRAIN_B200_MINB");
+    c->rows3_minb = (mb && atoi(mb) == 5) ? 5 : 4;  // 4 CTAs/SM (56 registers, no spills) measured best
+    if (c->rows3_minb == 4) {
+      c->grid_spmv[0] = one_wave(c, k_spmv_rows3<0, 4>, SPMV_TB, want);
+      c->grid_spmv[1] = one_wave(c, k_spmv_rows3<1, 4>, SPMV_TB, want);
+      c->grid_spmv[2] = one_wave(c, k_spmv_rows3<2, 4>, SPMV_TB, want);
+    } else {
+      c->grid_spmv[0] = one_wave(c, k_spmv_rows3<0, 5>, SPMV_TB, want);
+      c->grid_spmv[1] = one_wave(c, k_spmv_rows3<1, 5>, SPMV_TB, want);
+      c->grid_spmv[2] = one_wave(c, k_spmv_rows3<2, 5>, SPMV_TB, want);
+    }
+    c->grid_spmv[3] = one_wave(c, k_spmv_rows3<3, 4>, SPMV_TB, want);
+  } else if (c->spmv_group == 8) {
+    plan_generic<8>(c);
+  } else if (c->spmv_group == 32) {
+    plan_generic<32>(c);
+  } else {
+    plan_generic<16>(c);
+  }
+  const char *mode = getenv("FEMBRAIN_B200_PCG");
+  // Default: the reference's literal order (three kernels).  Measured on B200 after the row-owner prefetch
+  // (profiles/r01_pcg_schedules.txt): kernels vs fused, us per iteration in step: 26.7 / 26.3 at 200k tets, 56.4 / 56.0
+  // at 1M, 497.6 / 525.8 at 10M — the extra reads and the three-sum epilogue of k_spmv_rows3<3> cost what the saved
+  // launch gains, and graph replay changes nothing (the gaps are device-side dependencies, not host launch cost).
+  c->pcg_fused = c->use_rows3 && mode && (!strcmp(mode, "fused") || !strcmp(mode, "fused_nograph"));
+  c->pcg_graph = c->pcg_fused && !(mode && !strcmp(mode, "fused_nograph"));
+  return fb_pcg_plan_persistent(c);
+}
+
+int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked) {
+  (void)masked;
+  if (c->nV == 0) return FB_OK;
+  launch_spmv_mode<0>(c, A, x, y, c->rhs, nullptr);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+void fb_pcg_release(fb_context *c) {
+  if (c->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c->graph_exec); c->graph_exec = nullptr; }
+}
+
+// Solves Keff x = rhs on the constrained DOFs, x0 = 0.  On return c->last_iters holds the
+// reference's return value: +iterations if converged, -iterations otherwise (CGSolver.cpp:189).
+int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
+  cudaStream_t st = c->stream;
+  if (c->r == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
+  c->nprof = 0;
+  FB_TRY(start_solve(c, eps, maxIt));
+  if (c->pers_grid > 0 && !c->dist) {  // opt-in: one cooperative kernel runs the whole loop (fb_pcg_persistent.cu)
+    FB_TRY(fb_pcg_launch_persistent(c));
+    return finish_solve(c);
+  }
+  const bool fused = c->pcg_fused && !c->dist;
+  const bool useGraph = fused && c->pcg_graph && !c->profiling;
+  if (useGraph) FB_TRY(ensure_period_graph(c));
+  // Iterations are enqueued in chunks of one refresh period; the loop condition lives on the device (kernels turn
+  // into no-ops once `done` is set).  The host looks at the flag of chunk k-1 while chunk k runs.
+  const int CH = 30;
+  int it = 1, slot = 0, pending = 0;
+  bool finished = false;
+  while (!finished && it <= maxIt) {
+    const int end = (it + CH - 1 < maxIt) ? it + CH - 1 : maxIt;
+    if (useGraph && c->graph_exec && end - it + 1 == CH) {
+      FB_CUDA(cudaGraphLaunch((cudaGraphExec_t)c->graph_exec, st));
+      c->launches += c->graph_kernels;
+      it += CH;
+    } else {
+      for (; it <= end; it++) {
+        if (fused) enqueue_iteration_fused(c, it, true);
+        else enqueue_iteration_kernels(c, it);
+      }
+    }
+    FB_CUDA(cudaMemcpyAsync(&c->sc_host[slot], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaEventRecord(c->evChunk[slot], st));
+    pending++;
+    if (pending == 2) {
+      const int prev = slot ^ 1;
+      FB_CUDA(cudaEventSynchronize(c->evChunk[prev]));
+      if (c->sc_host[prev].done) finished = true;
+      pending--;
+    }
+    slot ^= 1;
+  }
+  return finish_solve(c);
+}
+
+int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
+  // time `repeats` full CG iterations on the current system with the stopping rule disabled (eps = 0)
+  if (c->r == 0 || repeats <= 0) { *sec = 0.0; return FB_OK; }
+  cudaStream_t st = c->stream;
+  const int warm = 30;
+  repeats = ((repeats + 29) / 30) * 30;  // whole refresh periods
+  FB_TRY(start_solve(c, 0.0, (c->pers_grid > 0 && !c->dist) ? repeats : (1 << 30)));
+  const bool fused = c->pcg_fused && !c->dist;
   if (c->pers_grid > 0 && !c->dist) {
-    k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS, &c->sc->rho[0]);
-    k_cg_begin<<<1, 1, 0, st>>>(c->sc, 0.0, repeats);
-    c->launches += 2;
     FB_CUDA(cudaEventRecord(c->ev[3], st));
     FB_TRY(fb_pcg_launch_persistent(c));
-    FB_CUDA(cudaEventRecord(c->ev[7], st));
-    FB_CUDA(cudaStreamSynchronize(st));
-    float ms = 0;
-    FB_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]));
-    *sec = 1e-3 * ms / repeats;
-    return FB_OK;
+  } else {
+    const bool useGraph = fused && c->pcg_graph;
+    if (useGraph) FB_TRY(ensure_period_graph(c));
+    int it = 1;
+    auto run = [&](int count) {
+      const int end = it + count - 1;
+      while (it <= end) {
+        if (useGraph && c->graph_exec && (it - 1) % 30 == 0 && end - it + 1 >= 30) {
+          cudaGraphLaunch((cudaGraphExec_t)c->graph_exec, st);
+          c->launches += c->graph_kernels;
+          it += 30;
+        } else {
+          if (fused) enqueue_iteration_fused(c, it, false);
+          else enqueue_iteration_kernels(c, it);
+          it++;
+        }
+      }
+    };
+    run(warm);
+    FB_CUDA(cudaEventRecord(c->ev[3], st));
+    run(repeats);
   }
-  k_cg_init<<<vg, VEC_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + FB_MAX_PARTIALS,
-                                   c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
-  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));
-  k_cg_begin<<<1, 1, 0, st>>>(c->sc, 0.0, 1 << 30);
-  c->launches += 2;
-  if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));
-  for (int it = 1; it <= 3; it++) enqueue_iteration(c, it);
-  FB_CUDA(cudaEventRecord(c->ev[3], st));
-  for (int it = 4; it < 4 + repeats; it++) enqueue_iteration(c, it);
   FB_CUDA(cudaEventRecord(c->ev[7], st));
   FB_CUDA(cudaStreamSynchronize(st));
+  FB_CUDA(cudaGetLastError());
   float ms = 0;
   FB_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]));
   *sec = 1e-3 * ms / repeats;

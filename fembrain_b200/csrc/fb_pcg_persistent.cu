@@ -212,8 +212,12 @@ __global__ void k_plan_cta_rows(int nV, int nB, int grid, const int *__restrict_
 
 int fb_pcg_plan_persistent(fb_context *c) {
   c->pers_grid = 0;
+  // Opt-in (FEMBRAIN_B200_PCG=persistent).  Measured on B200 (profiles/r01_pcg_persistent_vs_kernels.txt): correct, but
+  // SLOWER than the kernels path — 79.5 vs 55.3 us/iteration at 1M tets, 797 vs 526 us at 10M, 29.1 vs 26.5 us at 200k:
+  // cooperative-groups grid.sync() costs about as much as a kernel boundary here and the SpMV phase runs at 4
+  // CTAs/SM (57 registers) behind a barrier that waits for the slowest CTA.
   const char *env = getenv("FEMBRAIN_B200_PCG");
-  if (env && !strcmp(env, "kernels")) return FB_OK;
+  if (!(env && !strcmp(env, "persistent"))) return FB_OK;
   if (c->nV == 0 || c->nB == 0) return FB_OK;
   int coop = 0;
   if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess || !coop) { cudaGetLastError(); return FB_OK; }
@@ -247,7 +251,7 @@ int fb_pcg_launch_persistent(fb_context *c) {
   a.b = c->rhs; a.invD = c->invD;
   a.x = c->x; a.r = c->res; a.d = c->dir; a.q = c->Ad;
   a.sc = c->sc;
-  a.slotsA = c->partials; a.slotsB = c->partials + FB_MAX_PARTIALS;
+  a.slotsA = c->partials; a.slotsB = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
   a.prof = c->pers_prof;
   a.profiling = c->profiling;
   void *args[] = {&a};

@@ -68,6 +68,7 @@ __global__ void k_fill_contrib(size_t n, const unsigned long long *__restrict__ 
 
 __global__ void k_set_int(int *p, int v) { *p = v; }
 
+
 }  // namespace
 
 int fb_build_topology(fb_context *c) {

@@ -201,7 +201,7 @@ def run_reference(args):
         "assembly_mtets_per_s": res["assembly_mtets_per_s"], "cg_iterations_per_step_assumed": iters,
         "seconds_per_cg_iteration": res["seconds_per_cg_iteration"], "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.emit(line)
     return 0
 
 
@@ -346,7 +346,7 @@ def run_ours(args):
                                         "seconds_per_cg_iteration": cb["seconds_per_cg_iteration"]}
             except Exception as e:  # the checker is optional plumbing for the bench
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
-        print(json.dumps(line))
+        args.emit(line)
     sim.close()
     if world > 1:
         dist.destroy_process_group()
@@ -354,6 +354,24 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything libraries print there meanwhile (e.g. NCCL's version banner)
+    # is sent to stderr, and the saved descriptor is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _main(saved_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+
+
+def emit(saved_stdout, line):
+    sys.stdout.flush()
+    os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+
+
+def _main(saved_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -367,6 +385,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: timing rules ask for >= 3 warm-up steps", file=sys.stderr)
+    args.emit = lambda line: emit(saved_stdout, line)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 

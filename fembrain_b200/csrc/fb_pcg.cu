@@ -99,6 +99,47 @@ __device__ __forceinline__ bool block_reduce_to_total(double (&v)[N], double *sl
   return true;
 }
 
+// Deferred variant: the per-CTA sum goes to its slot and the CONSUMER kernel adds the slots (cta_sum_slots), every CTA
+// redundantly and in the same fixed order.  This takes the ticket atomics and the serial last-CTA pass off the tail of
+// the producer (the SpMV) — the slots are L2-resident and read in parallel by all CTAs of the next kernel.
+template <int TB>
+__device__ __forceinline__ void block_reduce_to_slot(double v, double *slots) {
+  __shared__ double wsum1[TB / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) wsum1[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double s = (lane < TB / 32) ? wsum1[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) slots[blockIdx.x] = s;
+  }
+}
+
+// same association order as the last-CTA pass of block_reduce_to_total: thread t adds slots t, t+TB, ..., then the tree
+template <int TB>
+__device__ __forceinline__ double cta_sum_slots(const double *__restrict__ slots, int n) {
+  __shared__ double wsum2[TB / 32];
+  __shared__ double bcast;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += TB) s += __ldcg(slots + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) wsum2[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double z = (lane < TB / 32) ? wsum2[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_down_sync(0xffffffffu, z, o);
+    if (lane == 0) bcast = z;
+  }
+  __syncthreads();
+  return bcast;
+}
+
 // what the lanes holding a finished row do with it, per MODE:
 // 0: y = A x                                   generic product (no mask, no sums)
 // 1: y = mask(A x); sum x.y                    q = A d with d.q                 (kernels schedule)
@@ -131,6 +172,10 @@ __device__ __forceinline__ void finish_row(double s, size_t row, const double *_
 template <int MODE>
 __device__ __forceinline__ void finish_kernel(double (&part)[3], FbScalars *sc, double *slots, double *outp) {
   if (MODE == 1 || MODE == 2) {
+    if (outp == nullptr) {  // deferred: the consumer kernel adds the slots
+      block_reduce_to_slot<SPMV_TB>(part[0], slots);
+      return;
+    }
     double p1[1] = {part[0]}, t1[1];
     if (block_reduce_to_total<SPMV_TB, 1>(p1, slots, &sc->ticket_a, t1) && threadIdx.x == 0) *outp = t1[0];
   } else if (MODE == 3) {
@@ -315,10 +360,12 @@ __global__ void k_cg_begin(FbScalars *sc, double eps, int maxIt) {
 template <bool REFRESH>
 __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restrict__ d, const double *__restrict__ q,
                                                    const double *__restrict__ invD, double *__restrict__ x,
-                                                   double *__restrict__ r, FbScalars *sc, double *slots, int itArg, double *outp) {
+                                                   double *__restrict__ r, FbScalars *sc, double *slots, int itArg, double *outp,
+                                                   const double *__restrict__ dqSlots, int nDqSlots) {
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
-  const double alpha = sc->rho[(it - 1) & 1] / sc->dq;
+  const double dq = dqSlots ? cta_sum_slots<VEC_TB>(dqSlots, nDqSlots) : sc->dq;
+  const double alpha = sc->rho[(it - 1) & 1] / dq;
   double part[1] = {0.0};
   // two doubles per thread per trip (128-bit loads/stores); element n-1 of an odd-length vector is handled last
   const size_t n2 = (size_t)n >> 1;
@@ -349,17 +396,23 @@ __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restri
     }
   }
   if (!REFRESH) {
-    double total[1];
-    if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) *outp = total[0];
+    if (outp == nullptr) {
+      block_reduce_to_slot<VEC_TB>(part[0], slots);
+    } else {
+      double total[1];
+      if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) *outp = total[0];
+    }
   }
 }
 
 // beta = rho'/rho; d = invD r + beta d; iteration++ and loop condition            (CGSolver.cpp:176-183, 150)
 __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__restrict__ r, const double *__restrict__ invD,
-                                                      double *__restrict__ d, FbScalars *sc, int itArg) {
+                                                      double *__restrict__ d, FbScalars *sc, int itArg,
+                                                      const double *__restrict__ rhoSlots, int nRhoSlots) {
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
-  const double rhoNew = sc->rho[it & 1], rhoOld = sc->rho[(it - 1) & 1];
+  const double rhoNew = rhoSlots ? cta_sum_slots<VEC_TB>(rhoSlots, nRhoSlots) : sc->rho[it & 1];
+  const double rhoOld = sc->rho[(it - 1) & 1];
   const double eps2 = sc->eps2, rho0 = sc->rho0;
   const int maxIt = sc->max_it;
   const double beta = rhoNew / rhoOld;
@@ -383,6 +436,7 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
   __syncthreads();
   if (last && threadIdx.x == 0) {
     sc->ticket_b = 0u;
+    if (rhoSlots) sc->rho[it & 1] = rhoNew;
     sc->iters = it;
     if (!((rhoNew > eps2 * rho0) && (it + 1 <= maxIt))) sc->done = 1;
   }
@@ -479,21 +533,29 @@ void enqueue_iteration_kernels(fb_context *c, int it) {
   double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
   const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64;
   if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
-  double *dqOut = c->dist ? &c->sc->dq_part : &c->sc->dq;
-  double *rhoOut = c->dist ? &c->sc->rho_part : &c->sc->rho[it & 1];
+  // one GPU: per-CTA sums stay in their slots and the next kernel adds them (no ticket / last-CTA pass on the SpMV tail);
+  // partitioned: the sums must become one scalar for ncclAllReduce, so the last-CTA pass is kept
+  const bool defer = !c->dist;
+  double *dqOut = c->dist ? &c->sc->dq_part : nullptr;
+  double *rhoOut = c->dist ? &c->sc->rho_part : nullptr;
+  const double *dqSlots = defer ? c->partials : nullptr;
+  const double *rhoSlots = nullptr;
+  int nRhoSlots = 0;
   launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, dqOut);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut);
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1]);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
+    if (defer) { rhoSlots = c->partials; nRhoSlots = c->grid_spmv[2]; }
   } else {
-    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut);
+    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1]);
     c->launches++;
+    if (defer) { rhoSlots = slotsV; nRhoSlots = vg; }
   }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
-  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it);
+  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots);
   c->launches++;
   if (c->dist) fb_dist_halo_exchange(c, c->dir);
 }
@@ -508,10 +570,10 @@ int enqueue_iteration_fused(fb_context *c, int it, bool allowSample) {
   launch_spmv_mode<3>(c, c->Keff, c->dir, c->Ad, c->res, nullptr);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr);
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr, nullptr, 0);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, &c->sc->rho[0]);  // it is even: rho[it & 1] = rho[0]
-    k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, 0);
+    k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, 0, nullptr, 0);
     c->launches++;
     return 4;
   }

@@ -114,6 +114,7 @@ def load_library():
         "fb_comm_unique_id": (ci, [vp]),
         "fb_create_partitioned": (ci, [pp, ci, vp, ci, vp, ci, vp, prm, ci, ci, vp]),
         "fb_partition_range": (ci, [vp, C.POINTER(ci), C.POINTER(ci)]),
+        "fb_partition_peer_memory": (ci, [vp]),
         "fb_plan_partition": (ci, [ci, ci, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -220,6 +221,10 @@ class Simulation:
         if st != FB_OK:
             detail = self._lib.fb_last_error_string().decode() or self._lib.fb_status_string(st).decode()
             raise FemBrainError(st, where, detail)
+
+    @property
+    def peer_memory(self):
+        return bool(self._lib.fb_partition_peer_memory(self._h))
 
     def partition_range(self):
         b, e = C.c_int(0), C.c_int(0)

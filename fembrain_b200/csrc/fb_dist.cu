@@ -22,9 +22,13 @@
 #include <vector>
 
 #include "fb_internal.h"
+#include "fb_pcg_common.cuh"
+
+#define FB_MAX_NBR 8
 
 struct FbDist {
-  ncclComm_t comm;
+  ncclComm_t ncomm;
+  ncclComm_t comm_nccl() const { return ncomm; }
   int rank, world;
   int nV_global, nT_global;
   int vbeg, vend;            // owned global vertex range
@@ -35,6 +39,16 @@ struct FbDist {
   int *sendIdx, *recvIdx;    // device: local vertex ids, concatenated per neighbour
   double *sendBuf, *recvBuf; // device: 3 doubles per vertex
   double *hostStage;         // pinned, local r doubles
+  // peer-memory exchange (CUDA IPC): see fb_pcg_common.cuh
+  int p2p;
+  double *comm;                      // this rank's comm block (device)
+  double *peerComm[FB_MAX_RANKS];    // every rank's comm block mapped here ([rank] = comm)
+  double *peerDir[FB_MAX_NBR];       // neighbours' search-direction vectors mapped here
+  int *remoteIdx;                    // device: neighbour-local vertex index of every send entry
+  unsigned int *pushTicket;          // device
+  unsigned long long solveCount;
+  void *opened[FB_MAX_RANKS + FB_MAX_NBR];
+  int nOpened;
 };
 
 #define FB_NCCL(call)                                                                        \
@@ -65,6 +79,38 @@ __global__ void k_mask_ghost(int nV, const unsigned char *__restrict__ ownedV, c
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 3 * nV) return;
   rowmask[t] = (fixed[t] || !ownedV[t / 3]) ? 1 : 0;
+}
+
+struct HaloPushArgs {
+  int nNbr;
+  int off[FB_MAX_NBR + 1];
+  int nbrRank[FB_MAX_NBR];
+  double *peerVec[FB_MAX_NBR];
+};
+
+// Owned boundary values of `vec` stored straight into the neighbours' ghost entries over NVLink, then (last CTA) the
+// halo flag of this rank raised in each neighbour's comm block.
+__global__ void k_halo_push(HaloPushArgs h, FbPeerArgs pa, const int *__restrict__ sendIdx, const int *__restrict__ remoteIdx,
+                            const double *__restrict__ vec, FbScalars *sc, unsigned int *ticket) {
+  if (sc->done) return;
+  const int total = 3 * h.off[h.nNbr];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int i = t / 3, k = t - 3 * i;
+    int j = 0;
+    while (j + 1 < h.nNbr && i >= h.off[j + 1]) j++;
+    h.peerVec[j][3 * (size_t)remoteIdx[i] + k] = vec[3 * (size_t)sendIdx[i] + k];
+  }
+  __threadfence_system();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *ticket = 0u;
+    __threadfence_system();
+    for (int j = 0; j < h.nNbr; j++)
+      ((volatile unsigned long long *)pa.comm[h.nbrRank[j]])[FB_COMM_FLAG(FB_COMM_HALO, pa.rank)] = pa.epoch;
+  }
 }
 
 // ---- the partition plan: pure host integer work, identical on every rank ------------------------------------
@@ -149,8 +195,8 @@ int fb_dist_halo_exchange(fb_context *c, double *vec) {
   FB_NCCL(ncclGroupStart());
   for (int i = 0; i < d->nNbr; i++) {
     const int ns = d->sendOff[i + 1] - d->sendOff[i], nr = d->recvOff[i + 1] - d->recvOff[i];
-    if (ns) FB_NCCL(ncclSend(d->sendBuf + 3 * (size_t)d->sendOff[i], 3 * (size_t)ns, ncclDouble, d->nbrRank[i], d->comm, c->stream));
-    if (nr) FB_NCCL(ncclRecv(d->recvBuf + 3 * (size_t)d->recvOff[i], 3 * (size_t)nr, ncclDouble, d->nbrRank[i], d->comm, c->stream));
+    if (ns) FB_NCCL(ncclSend(d->sendBuf + 3 * (size_t)d->sendOff[i], 3 * (size_t)ns, ncclDouble, d->nbrRank[i], d->ncomm, c->stream));
+    if (nr) FB_NCCL(ncclRecv(d->recvBuf + 3 * (size_t)d->recvOff[i], 3 * (size_t)nr, ncclDouble, d->nbrRank[i], d->ncomm, c->stream));
   }
   FB_NCCL(ncclGroupEnd());
   if (nR) { k_unpack<<<(3 * nR + 255) / 256, 256, 0, c->stream>>>(nR, d->recvIdx, d->recvBuf, vec); c->launches++; }
@@ -164,7 +210,129 @@ int fb_dist_allreduce_scalar(fb_context *c, const double *dev_part, double *dev_
     FB_CUDA(cudaMemcpyAsync(dev_total, dev_part, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return FB_OK;
   }
-  FB_NCCL(ncclAllReduce(dev_part, dev_total, 1, ncclDouble, ncclSum, d->comm, c->stream));
+  FB_NCCL(ncclAllReduce(dev_part, dev_total, 1, ncclDouble, ncclSum, d->ncomm, c->stream));
+  return FB_OK;
+}
+
+int fb_dist_p2p(const fb_context *c) { return (c && c->dist) ? c->dist->p2p : 0; }
+
+void fb_dist_peer_args(fb_context *c, FbPeerArgs *pa) {
+  memset(pa, 0, sizeof(*pa));
+  FbDist *d = c->dist;
+  if (!d || !d->p2p) return;
+  pa->enabled = 1;
+  pa->rank = d->rank;
+  pa->world = d->world;
+  for (int p = 0; p < d->world; p++) pa->comm[p] = d->peerComm[p];
+}
+
+unsigned long long fb_dist_epoch(fb_context *c, int it, int family) {
+  return (c->dist->solveCount << 32) | (unsigned long long)(3 * (long long)it + family + 1);
+}
+
+void fb_dist_next_solve(fb_context *c) {
+  if (c->dist) c->dist->solveCount++;
+}
+
+unsigned int fb_dist_halo_mask(const fb_context *c) {
+  unsigned int m = 0;
+  for (int i = 0; i < c->dist->nNbr; i++) m |= 1u << c->dist->nbrRank[i];
+  return m;
+}
+
+int fb_dist_halo_push(fb_context *c, const double *vec, unsigned long long epoch) {
+  FbDist *d = c->dist;
+  if (!d || !d->p2p || d->nNbr == 0) return FB_OK;
+  HaloPushArgs h;
+  memset(&h, 0, sizeof(h));
+  h.nNbr = d->nNbr;
+  for (int i = 0; i <= d->nNbr; i++) h.off[i] = d->sendOff[i];
+  for (int i = 0; i < d->nNbr; i++) { h.nbrRank[i] = d->nbrRank[i]; h.peerVec[i] = d->peerDir[i]; }
+  FbPeerArgs pa;
+  fb_dist_peer_args(c, &pa);
+  pa.epoch = epoch;
+  const int total = 3 * d->sendOff[d->nNbr];
+  int grid = (total + 255) / 256;
+  if (grid > 2 * c->sm_count) grid = 2 * c->sm_count;
+  if (grid < 1) grid = 1;
+  k_halo_push<<<grid, 256, 0, c->stream>>>(h, pa, d->sendIdx, d->remoteIdx, vec, c->sc, d->pushTicket);
+  c->launches++;
+  return FB_OK;
+}
+
+// Peer mappings for the exchange above: comm blocks of all ranks, `dir` vectors of the neighbours, and for every send
+// entry the neighbour's local index of that vertex (the neighbour's recv list, which mirrors this rank's send list).
+// Any failure leaves p2p = 0 and the context on the NCCL path.
+static int setup_p2p(fb_context *c) {
+  FbDist *d = c->dist;
+  d->p2p = 0;
+  const char *env = getenv("FEMBRAIN_B200_P2P");
+  if (env && atoi(env) == 0) return FB_OK;
+  if (d->world < 2) return FB_OK;
+  cudaStream_t st = c->stream;
+  {  // every rank takes part in this vote, so no rank can skip the collectives below on its own
+    int eligible = (d->world <= FB_MAX_RANKS && d->nNbr <= FB_MAX_NBR && c->use_rows3) ? 1 : 0, all = 0;
+    int *flag0 = nullptr;
+    FB_CUDA(cudaMalloc(&flag0, sizeof(int)));
+    FB_CUDA(cudaMemcpyAsync(flag0, &eligible, sizeof(int), cudaMemcpyHostToDevice, st));
+    ncclResult_t r0 = ncclAllReduce(flag0, flag0, 1, ncclInt, ncclMin, d->comm_nccl(), st);
+    cudaMemcpyAsync(&all, flag0, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(flag0);
+    if (r0 != ncclSuccess || !all) return FB_OK;
+  }
+  FB_TRY(fb_dev_alloc(c, &d->comm, (size_t)FB_COMM_WORDS));
+  FB_TRY(fb_dev_alloc(c, &d->pushTicket, 1));
+  FB_TRY(fb_dev_alloc(c, &d->remoteIdx, (size_t)d->sendOff[d->nNbr]));
+  FB_CUDA(cudaMemsetAsync(d->comm, 0, sizeof(double) * FB_COMM_WORDS, st));
+  FB_CUDA(cudaMemsetAsync(d->pushTicket, 0, sizeof(unsigned int), st));
+  // 1. IPC handles of (comm, dir) of every rank
+  struct Handles { cudaIpcMemHandle_t comm, dir; };
+  Handles mine;
+  int ok = (cudaIpcGetMemHandle(&mine.comm, d->comm) == cudaSuccess) && (cudaIpcGetMemHandle(&mine.dir, c->dir) == cudaSuccess);
+  if (!ok) cudaGetLastError();
+  char *devH = nullptr;
+  FB_CUDA(cudaMalloc(&devH, sizeof(Handles) * (size_t)(d->world + 1)));
+  FB_CUDA(cudaMemcpyAsync(devH + sizeof(Handles) * (size_t)d->world, &mine, sizeof(Handles), cudaMemcpyHostToDevice, st));
+  ncclResult_t nr = ncclAllGather(devH + sizeof(Handles) * (size_t)d->world, devH, sizeof(Handles), ncclChar, d->comm_nccl(), st);
+  std::vector<Handles> all((size_t)d->world);
+  if (nr == ncclSuccess) cudaMemcpyAsync(all.data(), devH, sizeof(Handles) * (size_t)d->world, cudaMemcpyDeviceToHost, st);
+  // 2. the neighbours' local indices of my send vertices = their recv lists for me
+  if (nr == ncclSuccess) nr = ncclGroupStart();
+  for (int i = 0; i < d->nNbr && nr == ncclSuccess; i++) {
+    const int ns = d->sendOff[i + 1] - d->sendOff[i], nrv = d->recvOff[i + 1] - d->recvOff[i];
+    if (nrv) nr = ncclSend(d->recvIdx + d->recvOff[i], (size_t)nrv, ncclInt, d->nbrRank[i], d->comm_nccl(), st);
+    if (ns && nr == ncclSuccess) nr = ncclRecv(d->remoteIdx + d->sendOff[i], (size_t)ns, ncclInt, d->nbrRank[i], d->comm_nccl(), st);
+  }
+  if (nr == ncclSuccess) nr = ncclGroupEnd();
+  cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(devH);
+  if (nr != ncclSuccess || ce != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  // 3. map the peers
+  d->nOpened = 0;
+  for (int p = 0; p < d->world && ok; p++) {
+    if (p == d->rank) { d->peerComm[p] = d->comm; continue; }
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[p].comm, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    d->peerComm[p] = (double *)ptr;
+    d->opened[d->nOpened++] = ptr;
+  }
+  for (int i = 0; i < d->nNbr && ok; i++) {
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[d->nbrRank[i]].dir, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    d->peerDir[i] = (double *)ptr;
+    d->opened[d->nOpened++] = ptr;
+  }
+  // 4. all ranks must agree (a rank that failed would otherwise wait for peers that never publish)
+  int *flag = nullptr;
+  FB_CUDA(cudaMalloc(&flag, sizeof(int)));
+  FB_CUDA(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (ncclAllReduce(flag, flag, 1, ncclInt, ncclMin, d->comm_nccl(), st) != ncclSuccess) ok = 0;
+  int agreed = 0;
+  cudaMemcpyAsync(&agreed, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(flag);
+  d->p2p = ok && agreed;
   return FB_OK;
 }
 
@@ -222,7 +390,11 @@ void fb_dist_destroy(fb_context *c) {
   if (d->recvBuf) cudaFree(d->recvBuf);
   if (d->hostStage) cudaFreeHost(d->hostStage);
   if (c->rowmask && c->rowmask != c->fixed) { cudaFree(c->rowmask); c->rowmask = nullptr; }
-  if (d->comm) ncclCommDestroy(d->comm);
+  for (int i = 0; i < d->nOpened; i++) cudaIpcCloseMemHandle(d->opened[i]);
+  if (d->comm) cudaFree(d->comm);
+  if (d->pushTicket) cudaFree(d->pushTicket);
+  if (d->remoteIdx) cudaFree(d->remoteIdx);
+  if (d->ncomm) ncclCommDestroy(d->ncomm);
   delete d;
   c->dist = nullptr;
 }
@@ -315,7 +487,8 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
   fb_context *c = nullptr;
   FB_TRY(fb_create_local(&c, nLV, lx.data(), nLT, lt.data(), (int)cd.size(), cd.data(), nullptr, nullptr, nullptr, prm));
   FbDist *d = new FbDist();
-  d->comm = nullptr; d->sendIdx = d->recvIdx = nullptr; d->sendBuf = d->recvBuf = nullptr; d->hostStage = nullptr;
+  d->ncomm = nullptr; d->sendIdx = d->recvIdx = nullptr; d->sendBuf = d->recvBuf = nullptr; d->hostStage = nullptr;
+  d->p2p = 0; d->comm = nullptr; d->remoteIdx = nullptr; d->pushTicket = nullptr; d->solveCount = 0; d->nOpened = 0;
   d->rank = rank; d->world = world; d->nV_global = nV; d->nT_global = nT;
   d->vbeg = pl.bounds[rank]; d->vend = pl.bounds[rank + 1];
   d->l2g = pl.l2g;
@@ -351,19 +524,22 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
   if (world > 1) {
     ncclUniqueId id;
     memcpy(&id, comm_id128, sizeof(id));
-    ncclResult_t r = ncclCommInitRank(&d->comm, world, id, rank);
+    ncclResult_t r = ncclCommInitRank(&d->ncomm, world, id, rank);
     if (r != ncclSuccess) {
       fb_set_error("ncclCommInitRank -> %s", ncclGetErrorString(r));
-      d->comm = nullptr;
+      d->ncomm = nullptr;
       fb_destroy(c);
       return FB_ERR_COMM;
     }
+    DCHK(setup_p2p(c));
   }
 #undef DCHK
 #undef DCUDA
   *out = c;
   return FB_OK;
 }
+
+int fb_partition_peer_memory(const fb_context *c) { return fb_dist_p2p(c); }
 
 int fb_partition_range(const fb_context *c, int *b, int *e) {
   if (!c) return FB_ERR_INVALID_ARGUMENT;

@@ -41,6 +41,8 @@ struct FbScalars {
   // partitioned contexts: this rank's partial sums; ncclAllReduce(part -> dq / rho[it&1]).  Kept apart from the
   // reduced values so that the all-reduces that still run after `done` cannot compound stale numbers.
   double dq_part, rho_part;
+  int comm_error;   // a bounded peer wait ran out (partitioned contexts, peer-memory exchange)
+  int pad2;
 };
 
 #define FB_MAX_PARTIALS 4096
@@ -175,6 +177,14 @@ int fb_dist_refresh_rowmask(fb_context *c);  // rowmask = fixed + ghost rows (af
 int fb_dist_upload_global(fb_context *c, const double *global_host, double *local_dev);
 int fb_dist_download_owned(fb_context *c, const double *local_dev, double *global_host);
 int fb_dist_global_sizes(const fb_context *c, int *nV, int *nT);
+// peer-memory (CUDA IPC over NVLink) exchange: 1 when the context exchanges scalars and halos through peer stores
+int fb_dist_p2p(const fb_context *c);
+struct FbPeerArgs;
+void fb_dist_peer_args(fb_context *c, FbPeerArgs *out);        // rank/world/comm pointers, epochs zeroed
+unsigned long long fb_dist_epoch(fb_context *c, int it, int family);  // epoch of (current solve, iteration, family)
+void fb_dist_next_solve(fb_context *c);
+unsigned int fb_dist_halo_mask(const fb_context *c);
+int fb_dist_halo_push(fb_context *c, const double *vec, unsigned long long epoch);
 
 template <typename T>
 static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {

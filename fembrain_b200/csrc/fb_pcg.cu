@@ -170,8 +170,14 @@ __device__ __forceinline__ void finish_row(double s, size_t row, const double *_
 }
 
 template <int MODE>
-__device__ __forceinline__ void finish_kernel(double (&part)[3], FbScalars *sc, double *slots, double *outp) {
+__device__ __forceinline__ void finish_kernel(double (&part)[3], FbScalars *sc, double *slots, double *outp, const FbPeerArgs &pa) {
   if (MODE == 1 || MODE == 2) {
+    if (pa.enabled) {  // partitioned, peer-memory exchange: this rank's total goes to every rank's comm block
+      double p1[1] = {part[0]}, t1[1];
+      if (block_reduce_to_total<SPMV_TB, 1>(p1, slots, &sc->ticket_a, t1) && threadIdx.x == 0)
+        peer_publish(pa, MODE == 1 ? FB_COMM_DQ : FB_COMM_RHO, t1[0]);
+      return;
+    }
     if (outp == nullptr) {  // deferred: the consumer kernel adds the slots
       block_reduce_to_slot<SPMV_TB>(part[0], slots);
       return;
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
                                                   const double *__restrict__ A, const double *__restrict__ x,
                                                   double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                   const double *__restrict__ b, const double *__restrict__ invD,
-                                                  FbScalars *sc, double *slots, double *outp) {
+                                                  FbScalars *sc, double *slots, double *outp, FbPeerArgs pa) {
   if (MODE != 0) {
     if (sc->done) return;
   }
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
     }
     if (lane < 3) finish_row<MODE>((lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2), 3 * (size_t)v + lane, x, y, mask, b, invD, part);
   }
-  finish_kernel<MODE>(part, sc, slots, outp);
+  finish_kernel<MODE>(part, sc, slots, outp, pa);
 }
 
 // ---- row-per-16-lanes SpMV with every load of a row in flight at once (no shared memory, no block syncs) ----
@@ -252,9 +258,10 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
                                                               const double *__restrict__ A, const double *__restrict__ x,
                                                               double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                               const double *__restrict__ b, const double *__restrict__ invD,
-                                                              FbScalars *sc, double *slots, double *outp) {
+                                                              FbScalars *sc, double *slots, double *outp, FbPeerArgs pa) {
   if (MODE != 0) {
     if (sc->done) return;
+    if (pa.enabled && pa.haloMask) peer_wait_halo(pa, sc);  // the neighbours' d has landed in my ghost entries
   }
   const int lane = threadIdx.x & (TILE_G - 1);
   const unsigned gmask = 0xffffu << (threadIdx.x & 16);
@@ -324,35 +331,49 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
     }
     v = vn; rs = rsn; re = ren;
   }
-  finish_kernel<MODE>(part, sc, slots, outp);
+  finish_kernel<MODE>(part, sc, slots, outp, pa);
 }
 
 // r = b (x0 = 0), d = invD r, x = 0, rho0 = sum r^2 invD           (CGSolver.cpp:139-147)
 __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restrict__ b, const double *__restrict__ invD,
                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
-                                                    FbScalars *sc, double *slots, double *outp) {
+                                                    FbScalars *sc, double *slots, double *outp, FbPeerArgs pa,
+                                                    const unsigned char *__restrict__ skipMask) {
   double part[1] = {0.0};
   for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB) {
     const double bi = b[i], di = invD[i];
     x[i] = 0.0;
     r[i] = bi;
-    d[i] = di * bi;
+    // peer-memory exchange: ghost entries of d belong to the neighbour's push (constrained entries stay 0 for ever)
+    if (!(skipMask && skipMask[i])) d[i] = di * bi;
     part[0] += (bi * bi) * di;
   }
   double total[1];
-  if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) *outp = total[0];
+  if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) {
+    if (pa.enabled) peer_publish(pa, FB_COMM_RHO, total[0]);
+    else *outp = total[0];
+  }
 }
 
 // after rho[0] is final (all-reduced in partitioned contexts): initial residual, loop condition at iteration 1
-__global__ void k_cg_begin(FbScalars *sc, double eps, int maxIt) {
-  const double total = sc->rho[0];
+__global__ void __launch_bounds__(32) k_cg_begin(FbScalars *sc, double eps, int maxIt, FbPeerArgs pa) {
+  double total;
+  if (pa.enabled) {
+    sc->comm_error = 0;
+    total = peer_collect<32>(pa, FB_COMM_RHO, sc);
+    if (threadIdx.x != 0) return;
+    sc->rho[0] = total;
+  } else {
+    if (threadIdx.x != 0) return;
+    total = sc->rho[0];
+  }
   sc->rho0 = total;
   sc->eps2 = eps * eps;
   sc->max_it = maxIt;
   sc->iters = 0;
   sc->dq = sc->rq = sc->qq = 0.0;
   // while ((residualNorm2 > eps*eps*initialResidualNorm2) && (iteration <= maxIterations)), iteration = 1
-  sc->done = !((total > eps * eps * total) && (1 <= maxIt));
+  sc->done = (!((total > eps * eps * total) && (1 <= maxIt))) || (pa.enabled && sc->comm_error);
 }
 
 // x += alpha d; REFRESH ? nothing more : (r -= alpha q; rho' = sum r^2 invD)     (CGSolver.cpp:155-174)
@@ -361,10 +382,11 @@ template <bool REFRESH>
 __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restrict__ d, const double *__restrict__ q,
                                                    const double *__restrict__ invD, double *__restrict__ x,
                                                    double *__restrict__ r, FbScalars *sc, double *slots, int itArg, double *outp,
-                                                   const double *__restrict__ dqSlots, int nDqSlots) {
+                                                   const double *__restrict__ dqSlots, int nDqSlots, FbPeerArgs pa) {
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
-  const double dq = dqSlots ? cta_sum_slots<VEC_TB>(dqSlots, nDqSlots) : sc->dq;
+  const double dq = pa.enabled ? peer_collect<VEC_TB>(pa, FB_COMM_DQ, sc)
+                               : (dqSlots ? cta_sum_slots<VEC_TB>(dqSlots, nDqSlots) : sc->dq);
   const double alpha = sc->rho[(it - 1) & 1] / dq;
   double part[1] = {0.0};
   // two doubles per thread per trip (128-bit loads/stores); element n-1 of an odd-length vector is handled last
@@ -396,7 +418,10 @@ __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restri
     }
   }
   if (!REFRESH) {
-    if (outp == nullptr) {
+    if (pa.enabled) {
+      double total[1];
+      if (block_reduce_to_total<VEC_TB, 1>(part, slots, &sc->ticket_b, total) && threadIdx.x == 0) peer_publish(pa, FB_COMM_RHO, total[0]);
+    } else if (outp == nullptr) {
       block_reduce_to_slot<VEC_TB>(part[0], slots);
     } else {
       double total[1];
@@ -408,10 +433,12 @@ __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restri
 // beta = rho'/rho; d = invD r + beta d; iteration++ and loop condition            (CGSolver.cpp:176-183, 150)
 __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__restrict__ r, const double *__restrict__ invD,
                                                       double *__restrict__ d, FbScalars *sc, int itArg,
-                                                      const double *__restrict__ rhoSlots, int nRhoSlots) {
+                                                      const double *__restrict__ rhoSlots, int nRhoSlots, FbPeerArgs pa,
+                                                      const unsigned char *__restrict__ skipMask) {
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
-  const double rhoNew = rhoSlots ? cta_sum_slots<VEC_TB>(rhoSlots, nRhoSlots) : sc->rho[it & 1];
+  const double rhoNew = pa.enabled ? peer_collect<VEC_TB>(pa, FB_COMM_RHO, sc)
+                                   : (rhoSlots ? cta_sum_slots<VEC_TB>(rhoSlots, nRhoSlots) : sc->rho[it & 1]);
   const double rhoOld = sc->rho[(it - 1) & 1];
   const double eps2 = sc->eps2, rho0 = sc->rho0;
   const int maxIt = sc->max_it;
@@ -419,13 +446,19 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
   const size_t n2 = (size_t)n >> 1;
   const double2 *r2 = reinterpret_cast<const double2 *>(r), *w2 = reinterpret_cast<const double2 *>(invD);
   double2 *d2 = reinterpret_cast<double2 *>(d);
-  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
-    const double2 rv = r2[i], wv = w2[i];
-    double2 dv = d2[i];
-    dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
-    d2[i] = dv;
+  if (skipMask) {
+    // peer-memory exchange: ghost entries of d are written by the neighbour's push, never here
+    for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB)
+      if (!skipMask[i]) d[i] = fma(invD[i], r[i], beta * d[i]);
+  } else {
+    for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
+      const double2 rv = r2[i], wv = w2[i];
+      double2 dv = d2[i];
+      dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
+      d2[i] = dv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
   // bookkeeping by the last CTA to finish, so that no CTA of this launch can still be reading sc->iters / done
   __shared__ bool last;
   __syncthreads();
@@ -436,7 +469,7 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
   __syncthreads();
   if (last && threadIdx.x == 0) {
     sc->ticket_b = 0u;
-    if (rhoSlots) sc->rho[it & 1] = rhoNew;
+    if (rhoSlots || pa.enabled) sc->rho[it & 1] = rhoNew;
     sc->iters = it;
     if (!((rhoNew > eps2 * rho0) && (it + 1 <= maxIt))) sc->done = 1;
   }
@@ -509,28 +542,70 @@ void plan_generic(fb_context *c) {
 }
 
 template <int MODE>
-void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, const double *b, double *outp) {
+void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y, const double *b, double *outp,
+                      const FbPeerArgs *peer = nullptr) {
+  FbPeerArgs pa;
+  if (peer) pa = *peer; else memset(&pa, 0, sizeof(pa));
   const int grid = c->grid_spmv[MODE];
   if (c->use_rows3) {
     if (MODE == 3 || c->rows3_minb == 4)
-      k_spmv_rows3<MODE, 4><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp);
+      k_spmv_rows3<MODE, 4><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
     else
-      k_spmv_rows3<MODE, 5><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp);
+      k_spmv_rows3<MODE, 5><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
   } else if (MODE != 3) {
     constexpr int M = MODE == 3 ? 1 : MODE;
     switch (c->spmv_group) {
-      case 8: k_spmv<8, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp); break;
-      case 32: k_spmv<32, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp); break;
-      default: k_spmv<16, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp); break;
+      case 8: k_spmv<8, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      case 32: k_spmv<32, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      default: k_spmv<16, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
     }
   }
   c->launches++;
 }
 
-// the reference's literal order, three kernels (+ NCCL in partitioned contexts)
-void enqueue_iteration_kernels(fb_context *c, int it) {
+// partitioned context with peer-memory exchange: same three kernels, no NCCL call and no extra launch for the sums —
+// producers store their total into every rank's comm block, consumers wait on their own flags (fb_pcg_common.cuh);
+// the halo of d is pushed into the neighbours' ghost entries by one small kernel and awaited at the top of the SpMV.
+void enqueue_iteration_p2p(fb_context *c, int it) {
   const int n = c->r, vg = c->grid_vec;
   double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
+  FbPeerArgs base, pa;
+  fb_dist_peer_args(c, &base);
+  // q = A d: waits for halo(it-1), publishes d.q(it)
+  pa = base;
+  pa.haloMask = fb_dist_halo_mask(c);
+  pa.epochWait = fb_dist_epoch(c, it - 1, FB_COMM_HALO);
+  pa.epoch = fb_dist_epoch(c, it, FB_COMM_DQ);
+  launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, nullptr, &pa);
+  // x, r update: collects d.q(it), publishes rho'(it) (or, on refresh iterations, the SpMV after it does)
+  pa = base;
+  pa.epochWait = fb_dist_epoch(c, it, FB_COMM_DQ);
+  pa.epoch = fb_dist_epoch(c, it, FB_COMM_RHO);
+  if (it % 30 == 0) {
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, nullptr, nullptr, 0, pa);
+    c->launches++;
+    FbPeerArgs pr = base;
+    pr.epoch = fb_dist_epoch(c, it, FB_COMM_RHO);
+    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, nullptr, &pr);
+  } else {
+    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, nullptr, nullptr, 0, pa);
+    c->launches++;
+  }
+  // direction: collects rho'(it); ghost entries are left to the neighbours
+  pa = base;
+  pa.epochWait = fb_dist_epoch(c, it, FB_COMM_RHO);
+  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it, nullptr, 0, pa, c->rowmask);
+  c->launches++;
+  fb_dist_halo_push(c, c->dir, fb_dist_epoch(c, it, FB_COMM_HALO));
+}
+
+// the reference's literal order, three kernels (+ NCCL in partitioned contexts without peer mapping)
+void enqueue_iteration_kernels(fb_context *c, int it) {
+  if (fb_dist_p2p(c)) { enqueue_iteration_p2p(c, it); return; }
+  const int n = c->r, vg = c->grid_vec;
+  double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
+  FbPeerArgs nopeer;
+  memset(&nopeer, 0, sizeof(nopeer));
   const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64;
   if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
   // one GPU: per-CTA sums stay in their slots and the next kernel adds them (no ticket / last-CTA pass on the SpMV tail);
@@ -545,17 +620,17 @@ void enqueue_iteration_kernels(fb_context *c, int it) {
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1]);
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
     if (defer) { rhoSlots = c->partials; nRhoSlots = c->grid_spmv[2]; }
   } else {
-    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1]);
+    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
     c->launches++;
     if (defer) { rhoSlots = slotsV; nRhoSlots = vg; }
   }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
-  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots);
+  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots, nopeer, nullptr);
   c->launches++;
   if (c->dist) fb_dist_halo_exchange(c, c->dir);
 }
@@ -564,16 +639,18 @@ void enqueue_iteration_kernels(fb_context *c, int it) {
 // so a captured period can be replayed).  Returns the number of kernels enqueued.
 int enqueue_iteration_fused(fb_context *c, int it, bool allowSample) {
   const int n = c->r, vg = c->grid_vec;
+  FbPeerArgs nopeer;
+  memset(&nopeer, 0, sizeof(nopeer));
   double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
   const bool sample = allowSample && c->profiling && (it % 16 == 1) && c->nprof < 64;
   if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
   launch_spmv_mode<3>(c, c->Keff, c->dir, c->Ad, c->res, nullptr);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr, nullptr, 0);
+    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr, nullptr, 0, nopeer);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, &c->sc->rho[0]);  // it is even: rho[it & 1] = rho[0]
-    k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, 0, nullptr, 0);
+    k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, 0, nullptr, 0, nopeer, nullptr);
     c->launches++;
     return 4;
   }
@@ -597,17 +674,32 @@ int finish_solve(fb_context *c) {
   const bool notConverged = rhoFinal > s.eps2 * s.rho0;
   c->last_iters = s.iters * (notConverged ? -1 : 1);
   c->last_ratio = (s.rho0 != 0.0) ? rhoFinal / s.rho0 : 0.0;
+  if (c->dist && s.comm_error) {
+    fb_set_error("peer-memory exchange timed out (a rank stopped publishing)");
+    return FB_ERR_COMM;
+  }
   return FB_OK;
 }
 
 int start_solve(fb_context *c, double eps, int maxIt) {
   cudaStream_t st = c->stream;
+  FbPeerArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  const bool p2p = fb_dist_p2p(c) != 0;
+  if (c->dist) fb_dist_next_solve(c);
+  if (p2p) {
+    fb_dist_peer_args(c, &pa);
+    pa.epoch = fb_dist_epoch(c, 0, FB_COMM_RHO);
+  }
   k_cg_init<<<c->grid_vec, VEC_TB, 0, st>>>(c->r, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + 3 * (size_t)FB_MAX_PARTIALS,
-                                            c->dist ? &c->sc->rho_part : &c->sc->rho[0]);
-  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));  // rho0 is a global sum
-  k_cg_begin<<<1, 1, 0, st>>>(c->sc, eps, maxIt);
+                                            c->dist ? &c->sc->rho_part : &c->sc->rho[0], pa, p2p ? c->rowmask : nullptr);
+  if (c->dist && !p2p) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));  // rho0 is a global sum
+  if (p2p) { pa.epoch = 0; pa.epochWait = fb_dist_epoch(c, 0, FB_COMM_RHO); }
+  k_cg_begin<<<1, 32, 0, st>>>(c->sc, eps, maxIt, pa);
   c->launches += 2;
-  if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));  // ghost entries of d = invD r live on the neighbours
+  // ghost entries of d = invD r live on the neighbours
+  if (p2p) FB_TRY(fb_dist_halo_push(c, c->dir, fb_dist_epoch(c, 0, FB_COMM_HALO)));
+  else if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));
   return FB_OK;
 }
 

@@ -30,3 +30,81 @@ __device__ __forceinline__ void load_row_chunk(const double *__restrict__ A, int
   }
 }
 
+
+// ---- peer-memory exchange between the ranks of a partitioned context (one process per GPU, NVLink/NVSwitch) --------
+// Every rank owns a small "comm block" in device memory, mapped into all other ranks with CUDA IPC.  A producer kernel
+// stores its value into slot [rank] of EVERY rank's block, fences at system scope, then stores the epoch into flag
+// [rank]; a consumer kernel spins (bounded) on its LOCAL flags until all carry the epoch, then adds the slots in rank
+// order — all ranks add the same bits in the same order, so alpha/beta/rho and the loop flag agree bit for bit.
+// Slots are single-buffered: a rank cannot overwrite a slot before every other rank has consumed it, because its next
+// write of that kind sits behind a wait on something each of them publishes only after consuming (fb_dist.cu).
+#define FB_MAX_RANKS 16
+enum { FB_COMM_DQ = 0, FB_COMM_RHO = 1, FB_COMM_HALO = 2 };  // slot/flag families
+// block layout in 8-byte words: slots[family][FB_MAX_RANKS], then flags[family][FB_MAX_RANKS]
+#define FB_COMM_SLOT(fam, r) ((fam) * FB_MAX_RANKS + (r))
+#define FB_COMM_FLAG(fam, r) (3 * FB_MAX_RANKS + (fam) * FB_MAX_RANKS + (r))
+#define FB_COMM_WORDS (6 * FB_MAX_RANKS)
+#define FB_SPIN_LIMIT (1ll << 24)  // x ~100 ns: a lost peer turns into FB_ERR_COMM after ~2 s instead of a hung GPU
+
+struct FbPeerArgs {
+  int enabled, rank, world;
+  unsigned long long epoch;      // epoch of the value this kernel PUBLISHES (0 = none)
+  unsigned long long epochWait;  // epoch of the value this kernel COLLECTS or waits for (0 = none)
+  unsigned int haloMask;         // ranks whose halo flag the kernel waits for (SpMV)
+  double *comm[FB_MAX_RANKS];
+};
+
+// executed by ONE thread (the thread that holds the rank's total)
+__device__ __forceinline__ void peer_publish(const FbPeerArgs &pa, int family, double value) {
+  for (int p = 0; p < pa.world; p++) ((volatile double *)pa.comm[p])[FB_COMM_SLOT(family, pa.rank)] = value;
+  __threadfence_system();
+  for (int p = 0; p < pa.world; p++) ((volatile unsigned long long *)pa.comm[p])[FB_COMM_FLAG(family, pa.rank)] = pa.epoch;
+}
+
+// executed by ALL threads of a CTA (TB >= 32); returns the rank-ordered sum in every thread; on timeout marks the solve
+template <int TB>
+__device__ __forceinline__ double peer_collect(const FbPeerArgs &pa, int family, FbScalars *sc) {
+  __shared__ double s_total;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const volatile unsigned long long *flags = (const volatile unsigned long long *)pa.comm[pa.rank];
+    bool ok = true;
+    if (lane < pa.world) {
+      long long spins = 0;
+      while (flags[FB_COMM_FLAG(family, lane)] < pa.epochWait) {
+        __nanosleep(64);
+        if (++spins > FB_SPIN_LIMIT) { ok = false; break; }
+      }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    const double v = (lane < pa.world) ? ((const volatile double *)pa.comm[pa.rank])[FB_COMM_SLOT(family, lane)] : 0.0;
+    double tot = 0.0;
+    for (int r = 0; r < pa.world; r++) tot += __shfl_sync(0xffffffffu, v, r);
+    if (lane == 0) {
+      s_total = tot;
+      if (!ok) { sc->comm_error = 1; sc->done = 1; }
+    }
+  }
+  __syncthreads();
+  const double t = s_total;
+  __syncthreads();
+  return t;
+}
+
+// executed by ALL threads of a CTA: wait until every rank in haloMask has pushed its halo for epochWait
+__device__ __forceinline__ void peer_wait_halo(const FbPeerArgs &pa, FbScalars *sc) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const volatile unsigned long long *flags = (const volatile unsigned long long *)pa.comm[pa.rank];
+    if (lane < pa.world && ((pa.haloMask >> lane) & 1u)) {
+      long long spins = 0;
+      while (flags[FB_COMM_FLAG(FB_COMM_HALO, lane)] < pa.epochWait) {
+        __nanosleep(64);
+        if (++spins > FB_SPIN_LIMIT) { sc->comm_error = 1; sc->done = 1; break; }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}

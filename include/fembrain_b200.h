@@ -212,6 +212,10 @@ int fb_create_partitioned(fb_context **out, int num_vertices, const double *rest
                           const int *fixed_vertices, const fb_params *params, int rank, int world,
                           const void *comm_id128);
 int fb_partition_range(const fb_context *ctx, int *vertex_begin, int *vertex_end);
+/* 1 when the ranks exchange the PCG scalars and the halo of d through peer-memory stores over NVLink (CUDA IPC mappings,
+ * flags in each rank's comm block), 0 when they go through NCCL calls between kernels (FEMBRAIN_B200_P2P=0, or the
+ * mapping could not be set up). */
+int fb_partition_peer_memory(const fb_context *ctx);
 /* On a partitioned context every vector argument of the force/state calls is GLOBAL length (3*num_vertices of the whole
  * mesh): setters take the global vector and keep this rank's part; getters write this rank's OWNED entries and zeros
  * elsewhere, so the sum over ranks is the full vector.  fb_num_vertices/_tets/_dofs report the global mesh; the

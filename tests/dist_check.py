@@ -86,7 +86,7 @@ def main():
     dist.broadcast(flag, 0)
     dist.barrier()
     if rank == 0:
-        print("DIST_CHECK", "OK" if ok else "FAILED", f"world={world} nx={nx} rows [{b},{e}) rhs_local={lrhs.size}", flush=True)
+        print("DIST_CHECK", "OK" if ok else "FAILED", f"world={world} nx={nx} rows [{b},{e}) rhs_local={lrhs.size} peer_memory={part.peer_memory}", flush=True)
     part.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag[0]) == 1 else 1)

@@ -448,8 +448,20 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
   double2 *d2 = reinterpret_cast<double2 *>(d);
   if (skipMask) {
     // peer-memory exchange: ghost entries of d are written by the neighbour's push, never here
-    for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * VEC_TB)
-      if (!skipMask[i]) d[i] = fma(invD[i], r[i], beta * d[i]);
+    const uchar2 *m2 = reinterpret_cast<const uchar2 *>(skipMask);
+    for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
+      const double2 rv = r2[i], wv = w2[i];
+      const uchar2 mk = m2[i];
+      double2 dv = d2[i];
+      dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
+      if (!(mk.x | mk.y)) {
+        d2[i] = dv;
+      } else {
+        if (!mk.x) d[2 * i] = dv.x;
+        if (!mk.y) d[2 * i + 1] = dv.y;
+      }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && !skipMask[n - 1]) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
   } else {
     for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
       const double2 rv = r2[i], wv = w2[i];
@@ -576,7 +588,10 @@ void enqueue_iteration_p2p(fb_context *c, int it) {
   pa.haloMask = fb_dist_halo_mask(c);
   pa.epochWait = fb_dist_epoch(c, it - 1, FB_COMM_HALO);
   pa.epoch = fb_dist_epoch(c, it, FB_COMM_DQ);
+  const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64;  // includes the wait for the neighbours' halo
+  if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
   launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, nullptr, &pa);
+  if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   // x, r update: collects d.q(it), publishes rho'(it) (or, on refresh iterations, the SpMV after it does)
   pa = base;
   pa.epochWait = fb_dist_epoch(c, it, FB_COMM_DQ);

@@ -124,6 +124,7 @@ struct fb_context {
   int use_rows3;         // 1: k_spmv_rows3 (16 lanes per row, all loads of a row in flight), 0: k_spmv<G>
   int rows3_minb;        // resident CTAs/SM requested for k_spmv_rows3 modes 0-2 (4 or 5)
   int grid_spmv[4], grid_vec;  // one-resident-wave launch shapes per SpMV mode and for the vector kernels
+  int pdl;                     // launch the PCG kernels with programmatic dependent launch
   int pcg_fused, pcg_graph;    // two-kernel schedule / CUDA-graph replay of a 30-iteration period
   void *graph_exec;            // cudaGraphExec_t
   int graph_kernels, graph_failed;

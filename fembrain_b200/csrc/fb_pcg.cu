@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
                                                   double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                   const double *__restrict__ b, const double *__restrict__ invD,
                                                   FbScalars *sc, double *slots, double *outp, FbPeerArgs pa) {
+  pdl_wait();
+  pdl_trigger();
   if (MODE != 0) {
     if (sc->done) return;
   }
@@ -259,6 +261,8 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
                                                               double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                               const double *__restrict__ b, const double *__restrict__ invD,
                                                               FbScalars *sc, double *slots, double *outp, FbPeerArgs pa) {
+  pdl_wait();
+  pdl_trigger();
   if (MODE != 0) {
     if (sc->done) return;
     if (pa.enabled && pa.haloMask) peer_wait_halo(pa, sc);  // the neighbours' d has landed in my ghost entries
@@ -383,6 +387,8 @@ __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restri
                                                    const double *__restrict__ invD, double *__restrict__ x,
                                                    double *__restrict__ r, FbScalars *sc, double *slots, int itArg, double *outp,
                                                    const double *__restrict__ dqSlots, int nDqSlots, FbPeerArgs pa) {
+  pdl_wait();
+  pdl_trigger();
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
   const double dq = pa.enabled ? peer_collect<VEC_TB>(pa, FB_COMM_DQ, sc)
@@ -435,6 +441,8 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
                                                       double *__restrict__ d, FbScalars *sc, int itArg,
                                                       const double *__restrict__ rhoSlots, int nRhoSlots, FbPeerArgs pa,
                                                       const unsigned char *__restrict__ skipMask) {
+  pdl_wait();
+  pdl_trigger();
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
   const double rhoNew = pa.enabled ? peer_collect<VEC_TB>(pa, FB_COMM_RHO, sc)
@@ -491,6 +499,8 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
 __global__ void __launch_bounds__(VEC_TB) k_fused_update(int n, const double *__restrict__ q, const double *__restrict__ invD,
                                                          double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
                                                          FbScalars *sc, double *slots) {
+  pdl_wait();
+  pdl_trigger();
   if (sc->done) return;
   const int it = sc->iters + 1;
   const double rho = sc->rho[(it - 1) & 1];
@@ -561,9 +571,9 @@ void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y
   const int grid = c->grid_spmv[MODE];
   if (c->use_rows3) {
     if (MODE == 3 || c->rows3_minb == 4)
-      k_spmv_rows3<MODE, 4><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
+      fb_launch(c->pdl && MODE != 0, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
     else
-      k_spmv_rows3<MODE, 5><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
+      fb_launch(c->pdl && MODE != 0, c->stream, k_spmv_rows3<MODE, 5>, grid, SPMV_TB, c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
   } else if (MODE != 3) {
     constexpr int M = MODE == 3 ? 1 : MODE;
     switch (c->spmv_group) {
@@ -597,19 +607,19 @@ void enqueue_iteration_p2p(fb_context *c, int it) {
   pa.epochWait = fb_dist_epoch(c, it, FB_COMM_DQ);
   pa.epoch = fb_dist_epoch(c, it, FB_COMM_RHO);
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, nullptr, nullptr, 0, pa);
+    fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, nullptr, nullptr, 0, pa);
     c->launches++;
     FbPeerArgs pr = base;
     pr.epoch = fb_dist_epoch(c, it, FB_COMM_RHO);
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, nullptr, &pr);
   } else {
-    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, nullptr, nullptr, 0, pa);
+    fb_launch(c->pdl, c->stream, k_update<false>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, nullptr, nullptr, 0, pa);
     c->launches++;
   }
   // direction: collects rho'(it); ghost entries are left to the neighbours
   pa = base;
   pa.epochWait = fb_dist_epoch(c, it, FB_COMM_RHO);
-  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it, nullptr, 0, pa, c->rowmask);
+  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, it, nullptr, 0, pa, c->rowmask);
   c->launches++;
   fb_dist_halo_push(c, c->dir, fb_dist_epoch(c, it, FB_COMM_HALO));
 }
@@ -635,17 +645,17 @@ void enqueue_iteration_kernels(fb_context *c, int it) {
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
+    fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
     if (defer) { rhoSlots = c->partials; nRhoSlots = c->grid_spmv[2]; }
   } else {
-    k_update<false><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
+    fb_launch(c->pdl, c->stream, k_update<false>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
     c->launches++;
     if (defer) { rhoSlots = slotsV; nRhoSlots = vg; }
   }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
-  k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots, nopeer, nullptr);
+  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots, nopeer, nullptr);
   c->launches++;
   if (c->dist) fb_dist_halo_exchange(c, c->dir);
 }
@@ -662,14 +672,14 @@ int enqueue_iteration_fused(fb_context *c, int it, bool allowSample) {
   launch_spmv_mode<3>(c, c->Keff, c->dir, c->Ad, c->res, nullptr);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (it % 30 == 0) {
-    k_update<true><<<vg, VEC_TB, 0, c->stream>>>(n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr, nullptr, 0, nopeer);
+    fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr, nullptr, 0, nopeer);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, &c->sc->rho[0]);  // it is even: rho[it & 1] = rho[0]
-    k_direction<<<vg, VEC_TB, 0, c->stream>>>(n, c->res, c->invD, c->dir, c->sc, 0, nullptr, 0, nopeer, nullptr);
+    fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, 0, nullptr, 0, nopeer, nullptr);
     c->launches++;
     return 4;
   }
-  k_fused_update<<<vg, VEC_TB, 0, c->stream>>>(n, c->Ad, c->invD, c->x, c->res, c->dir, c->sc, slotsV);
+  fb_launch(c->pdl, c->stream, k_fused_update, vg, VEC_TB, n, c->Ad, c->invD, c->x, c->res, c->dir, c->sc, slotsV);
   c->launches++;
   return 2;
 }
@@ -784,6 +794,8 @@ int fb_spmv_plan(fb_context *c) {
   // launch gains, and graph replay changes nothing (the gaps are device-side dependencies, not host launch cost).
   c->pcg_fused = c->use_rows3 && mode && (!strcmp(mode, "fused") || !strcmp(mode, "fused_nograph"));
   c->pcg_graph = c->pcg_fused && !(mode && !strcmp(mode, "fused_nograph"));
+  const char *pdl = getenv("FEMBRAIN_B200_PDL");
+  c->pdl = !(pdl && atoi(pdl) == 0);
   return fb_pcg_plan_persistent(c);
 }
 

@@ -1,6 +1,32 @@
 // fb_pcg_common.cuh — device helpers shared by the PCG translation units.
 #pragma once
+#include <cstring>
+
 #include "fb_internal.h"
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// have its CTAs scheduled while the previous kernel of the stream is still draining; pdl_wait() blocks until that
+// kernel has completed and its writes are visible (a no-op for ordinary launches), pdl_trigger() lets the NEXT
+// kernel's CTAs be scheduled as soon as this kernel's CTAs leave their SM slots.  Every PCG kernel calls both at its
+// top, before its first read of anything another kernel produced, so only launch latency and ramp-up overlap.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// launch with the attribute when enabled; same argument conversion rules as <<<>>>
+template <typename... KArgs, typename... Args>
+static inline void fb_launch(bool pdl, cudaStream_t st, void (*kernel)(KArgs...), int grid, int block, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ double ld_stream(const double *p) {
   double v;

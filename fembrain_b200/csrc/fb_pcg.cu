@@ -760,10 +760,16 @@ int fb_spmv_plan(fb_context *c) {
   const char *env = getenv("FEMBRAIN_B200_SPMV");
   c->use_rows3 = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
   const size_t n = (size_t)c->r;
-  int gv = one_wave(c, k_fused_update, VEC_TB, (n + VEC_TB - 1) / VEC_TB);
-  gv = min(gv, one_wave(c, k_update<false>, VEC_TB, (n + VEC_TB - 1) / VEC_TB));
-  gv = min(gv, one_wave(c, k_direction, VEC_TB, (n + VEC_TB - 1) / VEC_TB));
-  gv = min(gv, one_wave(c, k_cg_init, VEC_TB, (n + VEC_TB - 1) / VEC_TB));
+  // vector kernels: at most one resident wave, one 16-byte item per thread on small meshes.  Fatter CTAs (2/4/8 items per
+  // thread, fewer CTAs adding the producer's slots) were measured slower: 51.3 / 52.8 / 55.7 us per iteration at 1M tets,
+  // 22.0 / 24.5 / 28.8 at 200k (profiles/r01_vec_items.txt) — these kernels are latency bound, more CTAs hide more of it
+  const char *vi = getenv("FEMBRAIN_B200_VEC_ITEMS");
+  const size_t items = (vi && atoi(vi) > 0) ? (size_t)atoi(vi) : 1;
+  const size_t wantV = ((n >> 1) + VEC_TB * items - 1) / (VEC_TB * items);
+  int gv = one_wave(c, k_fused_update, VEC_TB, wantV);
+  gv = min(gv, one_wave(c, k_update<false>, VEC_TB, wantV));
+  gv = min(gv, one_wave(c, k_direction, VEC_TB, wantV));
+  gv = min(gv, one_wave(c, k_cg_init, VEC_TB, wantV));
   c->grid_vec = gv;
   if (c->use_rows3) {
     const size_t gpb = SPMV_TB / TILE_G;

@@ -391,27 +391,36 @@ __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restri
   pdl_trigger();
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
-  const double dq = pa.enabled ? peer_collect<VEC_TB>(pa, FB_COMM_DQ, sc)
-                               : (dqSlots ? cta_sum_slots<VEC_TB>(dqSlots, nDqSlots) : sc->dq);
-  const double alpha = sc->rho[(it - 1) & 1] / dq;
-  double part[1] = {0.0};
-  // two doubles per thread per trip (128-bit loads/stores); element n-1 of an odd-length vector is handled last
+  // two doubles per thread per trip (128-bit loads/stores); element n-1 of an odd-length vector is handled last.
+  // The first item's operands are requested BEFORE alpha is known, so their latency overlaps the slot sum / peer wait.
   const size_t n2 = (size_t)n >> 1;
   const double2 *d2 = reinterpret_cast<const double2 *>(d), *q2 = reinterpret_cast<const double2 *>(q);
   const double2 *w2 = reinterpret_cast<const double2 *>(invD);
   double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
-  for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
-    const double2 dv = d2[i];
-    double2 xv = x2[i];
+  const size_t stride = (size_t)gridDim.x * VEC_TB;
+  size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x;
+  double2 dv = make_double2(0.0, 0.0), xv = dv, qv = dv, wv = dv, rv = dv;
+  if (i < n2) {
+    dv = d2[i]; xv = x2[i];
+    if (!REFRESH) { qv = q2[i]; wv = w2[i]; rv = r2[i]; }
+  }
+  const double dq = pa.enabled ? peer_collect<VEC_TB>(pa, FB_COMM_DQ, sc)
+                               : (dqSlots ? cta_sum_slots<VEC_TB>(dqSlots, nDqSlots) : sc->dq);
+  const double alpha = sc->rho[(it - 1) & 1] / dq;
+  double part[1] = {0.0};
+  while (i < n2) {
     xv.x = fma(alpha, dv.x, xv.x); xv.y = fma(alpha, dv.y, xv.y);
     x2[i] = xv;
     if (!REFRESH) {
-      const double2 qv = q2[i], wv = w2[i];
-      double2 rv = r2[i];
       rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
       r2[i] = rv;
       part[0] += (rv.x * rv.x) * wv.x;
       part[0] += (rv.y * rv.y) * wv.y;
+    }
+    i += stride;
+    if (i < n2) {
+      dv = d2[i]; xv = x2[i];
+      if (!REFRESH) { qv = q2[i]; wv = w2[i]; rv = r2[i]; }
     }
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -445,40 +454,41 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
   pdl_trigger();
   if (sc->done) return;
   const int it = itArg > 0 ? itArg : sc->iters + 1;
+  const size_t n2 = (size_t)n >> 1;
+  const double2 *r2 = reinterpret_cast<const double2 *>(r), *w2 = reinterpret_cast<const double2 *>(invD);
+  const uchar2 *m2 = reinterpret_cast<const uchar2 *>(skipMask);
+  double2 *d2 = reinterpret_cast<double2 *>(d);
+  const size_t stride = (size_t)gridDim.x * VEC_TB;
+  size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x;
+  // first item requested before beta is known: the loads overlap the slot sum / peer wait
+  double2 rv = make_double2(0.0, 0.0), wv = rv, dv = rv;
+  uchar2 mk = make_uchar2(0, 0);
+  if (i < n2) {
+    rv = r2[i]; wv = w2[i]; dv = d2[i];
+    if (skipMask) mk = m2[i];
+  }
   const double rhoNew = pa.enabled ? peer_collect<VEC_TB>(pa, FB_COMM_RHO, sc)
                                    : (rhoSlots ? cta_sum_slots<VEC_TB>(rhoSlots, nRhoSlots) : sc->rho[it & 1]);
   const double rhoOld = sc->rho[(it - 1) & 1];
   const double eps2 = sc->eps2, rho0 = sc->rho0;
   const int maxIt = sc->max_it;
   const double beta = rhoNew / rhoOld;
-  const size_t n2 = (size_t)n >> 1;
-  const double2 *r2 = reinterpret_cast<const double2 *>(r), *w2 = reinterpret_cast<const double2 *>(invD);
-  double2 *d2 = reinterpret_cast<double2 *>(d);
-  if (skipMask) {
-    // peer-memory exchange: ghost entries of d are written by the neighbour's push, never here
-    const uchar2 *m2 = reinterpret_cast<const uchar2 *>(skipMask);
-    for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
-      const double2 rv = r2[i], wv = w2[i];
-      const uchar2 mk = m2[i];
-      double2 dv = d2[i];
-      dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
-      if (!(mk.x | mk.y)) {
-        d2[i] = dv;
-      } else {
-        if (!mk.x) d[2 * i] = dv.x;
-        if (!mk.y) d[2 * i + 1] = dv.y;
-      }
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && !skipMask[n - 1]) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
-  } else {
-    for (size_t i = (size_t)blockIdx.x * VEC_TB + threadIdx.x; i < n2; i += (size_t)gridDim.x * VEC_TB) {
-      const double2 rv = r2[i], wv = w2[i];
-      double2 dv = d2[i];
-      dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
+  while (i < n2) {
+    dv.x = fma(wv.x, rv.x, beta * dv.x); dv.y = fma(wv.y, rv.y, beta * dv.y);
+    // peer-memory exchange: ghost entries of d (masked) are written by the neighbour's push, never here
+    if (!(mk.x | mk.y)) {
       d2[i] = dv;
+    } else {
+      if (!mk.x) d[2 * i] = dv.x;
+      if (!mk.y) d[2 * i + 1] = dv.y;
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
+    i += stride;
+    if (i < n2) {
+      rv = r2[i]; wv = w2[i]; dv = d2[i];
+      if (skipMask) mk = m2[i];
+    }
   }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && !(skipMask && skipMask[n - 1])) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
   // bookkeeping by the last CTA to finish, so that no CTA of this launch can still be reading sc->iters / done
   __shared__ bool last;
   __syncthreads();

@@ -106,6 +106,11 @@ def load_library():
         "fb_get_effective_stiffness_values": (ci, [vp, vp]), "fb_get_rhs": (ci, [vp, vp]),
         "fb_get_internal_forces": (ci, [vp, vp]), "fb_get_qdelta": (ci, [vp, vp]),
         "fb_solve": (ci, [vp, vp, vp, cd, ci, C.POINTER(ci)]), "fb_system_multiply": (ci, [vp, vp, vp]),
+        "fb_veg_load": (ci, [C.c_char_p, C.POINTER(ci), C.POINTER(ci), pp, pp, pp, pp, pp]),
+        "fb_veg_free": (None, [vp]),
+        "fb_create_from_veg": (ci, [pp, C.c_char_p, ci, vp, prm]),
+        "fb_export_positions_float4": (ci, [vp, ci, vp, vp]),
+        "fb_export_positions_float4_dev": (ci, [vp, ci, vp, vp]),
         "fb_timer_start": (ci, [vp]), "fb_timer_stop": (ci, [vp, C.POINTER(cd)]),
         "fb_set_profiling": (ci, [vp, ci]),
         "fb_get_spmv_profile": (ci, [vp, C.POINTER(cd), C.POINTER(ci), C.POINTER(cd)]),
@@ -173,6 +178,26 @@ def plan_partition(num_vertices, tets, world, rank):
     }
 
 
+def veg_load(path):
+    """fb_veg_load: (verts [nV,3], tets [nT,4] 0-based, E[nT], nu[nT], density[nT]) with the reference loader's rules."""
+    lib = load_library()
+    nv, nt = C.c_int(0), C.c_int(0)
+    ptrs = [C.c_void_p() for _ in range(5)]
+    st = lib.fb_veg_load(str(path).encode(), C.byref(nv), C.byref(nt), *[C.byref(p) for p in ptrs])
+    if st != FB_OK:
+        raise FemBrainError(st, "fb_veg_load", lib.fb_last_error_string().decode())
+    try:
+        def arr(p, ctype, n, dt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(max(n, 1),))[:n].astype(dt, copy=True)
+        v = arr(ptrs[0], C.c_double, 3 * nv.value, np.float64).reshape(-1, 3)
+        t = arr(ptrs[1], C.c_int, 4 * nt.value, np.int32).reshape(-1, 4)
+        E, nu, rho = (arr(p, C.c_double, nt.value, np.float64) for p in ptrs[2:])
+    finally:
+        for p in ptrs:
+            lib.fb_veg_free(p)
+    return v, t, E, nu, rho
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -188,13 +213,21 @@ def _ptr(a):
 class Simulation:
     """One deformable model on one B200: the C-ABI context behind the reference's integrator interface."""
 
-    def __init__(self, verts, tets, fixed_verts=(), constrained_dofs=None, materials=None, partition=None, **params):
+    def __init__(self, verts=None, tets=None, fixed_verts=(), constrained_dofs=None, materials=None, partition=None, veg_path=None,
+                 **params):
         self._lib = load_library()
         self._h = C.c_void_p()
-        v, t = _f64(verts).reshape(-1, 3), _i32(tets).reshape(-1, 4)
-        self.nV, self.nT = len(v), len(t)
         p = default_params(**params)
         self.params = p
+        if veg_path is not None:
+            fx = _i32(fixed_verts)
+            st = self._lib.fb_create_from_veg(C.byref(self._h), str(veg_path).encode(), len(fx), _ptr(fx), C.byref(p))
+            self._check(st, "fb_create_from_veg")
+            self.nV, self.nT = self._lib.fb_num_vertices(self._h), self._lib.fb_num_tets(self._h)
+            self.r = self._lib.fb_num_dofs(self._h)
+            return
+        v, t = _f64(verts).reshape(-1, 3), _i32(tets).reshape(-1, 4)
+        self.nV, self.nT = len(v), len(t)
         if partition is not None:
             rank, world, comm_id = partition
             fx = _i32(fixed_verts)
@@ -357,6 +390,15 @@ class Simulation:
     @property
     def contact_count(self):
         return self._lib.fb_deformable_contact_count(self._h)
+
+    def export_positions_float4(self, rest_xyzw=None, count=None):
+        """ApplyVertexDeformations: float4 rest + float4(q, 0) for the first `count` vertices."""
+        n = self.nV if count is None else count
+        rest = np.ascontiguousarray(rest_xyzw, dtype=np.float32).reshape(-1, 4) if rest_xyzw is not None else None
+        out = np.zeros((n, 4), np.float32)
+        self._check(self._lib.fb_export_positions_float4(self._h, n, _ptr(rest) if rest is not None else None, _ptr(out)),
+                    "fb_export_positions_float4")
+        return out
 
     # -- statistics ------------------------------------------------------------------------------------------
     def assembly_time(self):

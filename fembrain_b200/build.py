@@ -26,6 +26,7 @@ UNITS = {
     "fb_pcg.cu": [],
     "fb_pcg_persistent.cu": [],
     "fb_dist.cu": [],
+    "fb_veg.cu": ["-fmad=false"],
     "fb_deformable.cu": ["-fmad=false"],
 }
 HEADERS = ["fb_internal.h", "fb_element_math.h", "fb_pcg_common.cuh", os.path.join("..", "..", "include", "fembrain_b200.h")]

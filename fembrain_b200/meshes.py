@@ -146,3 +146,28 @@ def read_veg(path: str):
     assert verts is not None and tets is not None
     tets = np.ascontiguousarray((tets - vbase).astype(np.int32))
     return verts, tets
+
+
+def write_veg(path, verts, tets, materials=(), sets=None, regions=(), sep=" "):
+    """Write a Vega .veg file (the format VolMeshIO::writeVega / PS_VegWriter produce for FemBrain's models).
+
+    materials: [(name, density, E, nu)], sets: {name: iterable of 0-based element ids}, regions: [(set name, material name)];
+    "allElements" is the implicit set of every element.  Vertices and elements are written 1-indexed like the reference's files."""
+    with open(path, "w") as fh:
+        fh.write("# Vega mesh file written by fembrain_b200.meshes.write_veg\n\n*VERTICES\n")
+        fh.write(f"{len(verts)} 3 0 0\n")
+        for i, p in enumerate(verts):
+            fh.write(f"{i + 1}{sep}{float(p[0])!r}{sep}{float(p[1])!r}{sep}{float(p[2])!r}\n")
+        fh.write("\n*ELEMENTS\nTET\n")
+        fh.write(f"{len(tets)} 4 0\n")
+        for i, t in enumerate(tets):
+            fh.write(f"{i + 1}{sep}{int(t[0]) + 1}{sep}{int(t[1]) + 1}{sep}{int(t[2]) + 1}{sep}{int(t[3]) + 1}\n")
+        for name, density, E, nu in materials:
+            fh.write(f"\n*MATERIAL {name}\nENU, {float(density)!r}, {float(E)!r}, {float(nu)!r}\n")
+        for name, els in (sets or {}).items():
+            fh.write(f"\n*SET {name}\n")
+            els = [int(e) + 1 for e in els]
+            for k in range(0, len(els), 8):
+                fh.write(", ".join(str(e) for e in els[k:k + 8]) + ",\n")
+        for set_name, mat_name in regions:
+            fh.write(f"\n*REGION\n{set_name}, {mat_name}\n")

@@ -148,6 +148,22 @@ int fb_deformable_contact_count(const fb_context *ctx);                         
  * reference's rings exactly; reference_quirk = 0 or num_edges = 0 returns to true adjacency. */
 int fb_deformable_set_edge_list(fb_context *ctx, int num_edges, const int *from_to, int reference_quirk);
 
+/* ---- mesh ingest and rendering hand-off (the callers either side of the path) ---------------------
+ * .veg reader with the rules of the reference's loader (VolumetricMesh(char*), VEGA/volumetricMesh/volumetricMesh.cpp:45-535):
+ * vertices, 0-based TET elements and one (E, nu, density) triple per element from the *MATERIAL / *SET / *REGION sections.
+ * Output arrays are malloc'ed by the library (any may be NULL to skip) and released with fb_veg_free.  Host-only: no GPU needed. */
+int fb_veg_load(const char *path, int *num_vertices, int *num_tets, double **vertices, int **tets, double **E, double **nu,
+                double **density);
+void fb_veg_free(void *array);
+/* TetMesh(char* filename) + the setup chain of fb_create_with_materials */
+int fb_create_from_veg(fb_context **out, const char *path, int num_fixed_vertices, const int *fixed_vertices, const fb_params *params);
+/* GPUPoly::applyFemDisplacements + ApplyVertexDeformations (implicit/OclPolygonizer.cpp:1543-1584, data/opencl/Polygonizer.cl:1417-1427):
+ * out[i] = rest[i] + (float4)(q[3i], q[3i+1], q[3i+2], 0) for the first `count` vertices, in float, on the device.
+ * rest_xyzw NULL = the context's rest positions cast to float with w = 1.  The _dev variant takes device pointers (e.g. a mapped
+ * GL vertex buffer) and involves no host copy at all. */
+int fb_export_positions_float4(fb_context *ctx, int count, const float *rest_xyzw, float *out_xyzw);
+int fb_export_positions_float4_dev(fb_context *ctx, int count, const float *rest_xyzw_dev, float *out_xyzw_dev);
+
 /* ---- timing / solver statistics (IntegratorBaseSparse::GetForceAssemblyTime / GetSystemSolveTime,
  * integratorBaseSparse.h:66-67; CGSolver return value, CGSolver.cpp:189) -------------------------- */
 double fb_force_assembly_seconds(const fb_context *ctx); /* CUDA-event time of the last step's assembly kernels */

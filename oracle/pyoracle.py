@@ -58,10 +58,21 @@ def _lib(kind: str):
         fn = getattr(lib, p + name)
         fn.restype, fn.argtypes = res, args
     if kind == "port":
+        lib.fbport_create_materials.restype = vp
+        lib.fbport_create_materials.argtypes = [ci, vp, ci, vp, vp, vp, vp, ci, vp, cd, cd, cd]
         lib.fbport_deformable_timestep.restype = ci
         lib.fbport_deformable_timestep.argtypes = [vp, ci, ci, vp, vp, ci, ci, ci, vp, ci, ci, cd, C.POINTER(ci)]
         lib.fbport_get_external_forces.restype = None
         lib.fbport_get_external_forces.argtypes = [vp, vp]
+    if kind == "ref":
+        lib.fbref_create_from_veg.restype = vp
+        lib.fbref_create_from_veg.argtypes = [C.c_char_p, ci, vp, cd, cd, cd]
+        lib.fbref_num_vertices.restype = ci
+        lib.fbref_num_vertices.argtypes = [vp]
+        lib.fbref_num_tets.restype = ci
+        lib.fbref_num_tets.argtypes = [vp]
+        lib.fbref_mesh.restype = None
+        lib.fbref_mesh.argtypes = [vp, vp, vp, vp, vp, vp]
     _loaded[kind] = lib
     return lib
 
@@ -85,15 +96,33 @@ def polar(F, tol=1e-6, kind="ref"):
 class Oracle:
     """One deformable model on the CPU checker; mirrors the methods of fembrain_b200.Simulation."""
 
-    def __init__(self, verts, tets, fixed_verts=(), E=1e7, nu=0.46, rho=1000.0, h=0.0333, damp_mass=0.0,
-                 damp_stiffness=0.01, kind="ref"):
+    def __init__(self, verts=None, tets=None, fixed_verts=(), E=1e7, nu=0.46, rho=1000.0, h=0.0333, damp_mass=0.0,
+                 damp_stiffness=0.01, kind="ref", materials=None, veg_path=None):
+        """materials = (E[nT], nu[nT], rho[nT]) arrays (port only); veg_path = let the reference's own .veg loader
+        build the mesh and its materials (ref only)."""
         self.kind = kind
         self._lib = _lib(kind)
         self._p = _PREFIX[kind]
-        v, t, fx = _f64(verts), _i32(tets), _i32(fixed_verts)
-        self.nV, self.nT = len(v), len(t)
-        self._h = self._fn("create")(self.nV, v.ctypes.data, self.nT, t.ctypes.data, E, nu, rho, len(fx),
-                                     fx.ctypes.data if len(fx) else None, h, damp_mass, damp_stiffness)
+        fx = _i32(fixed_verts)
+        if veg_path is not None:
+            assert kind == "ref", "only the compiled reference has the .veg loader"
+            self._h = self._lib.fbref_create_from_veg(str(veg_path).encode(), len(fx), fx.ctypes.data if len(fx) else None, h,
+                                                      damp_mass, damp_stiffness)
+            if not self._h:
+                raise RuntimeError("reference could not load " + str(veg_path))
+            self.nV, self.nT = self._lib.fbref_num_vertices(self._h), self._lib.fbref_num_tets(self._h)
+        else:
+            v, t = _f64(verts), _i32(tets)
+            self.nV, self.nT = len(v), len(t)
+            if materials is not None:
+                assert kind == "port", "per-element arrays: port only (the reference reads them from a .veg)"
+                me, mn, mr = (_f64(m) for m in materials)
+                self._h = self._lib.fbport_create_materials(self.nV, v.ctypes.data, self.nT, t.ctypes.data, me.ctypes.data, mn.ctypes.data,
+                                                            mr.ctypes.data, len(fx), fx.ctypes.data if len(fx) else None, h, damp_mass,
+                                                            damp_stiffness)
+            else:
+                self._h = self._fn("create")(self.nV, v.ctypes.data, self.nT, t.ctypes.data, E, nu, rho, len(fx),
+                                             fx.ctypes.data if len(fx) else None, h, damp_mass, damp_stiffness)
         if not self._h:
             raise RuntimeError("oracle create failed")
         self.r = self._fn("r")(self._h)
@@ -115,6 +144,14 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def mesh(self):
+        """(verts, tets, E, nu, rho) as the reference holds them after loading a .veg (ref only)."""
+        assert self.kind == "ref"
+        v, t = np.zeros((self.nV, 3)), np.zeros((self.nT, 4), np.int32)
+        E, nu, rho = np.zeros(self.nT), np.zeros(self.nT), np.zeros(self.nT)
+        self._lib.fbref_mesh(self._h, v.ctypes.data, t.ctypes.data, E.ctypes.data, nu.ctypes.data, rho.ctypes.data)
+        return v, t, E, nu, rho
 
     def _csr(self, name, n, nnz, values=True):
         ia, ja = np.zeros(n + 1, np.int32), np.zeros(max(nnz, 1), np.int32)[:nnz]

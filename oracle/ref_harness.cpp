@@ -25,6 +25,7 @@
 #include "generateMassMatrix.h"
 #include "polarDecomposition.h"
 #include "tetMesh.h"
+#include "volumetricMeshENuMaterial.h"
 #include "CGSolver.h"
 #undef protected
 #undef private
@@ -81,6 +82,48 @@ void *fbref_create(int nV, const double *verts, int nT, const int *tets, double 
       3 * nV, h, s->mass, s->forceModel, 0, (int)s->fixedDofs.size(),
       s->fixedDofs.empty() ? &dummy : &s->fixedDofs[0], dampM, dampK, 1, 1E-6, 1);
   return s;
+}
+
+/* The same chain, with the mesh and its materials read by the reference's own .veg loader
+ * (TetMesh(char*), volumetricMesh.cpp:45-535). */
+void *fbref_create_from_veg(const char *path, int nFixedVerts, const int *fixedVerts, double h, double dampM, double dampK) {
+  RefSim *s = new RefSim();
+  try {
+    s->mesh = new TetMesh((char *)path);
+  } catch (int) {
+    delete s;
+    return NULL;
+  }
+  s->nV = s->mesh->getNumVertices();
+  s->nT = s->mesh->getNumElements();
+  s->fem = new CorotationalLinearFEM(s->mesh);
+  s->forceModel = new CorotationalLinearFEMForceModel(s->fem);
+  GenerateMassMatrix::computeMassMatrix(s->mesh, &s->mass, true);
+  std::vector<int> fv(fixedVerts, fixedVerts + nFixedVerts);
+  std::sort(fv.begin(), fv.end());
+  s->fixedDofs.resize(3 * fv.size());
+  for (size_t i = 0; i < fv.size(); i++)
+    for (int k = 0; k < 3; k++) s->fixedDofs[3 * i + k] = 3 * fv[i] + k;
+  int dummy = 0;
+  s->integrator = new VolumeConservingIntegrator(3 * s->nV, h, s->mass, s->forceModel, 0, (int)s->fixedDofs.size(),
+                                                 s->fixedDofs.empty() ? &dummy : &s->fixedDofs[0], dampM, dampK, 1, 1E-6, 1);
+  return s;
+}
+
+int fbref_num_vertices(void *p) { return ((RefSim *)p)->nV; }
+int fbref_num_tets(void *p) { return ((RefSim *)p)->nT; }
+/* mesh as the reference holds it after loading: vertices, 0-based tets, per-element E / nu / density */
+void fbref_mesh(void *p, double *verts, int *tets, double *E, double *nu, double *rho) {
+  RefSim *s = (RefSim *)p;
+  for (int i = 0; i < s->nV; i++)
+    for (int k = 0; k < 3; k++) verts[3 * i + k] = (*s->mesh->getVertex(i))[k];
+  for (int el = 0; el < s->nT; el++) {
+    for (int k = 0; k < 4; k++) tets[4 * el + k] = s->mesh->getVertexIndex(el, k);
+    VolumetricMesh::ENuMaterial *m = downcastENuMaterial(s->mesh->getElementMaterial(el));
+    E[el] = m ? m->getE() : 0.0;
+    nu[el] = m ? m->getNu() : 0.0;
+    rho[el] = s->mesh->getElementDensity(el);
+  }
 }
 
 void fbref_destroy(void *p) {

@@ -30,6 +30,7 @@ typedef struct {
   double *x0; /* undeformedPositions, 3nV (corotationalLinearFEM.cpp:45-50) */
   int *tets;  /* 4nT */
   double rho, h, dampM, dampK;
+  const double *matE, *matNu, *matRho; /* optional per-element materials (fbport_create_materials) */
   double *lambda, *mu; /* per element (corotationalLinearFEM.cpp:55-68) */
   double *MInv;        /* 16 per element */
   double *K0;          /* 144 per element */
@@ -236,6 +237,8 @@ static void build_element_data(Port *s, double E_, double nu_) {
   s->K0 = (double *)malloc(sizeof(double) * 144 * (size_t)s->nT);
   for (int el = 0; el < s->nT; el++) {
     /* ENuMaterial::getLambda/getMu, VEGA/volumetricMesh/volumetricMeshENuMaterial.h:61-62 */
+    if (s->matE) E_ = s->matE[el];
+    if (s->matNu) nu_ = s->matNu[el];
     s->lambda[el] = (nu_ * E_) / ((1 + nu_) * (1 - 2 * nu_));
     s->mu[el] = E_ / (2 * (1 + nu_));
     const int *vt = s->tets + 4 * el;
@@ -283,7 +286,7 @@ static void build_mass(Port *s) {
   for (int el = 0; el < s->nT; el++) {
     const int *vt = s->tets + 4 * el;
     double vol = tet_volume(s->x0 + 3 * vt[0], s->x0 + 3 * vt[1], s->x0 + 3 * vt[2], s->x0 + 3 * vt[3]);
-    double factor = s->rho * vol / 20;
+    double factor = (s->matRho ? s->matRho[el] : s->rho) * vol / 20;
     for (int i = 0; i < 4; i++)
       for (int j = 0; j < 4; j++) {
         double entry = factor * mtx[4 * j + i];
@@ -353,10 +356,28 @@ static void build_system(Port *s) {
 
 static double *dalloc(size_t n) { return (double *)calloc(n ? n : 1, sizeof(double)); }
 
+static void *port_create(int nV, const double *verts, int nT, const int *tets, double E, double nu, double rho,
+                         const double *Ee, const double *nue, const double *rhoe, int nFixedVerts, const int *fixedVerts,
+                         double h, double dampM, double dampK);
+
 void *fbport_create(int nV, const double *verts, int nT, const int *tets, double E, double nu,
                     double rho, int nFixedVerts, const int *fixedVerts, double h, double dampM,
                     double dampK) {
+  return port_create(nV, verts, nT, tets, E, nu, rho, NULL, NULL, NULL, nFixedVerts, fixedVerts, h, dampM, dampK);
+}
+
+/* per-element ENU materials (what a .veg with several *MATERIAL / *REGION sections yields, volumetricMesh.cpp:45-535;
+ * arrays are only read during construction) */
+void *fbport_create_materials(int nV, const double *verts, int nT, const int *tets, const double *Ee, const double *nue,
+                              const double *rhoe, int nFixedVerts, const int *fixedVerts, double h, double dampM, double dampK) {
+  return port_create(nV, verts, nT, tets, 0, 0, 0, Ee, nue, rhoe, nFixedVerts, fixedVerts, h, dampM, dampK);
+}
+
+static void *port_create(int nV, const double *verts, int nT, const int *tets, double E, double nu, double rho,
+                         const double *Ee, const double *nue, const double *rhoe, int nFixedVerts, const int *fixedVerts,
+                         double h, double dampM, double dampK) {
   Port *s = (Port *)calloc(1, sizeof(Port));
+  s->matE = Ee; s->matNu = nue; s->matRho = rhoe;
   s->nV = nV; s->nT = nT; s->r = 3 * nV;
   s->rho = rho; s->h = h; s->dampM = dampM; s->dampK = dampK;
   s->x0 = (double *)malloc(sizeof(double) * 3 * (size_t)(nV ? nV : 1));
@@ -384,6 +405,7 @@ void *fbport_create(int nV, const double *verts, int nT, const int *tets, double
   s->buffer = dalloc(r); s->bufC = dalloc((size_t)s->nS);
   s->cr = dalloc((size_t)s->nS); s->cd = dalloc((size_t)s->nS); s->cq = dalloc((size_t)s->nS);
   s->invD = dalloc((size_t)s->nS);
+  s->matE = s->matNu = s->matRho = NULL;
   return s;
 }
 

@@ -1,0 +1,118 @@
+"""Mesh ingest: fb_veg_load against the reference's own .veg loader (oracle/_ref, when built) and against a
+plain reading of the file; covers several materials / sets / regions, region override order, unassigned elements, the
+loader's separator rule and error codes.  Host-only: runs without a GPU."""
+import numpy as np
+import pytest
+
+import fembrain_b200 as fb
+from fembrain_b200 import api, meshes
+from tests import cases
+
+
+def two_region_file(tmp_path, sep=" "):
+    v, t, fixed, _ = cases.cube_case(4)
+    nT = len(t)
+    path = tmp_path / "two_regions.veg"
+    meshes.write_veg(path, v, t, materials=[("SOFT", 1000.0, 1e7, 0.46), ("STIFF", 1200.0, 3e7, 0.3)],
+                     sets={"top": range(nT // 2, nT), "core": range(10, 20)},
+                     regions=[("allElements", "SOFT"), ("top", "STIFF"), ("core", "SOFT")], sep=sep)
+    E = np.full(nT, 1e7); nu = np.full(nT, 0.46); rho = np.full(nT, 1000.0)
+    E[nT // 2:], nu[nT // 2:], rho[nT // 2:] = 3e7, 0.3, 1200.0
+    E[10:20], nu[10:20], rho[10:20] = 1e7, 0.46, 1000.0  # later region wins
+    return path, v, t, fixed, E, nu, rho
+
+
+@pytest.mark.parametrize("sep", [" ", ","])  # one separator character, as the reference loader requires
+def test_veg_load_materials_sets_regions(tmp_path, sep):
+    path, v, t, fixed, E, nu, rho = two_region_file(tmp_path, sep)
+    lv, lt, lE, lnu, lrho = fb.veg_load(path)
+    assert np.array_equal(lv, v) and np.array_equal(lt, t)
+    assert np.array_equal(lE, E) and np.array_equal(lnu, nu) and np.array_equal(lrho, rho)
+    if sep == " ":
+        pv, pt = meshes.read_veg(str(path))
+        assert np.array_equal(pv, v) and np.array_equal(pt, t)
+
+
+def test_veg_load_matches_reference_loader(tmp_path, ref_oracle):
+    path, v, t, fixed, E, nu, rho = two_region_file(tmp_path)
+    ref = ref_oracle.Oracle(veg_path=path, fixed_verts=fixed, kind="ref")
+    rv, rt, rE, rnu, rrho = ref.mesh()
+    lv, lt, lE, lnu, lrho = fb.veg_load(path)
+    for a, b in ((lv, rv), (lt, rt), (lE, rE), (lnu, rnu), (lrho, rrho)):
+        assert np.array_equal(a, b)
+    # elements no region covers take the LAST material
+    p2 = tmp_path / "partial.veg"
+    meshes.write_veg(p2, v, t, materials=[("A", 900.0, 2e6, 0.4), ("B", 1100.0, 5e6, 0.45)], sets={"some": range(0, 30)},
+                     regions=[("some", "A")])
+    ref2 = ref_oracle.Oracle(veg_path=p2, fixed_verts=fixed, kind="ref")
+    for a, b in zip(fb.veg_load(p2), ref2.mesh()):
+        assert np.array_equal(a, b)
+    # no material at all: the reference's (argument-swapped) default material
+    p3 = tmp_path / "bare.veg"
+    meshes.write_veg(p3, v, t)
+    l3 = fb.veg_load(p3)
+    assert np.all(l3[2] == 0.45) and np.all(l3[3] == 1000) and np.all(l3[4] == 1e9)
+    r3 = ref_oracle.Oracle(veg_path=p3, fixed_verts=fixed, kind="ref").mesh()
+    for a, b in zip(l3[2:], r3[2:]):
+        assert np.array_equal(a, b)
+
+
+def test_veg_errors(tmp_path):
+    lib = fb.load_library()
+    with pytest.raises(fb.FemBrainError) as e:
+        fb.veg_load(tmp_path / "missing.veg")
+    assert e.value.status == api.FB_ERR_INVALID_ARGUMENT
+    bad = tmp_path / "cubic.veg"
+    bad.write_text("*VERTICES\n1 3 0 0\n1 0 0 0\n*ELEMENTS\nCUBIC\n0 8 0\n")
+    with pytest.raises(fb.FemBrainError) as e:
+        fb.veg_load(bad)
+    assert e.value.status == api.FB_ERR_NOT_SUPPORTED
+    short = tmp_path / "short.veg"
+    short.write_text("*VERTICES\n2 3 0 0\n1 0 0 0\n*ELEMENTS\nTET\n0 4 0\n")
+    with pytest.raises(fb.FemBrainError) as e:
+        fb.veg_load(short)
+    assert e.value.status == api.FB_ERR_BAD_MESH
+    assert lib.fb_veg_load(None, None, None, None, None, None, None, None) == api.FB_ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.gpu
+def test_create_from_veg_matches_reference_bit_exact(tmp_path, port_oracle):
+    """Per-element materials through the whole setup: K, f and the mass matrix bit-exact against the port oracle fed the same
+    arrays, and — where oracle/_ref is present — against the reference that loaded the same file itself."""
+    path, v, t, fixed, E, nu, rho = two_region_file(tmp_path)
+    sim = fb.Simulation(veg_path=path, fixed_verts=fixed)
+    ora = port_oracle.Oracle(v, t, fixed, kind="port", materials=(E, nu, rho))
+    u = cases.perturbation(v, 1.0, 2)
+    checkers = [ora]
+    if port_oracle.available("ref"):
+        checkers.append(port_oracle.Oracle(veg_path=path, fixed_verts=fixed, kind="ref"))
+    f, K = sim.force_and_matrix(u)
+    M = sim.M_csr()[2]
+    for o in checkers:
+        of, oK = o.force_and_matrix(u)
+        assert np.array_equal(K, oK) and np.array_equal(f, of)
+        assert np.array_equal(M, o.M_csr()[2])
+    load = cases.point_load(sim.r, int(np.argmax(v[:, 1] * 1000 + v[:, 0])))
+    for s in [sim] + checkers:
+        s.set_external_forces(load)
+        s.do_timestep()
+    for o in checkers:
+        assert np.array_equal(sim.K_values(), o.K_values()) and np.array_equal(sim.rhs(), o.rhs())
+        assert cases.rel_err(sim.get_state()[0], o.get_state()[0]) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_export_positions_float4_matches_apply_vertex_deformations():
+    """ApplyVertexDeformations (Polygonizer.cl:1417-1427): float4 rest + float4(displacement, 0), bit-exact in float."""
+    v, t, fixed, load = cases.cube_case(5)
+    sim = fb.Simulation(v, t, fixed)
+    sim.set_external_forces(cases.point_load(sim.r, load))
+    sim.do_timestep()
+    q = sim.get_state()[0].reshape(-1, 3)
+    rest = np.concatenate([v.astype(np.float32) * 1.5, np.ones((len(v), 1), np.float32)], axis=1)  # the polygonizer's own rest buffer
+    out = sim.export_positions_float4(rest)
+    disp = np.concatenate([q.astype(np.float32), np.zeros((len(v), 1), np.float32)], axis=1)
+    assert np.array_equal(out, rest + disp)
+    out2 = sim.export_positions_float4(None, count=17)
+    exp = np.concatenate([v[:17].astype(np.float32), np.ones((17, 1), np.float32)], axis=1) + disp[:17]
+    assert np.array_equal(out2, exp)

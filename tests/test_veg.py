@@ -40,13 +40,16 @@ def test_veg_load_matches_reference_loader(tmp_path, ref_oracle):
     lv, lt, lE, lnu, lrho = fb.veg_load(path)
     for a, b in ((lv, rv), (lt, rt), (lE, rE), (lnu, rnu), (lrho, rrho)):
         assert np.array_equal(a, b)
-    # elements no region covers take the LAST material
+    # Elements no region covers: the reference appends Region(numMaterials-1, defaultSet) (volumetricMesh.cpp:521-529) but never
+    # re-runs PropagateRegionsToElements, so elementMaterial[el] stays == numMaterials and getElementMaterial reads one past
+    # the materials array (undefined; it crashes or not depending on the heap).  fb_veg_load gives such elements the LAST
+    # material, which is what that appended region says; the reference cannot be run on this file.
     p2 = tmp_path / "partial.veg"
     meshes.write_veg(p2, v, t, materials=[("A", 900.0, 2e6, 0.4), ("B", 1100.0, 5e6, 0.45)], sets={"some": range(0, 30)},
                      regions=[("some", "A")])
-    ref2 = ref_oracle.Oracle(veg_path=p2, fixed_verts=fixed, kind="ref")
-    for a, b in zip(fb.veg_load(p2), ref2.mesh()):
-        assert np.array_equal(a, b)
+    l2 = fb.veg_load(p2)
+    assert np.all(l2[2][:30] == 2e6) and np.all(l2[3][:30] == 0.4) and np.all(l2[4][:30] == 900.0)
+    assert np.all(l2[2][30:] == 5e6) and np.all(l2[3][30:] == 0.45) and np.all(l2[4][30:] == 1100.0)
     # no material at all: the reference's (argument-swapped) default material
     p3 = tmp_path / "bare.veg"
     meshes.write_veg(p3, v, t)

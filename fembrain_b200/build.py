@@ -23,6 +23,7 @@ UNITS = {
     "fb_api.cu": [],
     "fb_setup.cu": [],
     "fb_fem.cu": ["-fmad=false"],
+    "fb_assembly.cu": ["-fmad=false"],
     "fb_pcg.cu": [],
     "fb_pcg_persistent.cu": [],
     "fb_dist.cu": [],

@@ -105,7 +105,8 @@ void free_all(fb_context *c) {
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,
-                  c->contact_dev, c->ctaRows, c->pers_prof};
+                  c->contact_dev, c->ctaRows, c->pers_prof, c->ga_incp, c->ga_inc, c->ga_ctaV, c->ga_csrc, c->ga_border,
+                  c->ga_sblk, c->ga_erec, c->ga_xu};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -263,8 +264,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   CR(fb_dev_alloc(c, &c->T, (size_t)c->nnzK));
   CR(fb_dev_alloc(c, &c->Keff, (size_t)c->nnzK));
   if (p.keep_raw_stiffness) CR(fb_dev_alloc(c, &c->Kraw, (size_t)c->nnzK));
-  CR(fb_dev_alloc(c, &c->scrK, 144 * (size_t)nT));
-  CR(fb_dev_alloc(c, &c->scrF, 12 * (size_t)nT));
+  CR(fb_build_gather_plan(c));  // two-phase scratch (1248 B/tet) is allocated on first use, only if this plan is off
   double **vecs[] = {&c->q, &c->qvel, &c->qaccel, &c->fext, &c->fint, &c->qres, &c->rhs, &c->x, &c->res, &c->dir, &c->Ad, &c->invD, &c->tmp};
   for (double **v : vecs) {
     CR(fb_dev_alloc(c, v, (size_t)c->r));

@@ -305,6 +305,9 @@ int fb_launch_mass(fb_context *c) {
 
 int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effective) {
   if (c->nT == 0) return FB_OK;
+  if (c->ga_ctas > 0) return fb_launch_assembly_gather(c, u, Kraw, effective);
+  if (!c->scrK) FB_TRY(fb_dev_alloc(c, &c->scrK, 144 * (size_t)c->nT));
+  if (!c->scrF) FB_TRY(fb_dev_alloc(c, &c->scrF, 12 * (size_t)c->nT));
   k_element<<<grid_for(c->nT, EL_TB), EL_TB, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance,
                                                               c->scrK, c->scrF);
   ReduceParams p;

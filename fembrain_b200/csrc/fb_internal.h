@@ -93,6 +93,17 @@ struct fb_context {
   // per-element scratch of the two-phase deterministic assembly
   double *scrK;  // [16][nT][9]
   double *scrF;  // [12][nT]
+  // row-gather assembly (fb_assembly.cu; default): incidences per vertex, CTA ranges, CTA-local contribution slots,
+  // per-CTA block order by decreasing list length, per-element rotations.  ga_ctas == 0 -> two-phase path (scrK/scrF).
+  int ga_ctas, ga_cfg;
+  int *ga_incp;              // [nV+1]
+  unsigned int *ga_inc;      // [4 nT] element*4 + i, ascending per vertex
+  int *ga_ctaV;              // [ga_ctas+1] first vertex of every CTA
+  unsigned short *ga_csrc;   // [16 nT] shared-memory slot of each contribution, in seg/src order
+  unsigned short *ga_sblk;   // [16 nT] CTA-local block (| i << 12) of each slot, in slot order
+  int *ga_border;            // [nB]
+  double *ga_erec;           // [nT][24] element records: R[9] (rewritten every assembly), G[12], volume, lambda, mu
+  double *ga_xu;             // [nV][6] rest position and displacement side by side (rewritten every assembly)
 
   // integrator state and work vectors, all [r]
   double *q, *qvel, *qaccel, *fext, *fint, *qres, *rhs, *x, *res, *dir, *Ad, *invD, *tmp;
@@ -160,6 +171,9 @@ int fb_launch_rhs(fb_context *c);
 int fb_launch_spmv_exact(fb_context *c, const double *A, const double *x, double *y);
 int fb_launch_state_update(fb_context *c);
 int fb_launch_expand_element(fb_context *c, double *minv16_dev, double *k0_dev, int el0, int n);
+// ---- fb_assembly.cu (compiled with -fmad=false) -----------------------------------------------------
+int fb_build_gather_plan(fb_context *c);  // after fb_build_topology
+int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool effective);
 // ---- fb_pcg.cu -------------------------------------------------------------------------------------
 int fb_pcg_solve(fb_context *c, double eps, int max_it);  // solves Keff x = rhs (masked), x0 = 0
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked);

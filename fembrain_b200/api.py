@@ -97,7 +97,7 @@ def load_library():
         "fb_deformable_set_edge_list": (ci, [vp, ci, vp, ci]),
         "fb_force_assembly_seconds": (cd, [vp]), "fb_system_solve_seconds": (cd, [vp]), "fb_step_seconds": (cd, [vp]),
         "fb_last_cg_iterations": (ci, [vp]), "fb_last_cg_residual_ratio": (cd, [vp]),
-        "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]),
+        "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]), "fb_trim_memory": (ci, []),
         "fb_get_stiffness_csr": (ci, [vp, vp, vp]), "fb_get_mass_csr": (ci, [vp, vp, vp, vp]),
         "fb_get_system_csr": (ci, [vp, vp, vp, vp]), "fb_get_element_maps": (ci, [vp, vp, vp]),
         "fb_get_element_data": (ci, [vp, vp, vp]), "fb_get_super_maps": (ci, [vp, vp, vp]),
@@ -176,6 +176,11 @@ def plan_partition(num_vertices, tets, world, rank):
         "send": {int(nbr[i]): sg[so[i]:so[i + 1]] for i in range(k)},
         "recv": {int(nbr[i]): rg[ro[i]:ro[i + 1]] for i in range(k)},
     }
+
+
+def trim_memory():
+    """Give the device memory that destroyed contexts left in the stream-ordered pool back to the driver."""
+    return load_library().fb_trim_memory()
 
 
 def veg_load(path):

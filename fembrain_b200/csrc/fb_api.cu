@@ -105,8 +105,7 @@ void free_all(fb_context *c) {
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,
-                  c->contact_dev, c->ctaRows, c->pers_prof, c->ga_incp, c->ga_inc, c->ga_ctaV, c->ga_csrc, c->ga_border,
-                  c->ga_sblk, c->ga_erec, c->ga_xu};
+                  c->contact_dev, c->ctaRows, c->pers_prof, c->ga_incp, c->ga_ctaV, c->ga_lists, c->ga_erec, c->ga_xu};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -225,6 +224,12 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
 #define CR(call) do { st = (call); if (st != FB_OK) { free_all(c); return st; } } while (0)
 #define CRC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fb_set_error("%s -> %s", #call, cudaGetErrorString(e__)); free_all(c); return e__ == cudaErrorMemoryAllocation ? FB_ERR_OUT_OF_MEMORY : FB_ERR_CUDA; } } while (0)
   CRC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {  // keep freed device memory in the default pool (see fb_dev_alloc); fb_trim_memory() releases it
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, p.device) != cudaSuccess ||
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) cudaGetLastError();
+  }
   for (auto &e : c->ev) CRC(cudaEventCreate(&e));
   for (auto &e : c->evChunk) CRC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CR(fb_dev_alloc(c, &c->x0, 3 * (size_t)nV));
@@ -267,7 +272,9 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   CR(fb_build_gather_plan(c));  // two-phase scratch (1248 B/tet) is allocated on first use, only if this plan is off
   double **vecs[] = {&c->q, &c->qvel, &c->qaccel, &c->fext, &c->fint, &c->qres, &c->rhs, &c->x, &c->res, &c->dir, &c->Ad, &c->invD, &c->tmp};
   for (double **v : vecs) {
-    CR(fb_dev_alloc(c, v, (size_t)c->r));
+    // the search direction is the one vector a neighbour rank writes into (halo push over CUDA IPC): not from the pool
+    if (v == &c->dir) CR(fb_dev_alloc_plain(c, v, (size_t)c->r));
+    else CR(fb_dev_alloc(c, v, (size_t)c->r));
     CRC(cudaMemsetAsync(*v, 0, sizeof(double) * (size_t)(c->r ? c->r : 1), c->stream));
   }
   CR(fb_dev_alloc(c, &c->sc, 1));
@@ -839,6 +846,16 @@ int fb_bench_assembly(fb_context *c, int repeats, double *sec) {
   float ms = 0;
   FB_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]));
   *sec = 1e-3 * ms / repeats;
+  return FB_OK;
+}
+int fb_trim_memory(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return FB_ERR_NO_DEVICE; }
+  for (int d = 0; d < ndev; d++) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
+  cudaGetLastError();
   return FB_OK;
 }
 int fb_bench_cg_iteration(fb_context *c, int repeats, double *sec) {

@@ -281,7 +281,7 @@ static int setup_p2p(fb_context *c) {
     cudaFree(flag0);
     if (r0 != ncclSuccess || !all) return FB_OK;
   }
-  FB_TRY(fb_dev_alloc(c, &d->comm, (size_t)FB_COMM_WORDS));
+  FB_TRY(fb_dev_alloc_plain(c, &d->comm, (size_t)FB_COMM_WORDS));  // exported with CUDA IPC
   FB_TRY(fb_dev_alloc(c, &d->pushTicket, 1));
   FB_TRY(fb_dev_alloc(c, &d->remoteIdx, (size_t)d->sendOff[d->nNbr]));
   FB_CUDA(cudaMemsetAsync(d->comm, 0, sizeof(double) * FB_COMM_WORDS, st));

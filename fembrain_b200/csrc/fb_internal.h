@@ -93,15 +93,12 @@ struct fb_context {
   // per-element scratch of the two-phase deterministic assembly
   double *scrK;  // [16][nT][9]
   double *scrF;  // [12][nT]
-  // row-gather assembly (fb_assembly.cu; default): incidences per vertex, CTA ranges, CTA-local contribution slots,
-  // per-CTA block order by decreasing list length, per-element rotations.  ga_ctas == 0 -> two-phase path (scrK/scrF).
+  // row-gather assembly (fb_assembly.cu; default): per-CTA index lists, element and vertex records.
+  // ga_ctas == 0 -> two-phase path (scrK/scrF, allocated on first use).
   int ga_ctas, ga_cfg;
-  int *ga_incp;              // [nV+1]
-  unsigned int *ga_inc;      // [4 nT] element*4 + i, ascending per vertex
+  int *ga_incp;              // [nV+1] incidence (vertex, element, i) counts, prefix sum
   int *ga_ctaV;              // [ga_ctas+1] first vertex of every CTA
-  unsigned short *ga_csrc;   // [16 nT] shared-memory slot of each contribution, in seg/src order
-  unsigned short *ga_sblk;   // [16 nT] CTA-local block (| i << 12) of each slot, in slot order
-  int *ga_border;            // [nB]
+  unsigned char *ga_lists;   // [ga_ctas] GaLists blobs
   double *ga_erec;           // [nT][24] element records: R[9] (rewritten every assembly), G[12], volume, lambda, mu
   double *ga_xu;             // [nV][6] rest position and displacement side by side (rewritten every assembly)
 
@@ -201,11 +198,30 @@ void fb_dist_next_solve(fb_context *c);
 unsigned int fb_dist_halo_mask(const fb_context *c);
 int fb_dist_halo_push(fb_context *c, const double *vec, unsigned long long epoch);
 
+// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync on the context's stream); the
+// pool's release threshold is raised at the first fb_create, so destroy -> create cycles (re-setup after a cut,
+// DEF/Deformable.cpp:127-220 via cutCompleted) reuse memory instead of paying cudaMalloc/cudaFree again
+// (fb_create at 1M tets: 75-200 ms with cudaMalloc, profiles/r01_setup_time.txt).  fb_trim_memory() gives it back.
+// Buffers exported with CUDA IPC (peer-memory exchange) cannot live in a pool: fb_dev_alloc_plain.
 template <typename T>
 static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {
   size_t bytes = (n ? n : 1) * sizeof(T);
+  cudaError_t e = cudaMallocAsync((void **)p, bytes, c->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fb_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    *p = nullptr;
+    return FB_ERR_OUT_OF_MEMORY;
+  }
+  c->bytes += bytes;
+  return FB_OK;
+}
+template <typename T>
+static inline int fb_dev_alloc_plain(fb_context *c, T **p, size_t n) {
+  size_t bytes = (n ? n : 1) * sizeof(T);
   cudaError_t e = cudaMalloc((void **)p, bytes);
   if (e != cudaSuccess) {
+    cudaGetLastError();
     fb_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     *p = nullptr;
     return FB_ERR_OUT_OF_MEMORY;
@@ -213,3 +229,7 @@ static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {
   c->bytes += bytes;
   return FB_OK;
 }
+// temporaries of the setup code: stream-ordered, freed with fb_tmp_free on the same stream
+template <typename T>
+static inline cudaError_t fb_tmp_alloc(cudaStream_t st, T **p, size_t bytes) { return cudaMallocAsync((void **)p, bytes ? bytes : 1, st); }
+static inline void fb_tmp_free(cudaStream_t st, void *p) { if (p) cudaFreeAsync(p, st); }

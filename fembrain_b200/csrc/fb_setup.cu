@@ -80,7 +80,7 @@ int fb_build_topology(fb_context *c) {
   void *tmp = nullptr;
   int status = FB_OK;
   auto cleanup = [&]() {
-    cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(blk); cudaFree(err); cudaFree(rowCount); cudaFree(tmp);
+    for (void *q : {(void *)keys, (void *)keys2, (void *)vals, (void *)vals2, (void *)blk, (void *)err, (void *)rowCount, tmp}) fb_tmp_free(st, q);
   };
 #define SETUP_CUDA(call)                                                                   \
   do {                                                                                     \
@@ -92,13 +92,13 @@ int fb_build_topology(fb_context *c) {
     }                                                                                      \
   } while (0)
 
-  SETUP_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * (n ? n : 1)));
-  SETUP_CUDA(cudaMalloc(&keys2, sizeof(unsigned long long) * (n ? n : 1)));
-  SETUP_CUDA(cudaMalloc(&vals, sizeof(unsigned int) * (n ? n : 1)));
-  SETUP_CUDA(cudaMalloc(&vals2, sizeof(unsigned int) * (n ? n : 1)));
-  SETUP_CUDA(cudaMalloc(&blk, sizeof(int) * (n ? n : 1)));
-  SETUP_CUDA(cudaMalloc(&err, sizeof(int) * 2));
-  SETUP_CUDA(cudaMalloc(&rowCount, sizeof(int) * ((size_t)c->nV + 1)));
+  SETUP_CUDA(fb_tmp_alloc(st, &keys, sizeof(unsigned long long) * (n ? n : 1)));
+  SETUP_CUDA(fb_tmp_alloc(st, &keys2, sizeof(unsigned long long) * (n ? n : 1)));
+  SETUP_CUDA(fb_tmp_alloc(st, &vals, sizeof(unsigned int) * (n ? n : 1)));
+  SETUP_CUDA(fb_tmp_alloc(st, &vals2, sizeof(unsigned int) * (n ? n : 1)));
+  SETUP_CUDA(fb_tmp_alloc(st, &blk, sizeof(int) * (n ? n : 1)));
+  SETUP_CUDA(fb_tmp_alloc(st, &err, sizeof(int) * 2));
+  SETUP_CUDA(fb_tmp_alloc(st, &rowCount, sizeof(int) * ((size_t)c->nV + 1)));
   SETUP_CUDA(cudaMemsetAsync(err, 0, sizeof(int) * 2, st));
   SETUP_CUDA(cudaMemsetAsync(rowCount, 0, sizeof(int) * ((size_t)c->nV + 1), st));
 
@@ -127,7 +127,7 @@ int fb_build_topology(fb_context *c) {
   SETUP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, dk, dv, (int64_t)n, 0, 32 + vbits, st));
   SETUP_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, blk, blk, (int64_t)(n > (size_t)c->nV + 1 ? n : (size_t)c->nV + 1), st));
   if (tb2 > tmpBytes) tmpBytes = tb2;
-  SETUP_CUDA(cudaMalloc(&tmp, tmpBytes ? tmpBytes : 1));
+  SETUP_CUDA(fb_tmp_alloc(st, &tmp, tmpBytes ? tmpBytes : 1));
   if (n) {
     SETUP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, dk, dv, (int64_t)n, 0, 32 + vbits, st));
     c->launches += 4;

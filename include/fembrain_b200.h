@@ -173,6 +173,11 @@ int fb_last_cg_iterations(const fb_context *ctx);
 double fb_last_cg_residual_ratio(const fb_context *ctx); /* rho_final / rho_0 (M^-1-weighted, squared) */
 long long fb_kernel_launches(const fb_context *ctx);     /* kernels of this library launched so far on this context */
 size_t fb_device_bytes(const fb_context *ctx);           /* device memory held by the context */
+/* Contexts take device memory from the device's stream-ordered pool and fb_destroy returns it there, so that a
+ * destroy -> create cycle (the reference's full re-setup after a cut: cutCompleted -> syncForceModel,
+ * main.cpp:614-617, DEF/Deformable.cpp:127-220) does not pay for allocation again.  This gives unused pool memory
+ * back to the driver. */
+int fb_trim_memory(void);
 
 /* ---- inspection hooks for parity (outputs are host buffers sized by the fb_nnz_ / fb_num_ calls) -
  * CSR in the layout of SparseMatrix::GenerateCompressedRowMajorFormat (sparseMatrix.cpp:1151-1175). */

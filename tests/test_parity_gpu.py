@@ -123,3 +123,53 @@ def test_converged_displacement_1e8(port_oracle, name):
     # SpMV on the constrained system
     y, oy = sim.sys_spmv(ox), ora.sys_spmv(ox)
     assert cases.rel_err(y, oy) <= 1e-13
+
+
+def _hub_mesh(n, seed=5):
+    """n tetrahedra that share ONE vertex (the hub) and nothing else: a vertex with n incident elements."""
+    rng = np.random.default_rng(seed)
+    verts = [np.zeros(3)]
+    tets = []
+    for k in range(n):
+        d = rng.standard_normal(3)
+        d /= np.linalg.norm(d)
+        a = np.cross(d, rng.standard_normal(3))
+        a /= np.linalg.norm(a)
+        b = np.cross(d, a)
+        base = len(verts)
+        verts += [d + 0.3 * a, d + 0.3 * b, 1.4 * d - 0.2 * a]
+        tets.append([0, base, base + 1, base + 2])
+    return np.array(verts), np.array(tets, np.int32), np.array([1, 2, 3], np.int32)
+
+
+@pytest.mark.parametrize("n", [20, 150, 230, 300])  # 128 / 192 / 256 incidences per CTA, then the two-phase path
+def test_assembly_paths_by_vertex_valence_bit_exact(port_oracle, n):
+    v, t, fixed = _hub_mesh(n)
+    sim, ora = _mk(port_oracle, v, t, fixed)
+    u = 0.05 * np.random.default_rng(n).standard_normal(v.size)
+    f, K = sim.force_and_matrix(u)
+    of, oK = ora.force_and_matrix(u)
+    assert np.array_equal(K, oK) and np.array_equal(f, of)
+    for s in (sim, ora):
+        s.set_state(u, np.zeros_like(u))
+        s.set_external_forces(cases.point_load(sim.r, 5))
+        assert s.do_timestep() == 0
+    assert np.array_equal(sim.K_values(), ora.K_values()) and np.array_equal(sim.rhs(), ora.rhs())
+    assert np.array_equal(sim.internal_forces(), ora.internal_forces())
+
+
+@pytest.mark.parametrize("env", [{"FEMBRAIN_B200_ASSEMBLY": "twophase"}, {"FEMBRAIN_B200_GA_CAP": "192"}, {"FEMBRAIN_B200_GA_CAP": "256"}])
+def test_assembly_variants_identical_on_a_cube(port_oracle, env, monkeypatch):
+    """Every assembly configuration (two-phase scratch path; row-gather at 128/192/256 incidences per CTA) produces the same bits."""
+    for k, val in env.items():
+        monkeypatch.setenv(k, val)
+    v, t, fixed = cases.cube_case(9)[:3]
+    sim, ora = _mk(port_oracle, v, t, fixed)
+    u = cases.perturbation(v, 2.0, 9)
+    f, K = sim.force_and_matrix(u)
+    of, oK = ora.force_and_matrix(u)
+    assert np.array_equal(K, oK) and np.array_equal(f, of)
+    for s in (sim, ora):
+        s.set_state(u, np.zeros_like(u))
+        assert s.do_timestep() == 0
+    assert np.array_equal(sim.K_values(), ora.K_values()) and np.array_equal(sim.rhs(), ora.rhs())

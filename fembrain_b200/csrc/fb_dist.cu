@@ -24,7 +24,6 @@
 #include "fb_internal.h"
 #include "fb_pcg_common.cuh"
 
-#define FB_MAX_NBR 8
 
 struct FbDist {
   ncclComm_t ncomm;
@@ -46,6 +45,9 @@ struct FbDist {
   double *peerDir[FB_MAX_NBR];       // neighbours' search-direction vectors mapped here
   int *remoteIdx;                    // device: neighbour-local vertex index of every send entry
   unsigned int *pushTicket;          // device
+  unsigned char *pushFlag;           // device [nV]: vertex is in some send list
+  int *pushPtr;                      // device [nV+1]
+  int2 *pushEnt;                     // device: (neighbour slot, neighbour-local vertex) per send entry, by vertex
   unsigned long long solveCount;
   void *opened[FB_MAX_RANKS + FB_MAX_NBR];
   int nOpened;
@@ -260,6 +262,16 @@ int fb_dist_halo_push(fb_context *c, const double *vec, unsigned long long epoch
   return FB_OK;
 }
 
+void fb_dist_push_args(fb_context *c, FbPushArgs *out, unsigned long long epoch) {
+  memset(out, 0, sizeof(*out));
+  FbDist *d = c->dist;
+  if (!d || !d->p2p || d->nNbr == 0) return;
+  out->nNbr = d->nNbr;
+  for (int i = 0; i < d->nNbr; i++) { out->nbrRank[i] = d->nbrRank[i]; out->peerVec[i] = d->peerDir[i]; }
+  out->pushFlag = d->pushFlag; out->pushPtr = d->pushPtr; out->pushEnt = d->pushEnt;
+  out->epoch = epoch;
+}
+
 // Peer mappings for the exchange above: comm blocks of all ranks, `dir` vectors of the neighbours, and for every send
 // entry the neighbour's local index of that vertex (the neighbour's recv list, which mirrors this rank's send list).
 // Any failure leaves p2p = 0 and the context on the NCCL path.
@@ -333,6 +345,30 @@ static int setup_p2p(fb_context *c) {
   cudaStreamSynchronize(st);
   cudaFree(flag);
   d->p2p = ok && agreed;
+  if (d->p2p) {  // send entries regrouped by local vertex for the push fused into k_direction
+    const int nS = d->sendOff[d->nNbr];
+    std::vector<int> sIdx((size_t)nS), rIdx((size_t)nS);
+    if (nS) {
+      FB_CUDA(cudaMemcpyAsync(sIdx.data(), d->sendIdx, sizeof(int) * (size_t)nS, cudaMemcpyDeviceToHost, st));
+      FB_CUDA(cudaMemcpyAsync(rIdx.data(), d->remoteIdx, sizeof(int) * (size_t)nS, cudaMemcpyDeviceToHost, st));
+      FB_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<int> ptr((size_t)c->nV + 1, 0);
+    std::vector<unsigned char> flag((size_t)c->nV, 0);
+    for (int k = 0; k < nS; k++) { ptr[(size_t)sIdx[k] + 1]++; flag[sIdx[k]] = 1; }
+    for (int v = 0; v < c->nV; v++) ptr[(size_t)v + 1] += ptr[v];
+    std::vector<int2> ent((size_t)(nS ? nS : 1));
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int j = 0; j < d->nNbr; j++)
+      for (int k = d->sendOff[j]; k < d->sendOff[j + 1]; k++) ent[(size_t)fill[sIdx[k]]++] = make_int2(j, rIdx[k]);
+    FB_TRY(fb_dev_alloc(c, &d->pushFlag, (size_t)c->nV));
+    FB_TRY(fb_dev_alloc(c, &d->pushPtr, (size_t)c->nV + 1));
+    FB_TRY(fb_dev_alloc(c, &d->pushEnt, (size_t)nS));
+    FB_CUDA(cudaMemcpyAsync(d->pushFlag, flag.data(), flag.size(), cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaMemcpyAsync(d->pushPtr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, st));
+    if (nS) FB_CUDA(cudaMemcpyAsync(d->pushEnt, ent.data(), sizeof(int2) * (size_t)nS, cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+  }
   return FB_OK;
 }
 
@@ -394,6 +430,9 @@ void fb_dist_destroy(fb_context *c) {
   if (d->comm) cudaFree(d->comm);
   if (d->pushTicket) cudaFree(d->pushTicket);
   if (d->remoteIdx) cudaFree(d->remoteIdx);
+  if (d->pushFlag) cudaFree(d->pushFlag);
+  if (d->pushPtr) cudaFree(d->pushPtr);
+  if (d->pushEnt) cudaFree(d->pushEnt);
   if (d->ncomm) ncclCommDestroy(d->ncomm);
   delete d;
   c->dist = nullptr;
@@ -488,7 +527,7 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
   FB_TRY(fb_create_local(&c, nLV, lx.data(), nLT, lt.data(), (int)cd.size(), cd.data(), nullptr, nullptr, nullptr, prm));
   FbDist *d = new FbDist();
   d->ncomm = nullptr; d->sendIdx = d->recvIdx = nullptr; d->sendBuf = d->recvBuf = nullptr; d->hostStage = nullptr;
-  d->p2p = 0; d->comm = nullptr; d->remoteIdx = nullptr; d->pushTicket = nullptr; d->solveCount = 0; d->nOpened = 0;
+  d->p2p = 0; d->comm = nullptr; d->remoteIdx = nullptr; d->pushTicket = nullptr; d->pushFlag = nullptr; d->pushPtr = nullptr; d->pushEnt = nullptr; d->solveCount = 0; d->nOpened = 0;
   d->rank = rank; d->world = world; d->nV_global = nV; d->nT_global = nT;
   d->vbeg = pl.bounds[rank]; d->vend = pl.bounds[rank + 1];
   d->l2g = pl.l2g;
@@ -506,6 +545,26 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
     d->recvOff[i + 1] = (int)rIdx.size();
   }
   c->dist = d;
+  {  // rows the solver visits: owned rows only, those that read ghost columns (= the send lists) last (FbRowSegs)
+    int lo = 0, hi = nLV;
+    while (lo < nLV && !d->owned[lo]) lo++;
+    while (hi > lo && !d->owned[hi - 1]) hi--;
+    bool contiguous = true;
+    for (int i = lo; i < hi; i++) contiguous &= (d->owned[i] != 0);
+    if (!contiguous) { fb_set_error("owned rows are not contiguous in the local numbering"); fb_destroy(c); return FB_ERR_INVALID_ARGUMENT; }
+    std::vector<unsigned char> cut((size_t)nLV, 0);
+    for (size_t k = 0; k < sIdx.size(); k++) cut[sIdx[k]] = 1;
+    int bestBeg = lo, bestEnd = lo, runBeg = lo;  // longest run of rows that read no ghost column
+    for (int i = lo; i <= hi; i++) {
+      if (i == hi || cut[i]) {
+        if (i - runBeg > bestEnd - bestBeg) { bestBeg = runBeg; bestEnd = i; }
+        runBeg = i + 1;
+      }
+    }
+    c->segs.beg[0] = bestBeg; c->segs.end[0] = bestEnd;
+    c->segs.beg[1] = lo;      c->segs.end[1] = bestBeg;
+    c->segs.beg[2] = bestEnd; c->segs.end[2] = hi;
+  }
   int st = FB_OK;
 #define DCHK(call) do { st = (call); if (st != FB_OK) { fb_destroy(c); return st; } } while (0)
 #define DCUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fb_set_error("%s -> %s", #call, cudaGetErrorString(e__)); fb_destroy(c); return FB_ERR_CUDA; } } while (0)

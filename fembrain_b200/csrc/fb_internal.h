@@ -49,6 +49,12 @@ struct FbScalars {
 
 struct FbDist;  // multi-GPU state (fb_dist.cu)
 
+// Block rows the solver's products visit, in order.  One GPU: [0] = all rows.  Partitioned: [0] = owned rows that read no
+// ghost column, [1] and [2] = the owned rows before / after them (next to the cuts); ghost rows are not visited at all.
+struct FbRowSegs {
+  int beg[3], end[3];
+};
+
 struct fb_context {
   int device;
   int sm_count;
@@ -128,6 +134,7 @@ struct fb_context {
   int last_iters;        // signed like the reference's return value
   double last_ratio;
   long long launches;
+  FbRowSegs segs;
   int spmv_group;        // lanes per block row chosen at setup
   int use_rows3;         // 1: k_spmv_rows3 (16 lanes per row, all loads of a row in flight), 0: k_spmv<G>
   int rows3_minb;        // resident CTAs/SM requested for k_spmv_rows3 modes 0-2 (4 or 5)
@@ -197,25 +204,15 @@ unsigned long long fb_dist_epoch(fb_context *c, int it, int family);  // epoch o
 void fb_dist_next_solve(fb_context *c);
 unsigned int fb_dist_halo_mask(const fb_context *c);
 int fb_dist_halo_push(fb_context *c, const double *vec, unsigned long long epoch);
+struct FbPushArgs;
+void fb_dist_push_args(fb_context *c, FbPushArgs *out, unsigned long long epoch);  // halo push fused into k_direction
 
 // Device memory comes from the device's default stream-ordered pool (cudaMallocAsync on the context's stream); the
 // pool's release threshold is raised at the first fb_create, so destroy -> create cycles (re-setup after a cut,
 // DEF/Deformable.cpp:127-220 via cutCompleted) reuse memory instead of paying cudaMalloc/cudaFree again
 // (fb_create at 1M tets: 75-200 ms with cudaMalloc, profiles/r01_setup_time.txt).  fb_trim_memory() gives it back.
 // Buffers exported with CUDA IPC (peer-memory exchange) cannot live in a pool: fb_dev_alloc_plain.
-template <typename T>
-static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {
-  size_t bytes = (n ? n : 1) * sizeof(T);
-  cudaError_t e = cudaMallocAsync((void **)p, bytes, c->stream);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    fb_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-    *p = nullptr;
-    return FB_ERR_OUT_OF_MEMORY;
-  }
-  c->bytes += bytes;
-  return FB_OK;
-}
+bool fb_use_pool();  // false with FEMBRAIN_B200_POOL=0: plain cudaMalloc for everything
 template <typename T>
 static inline int fb_dev_alloc_plain(fb_context *c, T **p, size_t n) {
   size_t bytes = (n ? n : 1) * sizeof(T);
@@ -223,6 +220,20 @@ static inline int fb_dev_alloc_plain(fb_context *c, T **p, size_t n) {
   if (e != cudaSuccess) {
     cudaGetLastError();
     fb_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    *p = nullptr;
+    return FB_ERR_OUT_OF_MEMORY;
+  }
+  c->bytes += bytes;
+  return FB_OK;
+}
+template <typename T>
+static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  if (!fb_use_pool()) return fb_dev_alloc_plain(c, p, n);
+  cudaError_t e = cudaMallocAsync((void **)p, bytes, c->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fb_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     *p = nullptr;
     return FB_ERR_OUT_OF_MEMORY;
   }

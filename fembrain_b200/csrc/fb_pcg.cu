@@ -196,7 +196,7 @@ __device__ __forceinline__ void finish_kernel(double (&part)[3], FbScalars *sc, 
 
 // ---- generic row-per-G-lanes SpMV (G = 8 or 32: meshes with very short or very long rows) -------------------
 template <int G, int MODE>
-__global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
+__global__ void __launch_bounds__(SPMV_TB) k_spmv(FbRowSegs segs, const int *__restrict__ bp, const int *__restrict__ bc,
                                                   const double *__restrict__ A, const double *__restrict__ x,
                                                   double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                   const double *__restrict__ b, const double *__restrict__ invD,
@@ -214,7 +214,9 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
   const int group = blockIdx.x * groupsPerBlock + threadIdx.x / G;
   const int nGroups = gridDim.x * groupsPerBlock;
   double part[3] = {0.0, 0.0, 0.0};
-  for (int v = group; v < nV; v += nGroups) {
+#pragma unroll 1
+  for (int sg = 0; sg < 3; sg++)
+  for (int v = segs.beg[sg] + group; v < segs.end[sg]; v += nGroups) {
     const int rs = __ldg(bp + v), re = __ldg(bp + v + 1);
     const int n3 = 3 * (re - rs);
     const double *a0 = A + 9 * (size_t)rs;
@@ -254,9 +256,17 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int nV, const int *__restrict_
 // ---- row-per-16-lanes SpMV with every load of a row in flight at once (no shared memory, no block syncs) ----
 // The three 16-wide passes over a row are fully unrolled and predicated, so a lane has 9 streaming value loads +
 // 3 column loads outstanding before the first multiply, and the row pointers of the group's next row are fetched
-// one row ahead.  MINB = resident CTAs per SM requested from the compiler (5 -> 48 registers, no spills).
+// one row ahead.  MINB = resident CTAs per SM requested from the compiler (4 -> <= 64 registers, no spills).
+//
+// Block rows [rowBeg, nV): all rows on one GPU, the owned rows of a partitioned context (ghost rows are not visited).
+// With peer-memory exchange the wait for the neighbours' halo of d sits at the top.  Tried and dropped
+// (profiles/r01_spmv_segments_ab.txt): (a) one kernel walking three row segments — rows that read no ghost column, the
+// wait, then the rows next to the cuts: sharing that body cost the single-GPU kernel 10 % (38.9 vs 35.2 us at 1M tets);
+// (b) two launches, interior rows first and the rows next to the cuts (which wait, add both sums and publish) second:
+// 279 vs 268 ms per step on 2 GPUs at 10M tets — the halo has already landed when the product starts, so there is no
+// wait to hide, and the second launch's own latency chain is added to every iteration.
 template <int MODE, int MINB>
-__global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
+__global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int rowBeg, int nV, const int *__restrict__ bp, const int *__restrict__ bc,
                                                               const double *__restrict__ A, const double *__restrict__ x,
                                                               double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                               const double *__restrict__ b, const double *__restrict__ invD,
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
   const int group = blockIdx.x * groupsPerBlock + threadIdx.x / TILE_G;
   const int nGroups = gridDim.x * groupsPerBlock;
   double part[3] = {0.0, 0.0, 0.0};
-  int v = group;
+  int v = rowBeg + group;
   int rs = 0, re = 0;
   if (v < nV) { rs = __ldg(bp + v); re = __ldg(bp + v + 1); }
   while (v < nV) {
@@ -341,6 +351,7 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int nV, const int 
 // r = b (x0 = 0), d = invD r, x = 0, rho0 = sum r^2 invD           (CGSolver.cpp:139-147)
 __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restrict__ b, const double *__restrict__ invD,
                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
+                                                    double *__restrict__ q,
                                                     FbScalars *sc, double *slots, double *outp, FbPeerArgs pa,
                                                     const unsigned char *__restrict__ skipMask) {
   double part[1] = {0.0};
@@ -348,6 +359,7 @@ __global__ void __launch_bounds__(VEC_TB) k_cg_init(int n, const double *__restr
     const double bi = b[i], di = invD[i];
     x[i] = 0.0;
     r[i] = bi;
+    q[i] = 0.0;  // rows the products skip (ghost rows of a partitioned context) must read as zero in the updates
     // peer-memory exchange: ghost entries of d belong to the neighbour's push (constrained entries stay 0 for ever)
     if (!(skipMask && skipMask[i])) d[i] = di * bi;
     part[0] += (bi * bi) * di;
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(VEC_TB) k_update(int n, const double *__restri
 __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__restrict__ r, const double *__restrict__ invD,
                                                       double *__restrict__ d, FbScalars *sc, int itArg,
                                                       const double *__restrict__ rhoSlots, int nRhoSlots, FbPeerArgs pa,
-                                                      const unsigned char *__restrict__ skipMask) {
+                                                      const unsigned char *__restrict__ skipMask, FbPushArgs push) {
   pdl_wait();
   pdl_trigger();
   if (sc->done) return;
@@ -482,15 +494,37 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
       if (!mk.x) d[2 * i] = dv.x;
       if (!mk.y) d[2 * i + 1] = dv.y;
     }
+    if (push.nNbr) {  // owned entries next to a cut go straight into the neighbours' ghost entries (NVLink stores)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const size_t dof = 2 * i + h;
+        const int v = (int)(dof / 3), k = (int)(dof - 3 * (size_t)v);
+        if (push.pushFlag[v]) {
+          const double val = h ? dv.y : dv.x;
+          for (int e = push.pushPtr[v]; e < push.pushPtr[v + 1]; e++) {
+            const int2 t = push.pushEnt[e];
+            push.peerVec[t.x][3 * (size_t)t.y + k] = val;
+          }
+        }
+      }
+    }
     i += stride;
     if (i < n2) {
       rv = r2[i]; wv = w2[i]; dv = d2[i];
       if (skipMask) mk = m2[i];
     }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && !(skipMask && skipMask[n - 1])) d[n - 1] = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && !(skipMask && skipMask[n - 1])) {
+    const double val = fma(invD[n - 1], r[n - 1], beta * d[n - 1]);
+    d[n - 1] = val;
+    if (push.nNbr) {
+      const int v = (n - 1) / 3, k = (n - 1) - 3 * v;
+      for (int e = push.pushPtr[v]; e < push.pushPtr[v + 1]; e++) push.peerVec[push.pushEnt[e].x][3 * (size_t)push.pushEnt[e].y + k] = val;
+    }
+  }
   // bookkeeping by the last CTA to finish, so that no CTA of this launch can still be reading sc->iters / done
   __shared__ bool last;
+  if (push.nNbr) __threadfence_system();  // this thread's peer stores are out before the CTA's ticket
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -498,6 +532,11 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
+    if (push.nNbr) {  // every CTA's stores are out: raise this rank's halo flag in each neighbour's comm block
+      __threadfence_system();
+      for (int j = 0; j < push.nNbr; j++)
+        ((volatile unsigned long long *)pa.comm[push.nbrRank[j]])[FB_COMM_FLAG(FB_COMM_HALO, pa.rank)] = push.epoch;
+    }
     sc->ticket_b = 0u;
     if (rhoSlots || pa.enabled) sc->rho[it & 1] = rhoNew;
     sc->iters = it;
@@ -579,17 +618,24 @@ void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y
   FbPeerArgs pa;
   if (peer) pa = *peer; else memset(&pa, 0, sizeof(pa));
   const int grid = c->grid_spmv[MODE];
+  // MODE 0 is the plain product of the inspection calls: all rows.  The solver's products visit owned rows only.
+  const FbRowSegs &sg = c->segs;
+  const int lo = (sg.end[1] > sg.beg[1]) ? sg.beg[1] : sg.beg[0], hi = (sg.end[2] > sg.beg[2]) ? sg.end[2] : sg.end[0];
   if (c->use_rows3) {
-    if (MODE == 3 || c->rows3_minb == 4)
-      fb_launch(c->pdl && MODE != 0, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
+    if (MODE == 0)
+      fb_launch(false, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, 0, c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
     else
-      fb_launch(c->pdl && MODE != 0, c->stream, k_spmv_rows3<MODE, 5>, grid, SPMV_TB, c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
+      fb_launch(c->pdl, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
   } else if (MODE != 3) {
     constexpr int M = MODE == 3 ? 1 : MODE;
+    FbRowSegs segs = c->segs;
+    if (MODE == 0) { segs.beg[0] = 0; segs.end[0] = c->nV; }
+    else { segs.beg[0] = lo; segs.end[0] = hi; }
+    segs.beg[1] = segs.end[1] = segs.beg[2] = segs.end[2] = 0;
     switch (c->spmv_group) {
-      case 8: k_spmv<8, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
-      case 32: k_spmv<32, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
-      default: k_spmv<16, M><<<grid, SPMV_TB, 0, c->stream>>>(c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      case 8: k_spmv<8, M><<<grid, SPMV_TB, 0, c->stream>>>(segs, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      case 32: k_spmv<32, M><<<grid, SPMV_TB, 0, c->stream>>>(segs, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      default: k_spmv<16, M><<<grid, SPMV_TB, 0, c->stream>>>(segs, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
     }
   }
   c->launches++;
@@ -629,9 +675,10 @@ void enqueue_iteration_p2p(fb_context *c, int it) {
   // direction: collects rho'(it); ghost entries are left to the neighbours
   pa = base;
   pa.epochWait = fb_dist_epoch(c, it, FB_COMM_RHO);
-  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, it, nullptr, 0, pa, c->rowmask);
+  FbPushArgs push;
+  fb_dist_push_args(c, &push, fb_dist_epoch(c, it, FB_COMM_HALO));  // the halo of the new d leaves from this kernel
+  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, it, nullptr, 0, pa, c->rowmask, push);
   c->launches++;
-  fb_dist_halo_push(c, c->dir, fb_dist_epoch(c, it, FB_COMM_HALO));
 }
 
 // the reference's literal order, three kernels (+ NCCL in partitioned contexts without peer mapping)
@@ -641,6 +688,8 @@ void enqueue_iteration_kernels(fb_context *c, int it) {
   double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
   FbPeerArgs nopeer;
   memset(&nopeer, 0, sizeof(nopeer));
+  FbPushArgs nopush;
+  memset(&nopush, 0, sizeof(nopush));
   const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64;
   if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
   // one GPU: per-CTA sums stay in their slots and the next kernel adds them (no ticket / last-CTA pass on the SpMV tail);
@@ -665,7 +714,7 @@ void enqueue_iteration_kernels(fb_context *c, int it) {
     if (defer) { rhoSlots = slotsV; nRhoSlots = vg; }
   }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
-  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots, nopeer, nullptr);
+  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots, nopeer, nullptr, nopush);
   c->launches++;
   if (c->dist) fb_dist_halo_exchange(c, c->dir);
 }
@@ -676,6 +725,8 @@ int enqueue_iteration_fused(fb_context *c, int it, bool allowSample) {
   const int n = c->r, vg = c->grid_vec;
   FbPeerArgs nopeer;
   memset(&nopeer, 0, sizeof(nopeer));
+  FbPushArgs nopush;
+  memset(&nopush, 0, sizeof(nopush));
   double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
   const bool sample = allowSample && c->profiling && (it % 16 == 1) && c->nprof < 64;
   if (sample) cudaEventRecord(c->evProf[2 * c->nprof], c->stream);
@@ -685,7 +736,7 @@ int enqueue_iteration_fused(fb_context *c, int it, bool allowSample) {
     fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, 0, nullptr, nullptr, 0, nopeer);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, &c->sc->rho[0]);  // it is even: rho[it & 1] = rho[0]
-    fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, 0, nullptr, 0, nopeer, nullptr);
+    fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, 0, nullptr, 0, nopeer, nullptr, nopush);
     c->launches++;
     return 4;
   }
@@ -726,7 +777,7 @@ int start_solve(fb_context *c, double eps, int maxIt) {
     fb_dist_peer_args(c, &pa);
     pa.epoch = fb_dist_epoch(c, 0, FB_COMM_RHO);
   }
-  k_cg_init<<<c->grid_vec, VEC_TB, 0, st>>>(c->r, c->rhs, c->invD, c->x, c->res, c->dir, c->sc, c->partials + 3 * (size_t)FB_MAX_PARTIALS,
+  k_cg_init<<<c->grid_vec, VEC_TB, 0, st>>>(c->r, c->rhs, c->invD, c->x, c->res, c->dir, c->Ad, c->sc, c->partials + 3 * (size_t)FB_MAX_PARTIALS,
                                             c->dist ? &c->sc->rho_part : &c->sc->rho[0], pa, p2p ? c->rowmask : nullptr);
   if (c->dist && !p2p) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[0]));  // rho0 is a global sum
   if (p2p) { pa.epoch = 0; pa.epochWait = fb_dist_epoch(c, 0, FB_COMM_RHO); }
@@ -784,17 +835,11 @@ int fb_spmv_plan(fb_context *c) {
   if (c->use_rows3) {
     const size_t gpb = SPMV_TB / TILE_G;
     const size_t want = ((size_t)c->nV + gpb - 1) / gpb;
-    const char *mb = getenv("FEMBRAIN_B200_MINB");
-    c->rows3_minb = (mb && atoi(mb) == 5) ? 5 : 4;  // 4 CTAs/SM (56 registers, no spills) measured best
-    if (c->rows3_minb == 4) {
-      c->grid_spmv[0] = one_wave(c, k_spmv_rows3<0, 4>, SPMV_TB, want);
-      c->grid_spmv[1] = one_wave(c, k_spmv_rows3<1, 4>, SPMV_TB, want);
-      c->grid_spmv[2] = one_wave(c, k_spmv_rows3<2, 4>, SPMV_TB, want);
-    } else {
-      c->grid_spmv[0] = one_wave(c, k_spmv_rows3<0, 5>, SPMV_TB, want);
-      c->grid_spmv[1] = one_wave(c, k_spmv_rows3<1, 5>, SPMV_TB, want);
-      c->grid_spmv[2] = one_wave(c, k_spmv_rows3<2, 5>, SPMV_TB, want);
-    }
+    // 4 CTAs/SM (<= 64 registers, no spills) measured best; 5 CTAs/SM (48 registers) spills (profiles/r01_pcg_schedules.txt)
+    c->rows3_minb = 4;
+    c->grid_spmv[0] = one_wave(c, k_spmv_rows3<0, 4>, SPMV_TB, want);
+    c->grid_spmv[1] = one_wave(c, k_spmv_rows3<1, 4>, SPMV_TB, want);
+    c->grid_spmv[2] = one_wave(c, k_spmv_rows3<2, 4>, SPMV_TB, want);
     c->grid_spmv[3] = one_wave(c, k_spmv_rows3<3, 4>, SPMV_TB, want);
   } else if (c->spmv_group == 8) {
     plan_generic<8>(c);

@@ -80,6 +80,19 @@ struct FbPeerArgs {
   double *comm[FB_MAX_RANKS];
 };
 
+// Halo of the search direction pushed by the kernel that computes it (k_direction): per local vertex the list of
+// (neighbour slot, neighbour-local vertex) it must be stored to; pushFlag skips the other vertices with one byte.
+#define FB_MAX_NBR 8
+struct FbPushArgs {
+  int nNbr;                          // 0 = nothing to push (one GPU, NCCL path)
+  int nbrRank[FB_MAX_NBR];
+  double *peerVec[FB_MAX_NBR];       // the neighbours' direction vectors, mapped here
+  const unsigned char *pushFlag;     // [nV]
+  const int *pushPtr;                // [nV + 1]
+  const int2 *pushEnt;               // (neighbour slot, neighbour-local vertex)
+  unsigned long long epoch;          // halo epoch raised in the neighbours' comm blocks when all stores are out
+};
+
 // executed by ONE thread (the thread that holds the rank's total)
 __device__ __forceinline__ void peer_publish(const FbPeerArgs &pa, int family, double value) {
   for (int p = 0; p < pa.world; p++) ((volatile double *)pa.comm[p])[FB_COMM_SLOT(family, pa.rank)] = value;

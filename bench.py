@@ -163,6 +163,15 @@ def cpu_reference_sample(nx, cg_sample_iters, iters_per_step, steps, warmup, log
 # committed iteration counts of the bench workload (from rest, steps 1..): measured on B200 by this
 # bench (matches the CPU oracle to +-1 where the oracle is affordable); used by --impl reference to
 # extrapolate its bounded PCG sample without touching the GPU arm
+def ncu_assembly(nx):
+    """ncu figures of the assembly kernels for this size (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh).get(str(nx), {}).get("assembly")
+    except Exception:
+        return None
+
+
 def ncu_traffic(nx):
     """dram__bytes_read.sum + dram__bytes_write.sum per SpMV launch from the committed `ncu --set full` capture
     (profiles/ncu_traffic.json), or None when no capture exists for this size."""
@@ -336,6 +345,11 @@ def run_ours(args):
             "assembly_mtets_per_s": units * nT * args.steps / t_asm / 1e6 if t_asm > 0 else None,
             "assembly_mtets_per_s_isolated": nT / t_asm_iso / 1e6,
             "assembly_share_of_step": t_asm / sec, "solve_share_of_step": t_solve / sec,
+            # compulsory bytes of one assembly = tet ids + x0, u read, f write + K values written; the kernels are
+            # bound by the FP64 pipe (no-FMA arithmetic, bit-identical to the reference), not by these bytes
+            "assembly": {"compulsory_bytes": 16.0 * nT + 72.0 * (rows / 3) + 8.0 * nnz,
+                         "compulsory_gbs": (16.0 * nT + 72.0 * (rows / 3) + 8.0 * nnz) / t_asm_iso / 1e9,
+                         "seconds_isolated": t_asm_iso, "ncu": ncu_assembly(nx)},
             "setup_seconds": t_setup, "device_bytes": sim.device_bytes, "nnz_K": nnz, "tets": nT,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -95,6 +95,7 @@ def load_library():
         "fb_deformable_set_haptic_neighborhood": (ci, [vp, ci]),
         "fb_deformable_contact_count": (ci, [vp]),
         "fb_deformable_set_edge_list": (ci, [vp, ci, vp, ci]),
+        "fb_deformable_pick_vertices": (ci, [vp, vp, vp, ci, vp, vp, vp]), "fb_deformable_pick_vertex": (ci, [vp, vp, vp, vp, vp]),
         "fb_force_assembly_seconds": (cd, [vp]), "fb_system_solve_seconds": (cd, [vp]), "fb_step_seconds": (cd, [vp]),
         "fb_last_cg_iterations": (ci, [vp]), "fb_last_cg_residual_ratio": (cd, [vp]),
         "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]), "fb_trim_memory": (ci, []),
@@ -108,6 +109,7 @@ def load_library():
         "fb_solve": (ci, [vp, vp, vp, cd, ci, C.POINTER(ci)]), "fb_system_multiply": (ci, [vp, vp, vp]),
         "fb_veg_load": (ci, [C.c_char_p, C.POINTER(ci), C.POINTER(ci), pp, pp, pp, pp, pp]),
         "fb_veg_free": (None, [vp]),
+        "fb_tetgen_load": (ci, [C.c_char_p, C.POINTER(ci), C.POINTER(ci), pp, pp, pp, pp, pp]),
         "fb_create_from_veg": (ci, [pp, C.c_char_p, ci, vp, prm]),
         "fb_export_positions_float4": (ci, [vp, ci, vp, vp]),
         "fb_export_positions_float4_dev": (ci, [vp, ci, vp, vp]),
@@ -183,14 +185,19 @@ def trim_memory():
     return load_library().fb_trim_memory()
 
 
-def veg_load(path):
+def tetgen_load(basename):
+    """fb_tetgen_load: <basename>.node / .ele with the rules of the reference's TetMesh(char*) constructor."""
+    return veg_load(basename, _fn="fb_tetgen_load")
+
+
+def veg_load(path, _fn="fb_veg_load"):
     """fb_veg_load: (verts [nV,3], tets [nT,4] 0-based, E[nT], nu[nT], density[nT]) with the reference loader's rules."""
     lib = load_library()
     nv, nt = C.c_int(0), C.c_int(0)
     ptrs = [C.c_void_p() for _ in range(5)]
-    st = lib.fb_veg_load(str(path).encode(), C.byref(nv), C.byref(nt), *[C.byref(p) for p in ptrs])
+    st = getattr(lib, _fn)(str(path).encode(), C.byref(nv), C.byref(nt), *[C.byref(p) for p in ptrs])
     if st != FB_OK:
-        raise FemBrainError(st, "fb_veg_load", lib.fb_last_error_string().decode())
+        raise FemBrainError(st, _fn, lib.fb_last_error_string().decode())
     try:
         def arr(p, ctype, n, dt):
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(max(n, 1),))[:n].astype(dt, copy=True)
@@ -391,6 +398,22 @@ class Simulation:
     def set_edge_list(self, edges, reference_quirk=True):
         e = _i32(edges).reshape(-1)
         self._check(self._lib.fb_deformable_set_edge_list(self._h, e.size // 2, _ptr(e), int(reference_quirk)), "fb_deformable_set_edge_list")
+
+    def pick_vertices(self, box_lo, box_hi, capacity=None):
+        """Deformable::pickVertices: (indices ascending, coordinates) of the vertices whose current position is in the closed box."""
+        lo, hi = _f64(box_lo), _f64(box_hi)
+        cap = self.nV if capacity is None else capacity
+        idx, co, n = np.zeros(max(cap, 1), np.int32), np.zeros(3 * max(cap, 1)), C.c_int(0)
+        self._check(self._lib.fb_deformable_pick_vertices(self._h, _ptr(lo), _ptr(hi), cap, _ptr(idx), _ptr(co), C.byref(n)), "fb_deformable_pick_vertices")
+        k = min(n.value, cap)
+        return idx[:k].copy(), co[:3 * k].reshape(-1, 3).copy(), n.value
+
+    def pick_vertex(self, world_pos):
+        """Deformable::pickVertex: (index, distance, position) of the vertex nearest to world_pos (lowest index on ties)."""
+        w = _f64(world_pos)
+        i, d, v = C.c_int(-1), C.c_double(0), np.zeros(3)
+        self._check(self._lib.fb_deformable_pick_vertex(self._h, _ptr(w), C.byref(i), C.byref(d), _ptr(v)), "fb_deformable_pick_vertex")
+        return i.value, d.value, v
 
     @property
     def contact_count(self):

@@ -10,7 +10,10 @@
 //   default ............. true mesh adjacency (vertices sharing a tetrahedron edge), from the K block structure
 //   reference quirk ..... bit-for-bit the reference's behaviour, given the host's edge array in VolMesh order
 //                         (fb_deformable_set_edge_list; the FemBrain host has it as m_lpVolMesh->const_edgeAt(i))
+#include <cub/cub.cuh>
+
 #include <algorithm>
+#include <cfloat>
 #include <cstdlib>
 #include <cstring>
 #include <set>
@@ -52,6 +55,60 @@ __global__ void k_floor_poststep(int nV, double floorY, const double *__restrict
     atomicAdd(contacts, 1);  // integer count
     q[3 * (size_t)i + 1] = floorY - pry;
   }
+}
+
+// Deformable::pickVertices (DEF/Deformable.cpp:430-448) with Contains<double> (graphics/AABB.h:84-92, closed box) on the
+// current node positions pos = restpos + u (VolMesh::displace, DEF/VolMesh.cpp:1370-1385): one flag per vertex, then an
+// order-preserving compaction so the indices come out ascending like the reference's push_back loop.
+__global__ void k_pick_flags(int nV, const double *__restrict__ x0, const double *__restrict__ q, double lx, double ly, double lz,
+                             double hx, double hy, double hz, int *__restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nV) return;
+  const double px = x0[3 * (size_t)i] + q[3 * (size_t)i], py = x0[3 * (size_t)i + 1] + q[3 * (size_t)i + 1],
+               pz = x0[3 * (size_t)i + 2] + q[3 * (size_t)i + 2];
+  flag[i] = ((px >= lx) && (px <= hx) && (py >= ly) && (py <= hy) && (pz >= lz) && (pz <= hz)) ? 1 : 0;
+}
+__global__ void k_pick_scatter(int nV, const double *__restrict__ x0, const double *__restrict__ q, const int *__restrict__ flag,
+                               const int *__restrict__ pos, int capacity, int *__restrict__ idx, double *__restrict__ coords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nV || !flag[i]) return;
+  const int o = pos[i];
+  if (o >= capacity) return;
+  idx[o] = i;
+  if (coords)
+    for (int k = 0; k < 3; k++) coords[3 * (size_t)o + k] = x0[3 * (size_t)i + k] + q[3 * (size_t)i + k];
+}
+
+// CuttableMesh::findClosestVertex (DEF/CuttableMesh.cpp:511-526): squared distance (dx*dx + dy*dy + dz*dz, Vec3::length2)
+// to the current position, strict '<' in index order => the LOWEST index among equal minima.
+struct PickBest {
+  double d2;
+  int idx;
+};
+__device__ __forceinline__ PickBest pick_min(PickBest a, PickBest b) {
+  return (b.d2 < a.d2 || (b.d2 == a.d2 && b.idx < a.idx)) ? b : a;
+}
+__global__ void __launch_bounds__(256) k_pick_closest(int nV, const double *__restrict__ x0, const double *__restrict__ q, double wx,
+                                                      double wy, double wz, PickBest *__restrict__ out) {
+  __shared__ PickBest sm[256];
+  PickBest best;
+  best.d2 = DBL_MAX;  // GetMaxLimit<double>()
+  best.idx = 0x7fffffff;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < nV; i += gridDim.x * 256) {
+    const double dx = wx - (x0[3 * (size_t)i] + q[3 * (size_t)i]), dy = wy - (x0[3 * (size_t)i + 1] + q[3 * (size_t)i + 1]),
+                 dz = wz - (x0[3 * (size_t)i + 2] + q[3 * (size_t)i + 2]);
+    PickBest c;
+    c.d2 = dx * dx + dy * dy + dz * dz;
+    c.idx = i;
+    if (c.d2 < DBL_MAX) best = pick_min(best, c);  // the reference never accepts a distance that is not below the limit (NaN, inf)
+  }
+  sm[threadIdx.x] = best;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = pick_min(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
 }
 
 // neighbours of vtx under the chosen rule
@@ -127,6 +184,86 @@ int fb_deformable_set_edge_list(fb_context *c, int numEdges, const int *fromTo, 
   return FB_OK;
 }
 int fb_deformable_contact_count(const fb_context *c) { return c ? c->contact_count : 0; }
+
+int fb_deformable_pick_vertices(fb_context *c, const double *lo, const double *hi, int capacity, int *indices, double *coords,
+                                int *count) {
+  CHECK_CTX(c);
+  if (!lo || !hi || !count || capacity < 0 || (capacity > 0 && !indices)) { fb_set_error("bad arguments to fb_deformable_pick_vertices"); return FB_ERR_INVALID_ARGUMENT; }
+  if (c->dist) { fb_set_error("picking on a partitioned context is not supported"); return FB_ERR_NOT_SUPPORTED; }
+  *count = 0;
+  const int nV = c->nV;
+  if (nV == 0) return FB_OK;
+  cudaStream_t st = c->stream;
+  int *flag = nullptr, *pos = nullptr, *dIdx = nullptr;
+  double *dCo = nullptr;
+  void *tmp = nullptr;
+  size_t tmpBytes = 0;
+  int status = FB_OK;
+  auto cleanup = [&]() { for (void *q : {(void *)flag, (void *)pos, (void *)dIdx, (void *)dCo, tmp}) fb_tmp_free(st, q); };
+#define PK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fb_set_error("%s -> %s", #call, cudaGetErrorString(e__)); cleanup(); return FB_ERR_CUDA; } } while (0)
+  PK(fb_tmp_alloc(st, &flag, sizeof(int) * ((size_t)nV + 1)));
+  PK(fb_tmp_alloc(st, &pos, sizeof(int) * ((size_t)nV + 1)));
+  PK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, flag, pos, (int64_t)nV + 1, st));
+  PK(fb_tmp_alloc(st, &tmp, tmpBytes));
+  PK(cudaMemsetAsync(flag + nV, 0, sizeof(int), st));
+  k_pick_flags<<<(nV + 255) / 256, 256, 0, st>>>(nV, c->x0, c->q, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], flag);
+  PK(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, flag, pos, (int64_t)nV + 1, st));
+  int found = 0;
+  PK(cudaMemcpyAsync(&found, pos + nV, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PK(cudaStreamSynchronize(st));
+  c->launches += 3;
+  *count = found;  // the full count even when it exceeds the caller's capacity (call again with a larger buffer)
+  const int n = found < capacity ? found : capacity;
+  if (n > 0) {
+    PK(fb_tmp_alloc(st, &dIdx, sizeof(int) * (size_t)n));
+    if (coords) PK(fb_tmp_alloc(st, &dCo, sizeof(double) * 3 * (size_t)n));
+    k_pick_scatter<<<(nV + 255) / 256, 256, 0, st>>>(nV, c->x0, c->q, flag, pos, n, dIdx, dCo);
+    c->launches++;
+    PK(cudaMemcpyAsync(indices, dIdx, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (coords) PK(cudaMemcpyAsync(coords, dCo, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    PK(cudaStreamSynchronize(st));
+  }
+  cleanup();
+  return status;
+}
+
+int fb_deformable_pick_vertex(fb_context *c, const double *wpos, int *index, double *dist, double *vertex) {
+  CHECK_CTX(c);
+  if (!wpos || !index) { fb_set_error("bad arguments to fb_deformable_pick_vertex"); return FB_ERR_INVALID_ARGUMENT; }
+  if (c->dist) { fb_set_error("picking on a partitioned context is not supported"); return FB_ERR_NOT_SUPPORTED; }
+  *index = -1;
+  if (dist) *dist = sqrt(DBL_MAX);
+  const int nV = c->nV;
+  if (nV == 0) return FB_OK;
+  cudaStream_t st = c->stream;
+  int grid = (nV + 255) / 256;
+  if (grid > 4 * c->sm_count) grid = 4 * c->sm_count;
+  PickBest *part = nullptr;
+  void *tmpv = nullptr;
+  auto cleanup = [&]() { fb_tmp_free(st, part); fb_tmp_free(st, tmpv); };
+  PK(fb_tmp_alloc(st, &part, sizeof(PickBest) * ((size_t)grid + 1)));
+  k_pick_closest<<<grid, 256, 0, st>>>(nV, c->x0, c->q, wpos[0], wpos[1], wpos[2], part);
+  c->launches++;
+  std::vector<PickBest> h((size_t)grid);
+  PK(cudaMemcpyAsync(h.data(), part, sizeof(PickBest) * (size_t)grid, cudaMemcpyDeviceToHost, st));
+  PK(cudaStreamSynchronize(st));
+  PickBest best = h[0];
+  for (int i = 1; i < grid; i++)
+    if (h[i].d2 < best.d2 || (h[i].d2 == best.d2 && h[i].idx < best.idx)) best = h[i];
+  cleanup();
+#undef PK
+  if (best.idx == 0x7fffffff) return FB_OK;  // no vertex at a finite distance: the reference returns -1 too
+  *index = best.idx;
+  if (dist) *dist = sqrt(best.d2);
+  if (vertex) {
+    double x[3], u[3];
+    FB_CUDA(cudaMemcpyAsync(x, c->x0 + 3 * (size_t)best.idx, sizeof(x), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaMemcpyAsync(u, c->q + 3 * (size_t)best.idx, sizeof(u), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; k++) vertex[k] = x[k] + u[k];
+  }
+  return FB_OK;
+}
 
 int fb_deformable_timestep(fb_context *c) {
   CHECK_CTX(c);

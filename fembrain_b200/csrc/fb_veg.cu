@@ -241,6 +241,59 @@ int fb_veg_load(const char *path, int *num_vertices, int *num_tets, double **ver
 
 void fb_veg_free(void *p) { free(p); }
 
+// TetMesh(char* filename, int specialFileType = 0), src/3rdparty/vegafem/volumetricMesh/tetMesh.cpp:45-127: TetGen's
+// <base>.node ("numVertices 3", then "index x y z", 1-indexed and consecutive) and <base>.ele ("numElements 4", then
+// "index v0 v1 v2 v3", vertices 1-indexed); comment and blank lines skipped as everywhere in the parser; one material
+// for all elements, E = 1e8, nu = 0.45, density = 1000 (:47-49, setSingleMaterial :126).  The reference throws an int
+// on every irregularity (2-6); here: FB_ERR_INVALID_ARGUMENT for a file that cannot be opened, FB_ERR_BAD_MESH otherwise.
+// (That constructor cannot serve as the checker: its setSingleMaterial writes elementMaterial[] through a pointer the
+// constructor never allocates, volumetricMesh.cpp:1002-1034, and crashes when compiled here — parity unpinned.)
+int fb_tetgen_load(const char *basename, int *num_vertices, int *num_tets, double **vertices, int **tets, double **E, double **nu,
+                   double **density) {
+  if (!basename || !num_vertices || !num_tets) { fb_set_error("bad arguments to fb_tetgen_load"); return FB_ERR_INVALID_ARGUMENT; }
+  char line[4096];
+  std::string path = std::string(basename) + ".node";
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) { fb_set_error("could not open file %s", path.c_str()); return FB_ERR_INVALID_ARGUMENT; }
+  int nV = 0, nT = 0, dim = 0;
+  if (!next_line(f, line, sizeof(line)) || sscanf(line, "%d %d", &nV, &dim) != 2 || dim != 3 || nV < 0) {
+    fclose(f); fb_set_error("%s: not a 3D TetGen node file", path.c_str()); return FB_ERR_BAD_MESH;
+  }
+  std::vector<double> v(3 * (size_t)nV);
+  for (int i = 0; i < nV; i++) {
+    int index = 0;
+    if (!next_line(f, line, sizeof(line)) || sscanf(line, "%d %lf %lf %lf", &index, &v[3 * (size_t)i], &v[3 * (size_t)i + 1], &v[3 * (size_t)i + 2]) != 4 ||
+        index != i + 1) {
+      fclose(f); fb_set_error("%s: vertex line %d is missing, malformed or out of sequence", path.c_str(), i + 1); return FB_ERR_BAD_MESH;
+    }
+  }
+  fclose(f);
+  path = std::string(basename) + ".ele";
+  f = fopen(path.c_str(), "r");
+  if (!f) { fb_set_error("could not open file %s", path.c_str()); return FB_ERR_INVALID_ARGUMENT; }
+  if (!next_line(f, line, sizeof(line)) || sscanf(line, "%d %d", &nT, &dim) != 2 || nT < 0) {
+    fclose(f); fb_set_error("%s: not a TetGen element file", path.c_str()); return FB_ERR_BAD_MESH;
+  }
+  if (dim != 4) { fclose(f); fb_set_error("%s: not a tet mesh file (%d vertices per tet encountered)", path.c_str(), dim); return FB_ERR_BAD_MESH; }
+  std::vector<int> t(4 * (size_t)nT);
+  for (int i = 0; i < nT; i++) {
+    int index = 0, w[4];
+    if (!next_line(f, line, sizeof(line)) || sscanf(line, "%d %d %d %d %d", &index, &w[0], &w[1], &w[2], &w[3]) != 5 || index != i + 1) {
+      fclose(f); fb_set_error("%s: element line %d is missing, malformed or out of sequence", path.c_str(), i + 1); return FB_ERR_BAD_MESH;
+    }
+    for (int j = 0; j < 4; j++) t[4 * (size_t)i + j] = w[j] - 1;  // vertices are 1-indexed in .ele files
+  }
+  fclose(f);
+  *num_vertices = nV;
+  *num_tets = nT;
+  if (vertices) *vertices = dup_array(v);
+  if (tets) *tets = dup_array(t);
+  if (E) *E = dup_array(std::vector<double>((size_t)nT, 1E8));
+  if (nu) *nu = dup_array(std::vector<double>((size_t)nT, 0.45));
+  if (density) *density = dup_array(std::vector<double>((size_t)nT, 1000.0));
+  return FB_OK;
+}
+
 int fb_create_from_veg(fb_context **out, const char *path, int num_fixed_vertices, const int *fixed_vertices, const fb_params *params) {
   if (!out || !path) { fb_set_error("bad arguments to fb_create_from_veg"); return FB_ERR_INVALID_ARGUMENT; }
   VegMesh m;

@@ -147,6 +147,14 @@ int fb_deformable_contact_count(const fb_context *ctx);                         
  * host's edge array (num_edges pairs from,to in VolMesh::m_vEdges order) with reference_quirk = 1 reproduces the
  * reference's rings exactly; reference_quirk = 0 or num_edges = 0 returns to true adjacency. */
 int fb_deformable_set_edge_list(fb_context *ctx, int num_edges, const int *from_to, int reference_quirk);
+/* Force producers' vertex queries on the CURRENT positions (rest + displacement), evaluated on the device:
+ * Deformable::pickVertices (DEF/Deformable.cpp:430-448; closed box, graphics/AABB.h:84-92) — ascending indices,
+ * up to `capacity` of them (and their coordinates if coords != NULL, 3 per vertex); *count = all vertices inside.
+ * Deformable::pickVertex -> CuttableMesh::findClosestVertex (DEF/Deformable.cpp:422-428, DEF/CuttableMesh.cpp:511-526) —
+ * lowest index among the nearest vertices, -1 for an empty mesh; dist / vertex may be NULL. */
+int fb_deformable_pick_vertices(fb_context *ctx, const double *box_lo, const double *box_hi, int capacity, int *indices,
+                                double *coords, int *count);
+int fb_deformable_pick_vertex(fb_context *ctx, const double *world_pos, int *index, double *dist, double *vertex);
 
 /* ---- mesh ingest and rendering hand-off (the callers either side of the path) ---------------------
  * .veg reader with the rules of the reference's loader (VolumetricMesh(char*), VEGA/volumetricMesh/volumetricMesh.cpp:45-535):
@@ -155,6 +163,11 @@ int fb_deformable_set_edge_list(fb_context *ctx, int num_edges, const int *from_
 int fb_veg_load(const char *path, int *num_vertices, int *num_tets, double **vertices, int **tets, double **E, double **nu,
                 double **density);
 void fb_veg_free(void *array);
+/* TetGen <basename>.node / <basename>.ele with the rules of TetMesh(char*, int) (VEGA/volumetricMesh/tetMesh.cpp:45-127):
+ * 1-indexed consecutive lines, 3 coordinates, 4 vertices per element; one material (E 1e8, nu 0.45, density 1000).
+ * Same output conventions as fb_veg_load (release with fb_veg_free).  Host-only. */
+int fb_tetgen_load(const char *basename, int *num_vertices, int *num_tets, double **vertices, int **tets, double **E, double **nu,
+                   double **density);
 /* TetMesh(char* filename) + the setup chain of fb_create_with_materials */
 int fb_create_from_veg(fb_context **out, const char *path, int num_fixed_vertices, const int *fixed_vertices, const fb_params *params);
 /* GPUPoly::applyFemDisplacements + ApplyVertexDeformations (implicit/OclPolygonizer.cpp:1543-1584, data/opencl/Polygonizer.cl:1417-1427):

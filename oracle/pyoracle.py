@@ -273,3 +273,27 @@ class Oracle:
 
     def solve_time(self):
         return self._fn("solve_time")(self._h)
+
+
+# -- Deformable's vertex queries (force producers), restated with numpy.  PARITY UNPINNED: Deformable.cpp and
+#    CuttableMesh.cpp cannot be compiled here (TBB, Loki, GL); restated from source. -------------------------------------------
+def pick_vertices(rest_pos, u, box_lo, box_hi):
+    """Deformable::pickVertices (src/deformable/Deformable.cpp:430-448) with Contains<double> (src/graphics/AABB.h:84-92, closed
+    box) on pos = restpos + u (VolMesh::displace, src/deformable/VolMesh.cpp:1370-1385): ascending indices and coordinates."""
+    pos = _f64(rest_pos).reshape(-1, 3) + _f64(u).reshape(-1, 3)
+    lo, hi = _f64(box_lo), _f64(box_hi)
+    inside = np.all((pos >= lo) & (pos <= hi), axis=1)
+    idx = np.nonzero(inside)[0].astype(np.int32)
+    return idx, pos[idx]
+
+
+def pick_vertex(rest_pos, u, world_pos):
+    """Deformable::pickVertex -> CuttableMesh::findClosestVertex (src/deformable/Deformable.cpp:422-428,
+    src/deformable/CuttableMesh.cpp:511-526): strict '<' on dx*dx + dy*dy + dz*dz in index order = first minimum."""
+    pos = _f64(rest_pos).reshape(-1, 3) + _f64(u).reshape(-1, 3)
+    if len(pos) == 0:
+        return -1, float(np.sqrt(np.finfo(np.float64).max)), None
+    d = _f64(world_pos) - pos
+    d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+    i = int(np.argmin(d2))  # first occurrence of the minimum
+    return i, float(np.sqrt(d2[i])), pos[i]

@@ -92,3 +92,34 @@ def test_floor_poststep_rewrites_every_velocity(port_oracle):
     # random (high-frequency) initial velocities: two eps = 1e-6 solves that stop an iteration apart differ by
     # ~cond * 1e-6 in the solution, so the bound here is looser than in the smooth cases
     assert cases.rel_err(qv, oqv) <= 5e-3 and cases.rel_err(q, oq) <= 5e-3
+
+
+def test_pick_vertices_and_pick_vertex_match_restatement(port_oracle):
+    """Force producers' queries (Deformable::pickVertices / pickVertex) on the deformed positions, incl. box faces
+    (closed interval), ties (lowest index), empty results and a too-small output buffer."""
+    import fembrain_b200 as fb
+
+    v, t, fixed, load = cases.cube_case(7)
+    sim = fb.Simulation(v, t, fixed)
+    sim.set_external_forces(cases.point_load(sim.r, load))
+    sim.do_timestep()
+    q = sim.get_state()[0]
+    pos = v + q.reshape(-1, 3)
+    boxes = [((-0.25, 0.15, -0.25), (0.25, 0.65, 0.25)), ((-10, -10, -10), (10, 10, 10)), ((5, 5, 5), (6, 6, 6)),
+             (tuple(pos[10]), tuple(pos[10])),  # a degenerate box exactly on a vertex: closed interval keeps it
+             (tuple(pos.min(axis=0)), tuple(pos.max(axis=0)))]
+    for lo, hi in boxes:
+        idx, co, n = sim.pick_vertices(lo, hi)
+        oidx, oco = port_oracle.pick_vertices(v, q, lo, hi)
+        assert n == len(oidx) and np.array_equal(idx, oidx) and np.array_equal(co, oco)
+    idx, co, n = sim.pick_vertices((-10, -10, -10), (10, 10, 10), capacity=5)
+    assert n == sim.nV and np.array_equal(idx, np.arange(5))
+    rng = np.random.default_rng(3)
+    for w in list(rng.uniform(-1, 2, size=(8, 3))) + [pos[17], 0.5 * (pos[0] + pos[1])]:
+        i, d, p = sim.pick_vertex(w)
+        oi, od, op = port_oracle.pick_vertex(v, q, w)
+        assert i == oi and d == od and np.array_equal(p, op)
+    # tie: a point equidistant from vertices 0 and 1 of the REST mesh -> the lower index
+    sim.reset_to_rest()
+    i, d, p = sim.pick_vertex(0.5 * (v[0] + v[1]))
+    assert i == port_oracle.pick_vertex(v, np.zeros_like(q), 0.5 * (v[0] + v[1]))[0]

@@ -98,6 +98,7 @@ def load_library():
         "fb_deformable_pick_vertices": (ci, [vp, vp, vp, ci, vp, vp, vp]), "fb_deformable_pick_vertex": (ci, [vp, vp, vp, vp, vp]),
         "fb_force_assembly_seconds": (cd, [vp]), "fb_system_solve_seconds": (cd, [vp]), "fb_step_seconds": (cd, [vp]),
         "fb_last_cg_iterations": (ci, [vp]), "fb_last_cg_residual_ratio": (cd, [vp]),
+        "fb_partition_ordering": (ci, [ci, ci, vp, ci, vp, C.POINTER(ci)]), "fb_partition_reordered": (ci, [vp]),
         "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]), "fb_trim_memory": (ci, []),
         "fb_get_stiffness_csr": (ci, [vp, vp, vp]), "fb_get_mass_csr": (ci, [vp, vp, vp, vp]),
         "fb_get_system_csr": (ci, [vp, vp, vp, vp]), "fb_get_element_maps": (ci, [vp, vp, vp]),
@@ -178,6 +179,17 @@ def plan_partition(num_vertices, tets, world, rank):
         "send": {int(nbr[i]): sg[so[i]:so[i + 1]] for i in range(k)},
         "recv": {int(nbr[i]): rg[ro[i]:ro[i + 1]] for i in range(k)},
     }
+
+
+def partition_ordering(num_vertices, tets, world):
+    """fb_partition_ordering: (order[new] = caller's vertex id, reordered flag) of the numbering the row blocks are cut from."""
+    lib = load_library()
+    t = _i32(tets).reshape(-1)
+    order, flag = np.zeros(max(num_vertices, 1), np.int32), C.c_int(0)
+    st = lib.fb_partition_ordering(num_vertices, len(t) // 4, t.ctypes.data if len(t) else None, world, order.ctypes.data, C.byref(flag))
+    if st != FB_OK:
+        raise FemBrainError(st, "fb_partition_ordering", lib.fb_last_error_string().decode())
+    return order[:num_vertices], bool(flag.value)
 
 
 def trim_memory():
@@ -270,6 +282,11 @@ class Simulation:
     @property
     def peer_memory(self):
         return bool(self._lib.fb_partition_peer_memory(self._h))
+
+    @property
+    def reordered(self):
+        """1 when the row blocks were cut from a Cuthill-McKee ordering instead of the caller's numbering."""
+        return int(self._lib.fb_partition_reordered(self._h))
 
     def partition_range(self):
         b, e = C.c_int(0), C.c_int(0)

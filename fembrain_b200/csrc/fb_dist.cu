@@ -30,7 +30,8 @@ struct FbDist {
   ncclComm_t comm_nccl() const { return ncomm; }
   int rank, world;
   int nV_global, nT_global;
-  int vbeg, vend;            // owned global vertex range
+  int vbeg, vend;            // owned vertex range, in the ordering the partition was cut from
+  int reordered;             // 1: that ordering is Cuthill-McKee, not the caller's numbering
   std::vector<int> l2g;      // local vertex -> global vertex (ascending)
   std::vector<unsigned char> owned;  // per local vertex
   int nNbr;
@@ -143,6 +144,95 @@ void make_bounds(int nV, int nT, const int *tets, int world, std::vector<int> &b
     bounds[p] = v;
   }
   bounds[world] = nV;
+}
+
+// number of tets whose vertices do not all belong to one rank
+long long count_cut_tets(const std::vector<int> &bounds, int nT, const int *tets) {
+  long long cut = 0;
+  for (int el = 0; el < nT; el++) {
+    const int *t = tets + 4 * (size_t)el;
+    const int o = owner_of(bounds, t[0]);
+    cut += (owner_of(bounds, t[1]) != o || owner_of(bounds, t[2]) != o || owner_of(bounds, t[3]) != o) ? 1 : 0;
+  }
+  return cut;
+}
+
+// Cuthill-McKee ordering of the vertex graph (vertices sharing a tet), per connected component from a pseudo-peripheral
+// root (two breadth-first sweeps), neighbours visited by increasing degree.  order[new] = old.  Contiguous ranges of this
+// ordering are breadth-first "slabs": the row-block partition's cut becomes a level-set surface instead of whatever the
+// mesh generator's numbering implies.  Pure host integer work, identical on every rank.
+void cuthill_mckee(int nV, int nT, const int *tets, std::vector<int> &order) {
+  std::vector<long long> ptr((size_t)nV + 1, 0);
+  for (size_t i = 0; i < 4 * (size_t)nT; i++) ptr[(size_t)tets[i] + 1] += 3;
+  for (int v = 0; v < nV; v++) ptr[(size_t)v + 1] += ptr[v];
+  std::vector<int> adj((size_t)ptr[nV]);
+  {
+    std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
+    for (int el = 0; el < nT; el++) {
+      const int *t = tets + 4 * (size_t)el;
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+          if (i != j) adj[(size_t)fill[t[i]]++] = t[j];
+    }
+  }
+  // unique neighbours per vertex, then sorted by (degree, id)
+  std::vector<int> deg((size_t)nV, 0);
+  for (int v = 0; v < nV; v++) {
+    int *b = adj.data() + ptr[v], *e = adj.data() + ptr[v + 1];
+    std::sort(b, e);
+    deg[v] = (int)(std::unique(b, e) - b);
+  }
+  for (int v = 0; v < nV; v++) {
+    int *b = adj.data() + ptr[v];
+    std::sort(b, b + deg[v], [&](int x, int y) { return deg[x] != deg[y] ? deg[x] < deg[y] : x < y; });
+  }
+  order.clear();
+  order.reserve((size_t)nV);
+  std::vector<int> mark((size_t)nV, 0);  // 0 = unvisited; sweeps use increasing stamps
+  std::vector<int> queue;
+  queue.reserve((size_t)nV);
+  int stamp = 0;
+  auto sweep = [&](int root) {  // breadth-first from root over unfinished vertices; returns the last vertex reached
+    stamp++;
+    queue.clear();
+    queue.push_back(root);
+    mark[root] = stamp;
+    for (size_t h = 0; h < queue.size(); h++) {
+      const int v = queue[h];
+      const int *b = adj.data() + ptr[v];
+      for (int k = 0; k < deg[v]; k++)
+        if (mark[b[k]] >= 0 && mark[b[k]] != stamp) { mark[b[k]] = stamp; queue.push_back(b[k]); }
+    }
+    return queue.back();
+  };
+  for (int seed = 0; seed < nV; seed++) {
+    if (mark[seed] < 0) continue;           // already ordered
+    const int far1 = sweep(seed);           // pseudo-peripheral root: the far end of the far end
+    const int far2 = sweep(far1);
+    sweep(far2);
+    for (size_t h = 0; h < queue.size(); h++) { order.push_back(queue[h]); mark[queue[h]] = -1; }
+  }
+}
+
+// The numbering the row blocks are cut from: the caller's, unless its cut is large AND Cuthill-McKee's is clearly smaller
+// (structured inputs like the cube keep their numbering and their slabs).  order empty = identity.
+void choose_ordering(int nV, int nT, const int *tets, int world, std::vector<int> &order) {
+  order.clear();
+  if (world < 2 || nT == 0) return;
+  std::vector<int> bounds;
+  make_bounds(nV, nT, tets, world, bounds);
+  const long long cutI = count_cut_tets(bounds, nT, tets);
+  if (cutI * 20 <= (long long)nT) return;  // <= 5 % of the tets are cut: nothing to gain
+  std::vector<int> cm;
+  cuthill_mckee(nV, nT, tets, cm);
+  if ((int)cm.size() != nV) return;
+  std::vector<int> inv((size_t)nV);
+  for (int i = 0; i < nV; i++) inv[cm[i]] = i;
+  std::vector<int> pt(4 * (size_t)nT);
+  for (size_t i = 0; i < pt.size(); i++) pt[i] = inv[tets[i]];
+  make_bounds(nV, nT, pt.data(), world, bounds);
+  const long long cutR = count_cut_tets(bounds, nT, pt.data());
+  if (cutR * 10 < cutI * 9) order.swap(cm);
 }
 
 void make_plan(int nV, int nT, const int *tets, int world, int rank, Plan &pl) {
@@ -464,7 +554,22 @@ int fb_plan_partition(int nV, int nT, const int *tets, int world, int rank, int 
   for (size_t i = 0; i < 4 * (size_t)nT; i++)
     if (tets[i] < 0 || tets[i] >= nV) { fb_set_error("tetrahedron %zu references a vertex outside [0, %d)", i / 4, nV); return FB_ERR_BAD_MESH; }
   Plan pl;
-  make_plan(nV, nT, tets, world, rank, pl);
+  std::vector<int> order, ptets;
+  choose_ordering(nV, nT, tets, world, order);
+  if (!order.empty()) {  // plan on the renumbered mesh, report in the caller's vertex ids
+    std::vector<int> inv((size_t)nV);
+    for (int i = 0; i < nV; i++) inv[order[i]] = i;
+    ptets.resize(4 * (size_t)nT);
+    for (size_t i = 0; i < ptets.size(); i++) ptets[i] = inv[tets[i]];
+    make_plan(nV, nT, ptets.data(), world, rank, pl);
+    for (size_t i = 0; i < pl.l2g.size(); i++) pl.l2g[i] = order[pl.l2g[i]];
+    for (size_t i = 0; i < pl.nbr.size(); i++) {
+      for (size_t k = 0; k < pl.send[i].size(); k++) pl.send[i][k] = order[pl.send[i][k]];
+      for (size_t k = 0; k < pl.recv[i].size(); k++) pl.recv[i][k] = order[pl.recv[i][k]];
+    }
+  } else {
+    make_plan(nV, nT, tets, world, rank, pl);
+  }
   size_t ns = 0, nr = 0;
   for (size_t i = 0; i < pl.nbr.size(); i++) { ns += pl.send[i].size(); nr += pl.recv[i].size(); }
   counts[0] = pl.bounds[rank]; counts[1] = pl.bounds[rank + 1];
@@ -485,8 +590,21 @@ int fb_plan_partition(int nV, int nT, const int *tets, int world, int rank, int 
   return FB_OK;
 }
 
-int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, const int *tets, int nFixed, const int *fixedVerts,
+int fb_partition_ordering(int nV, int nT, const int *tets, int world, int *order, int *reordered) {
+  if (nV < 0 || nT < 0 || (nT > 0 && !tets) || world < 1 || !reordered) { fb_set_error("bad arguments to fb_partition_ordering"); return FB_ERR_INVALID_ARGUMENT; }
+  for (size_t i = 0; i < 4 * (size_t)nT; i++)
+    if (tets[i] < 0 || tets[i] >= nV) { fb_set_error("tetrahedron %zu references a vertex outside [0, %d)", i / 4, nV); return FB_ERR_BAD_MESH; }
+  std::vector<int> ord;
+  choose_ordering(nV, nT, tets, world, ord);
+  *reordered = ord.empty() ? 0 : 1;
+  if (order)
+    for (int i = 0; i < nV; i++) order[i] = ord.empty() ? i : ord[i];
+  return FB_OK;
+}
+
+int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, const int *tetsIn, int nFixed, const int *fixedVerts,
                           const fb_params *prm, int rank, int world, const void *comm_id128) {
+  const int *tets = tetsIn;
   if (!out) return FB_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (nV < 0 || nT < 0 || (nV > 0 && !x0) || (nT > 0 && !tets) || world < 1 || rank < 0 || rank >= world || nFixed < 0 ||
@@ -502,27 +620,42 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
     for (int v = 0; v < nV; v++)
       if (!used[v]) { fb_set_error("vertex %d belongs to no tetrahedron", v); return FB_ERR_BAD_MESH; }
   }
+  // The partition is cut from the caller's numbering or, for unstructured numberings, from a Cuthill-McKee ordering
+  // (choose_ordering).  From here on "global" ids are ids in that ordering; order[] maps them back to the caller's, which
+  // is what the vector API (fb_dist_upload_global / _download_owned, through l2g) and the fixed-vertex list speak.
+  std::vector<int> order, ptets, inv;
+  choose_ordering(nV, nT, tets, world, order);
+  if (!order.empty()) {
+    inv.resize((size_t)nV);
+    for (int i = 0; i < nV; i++) inv[order[i]] = i;
+    ptets.resize(4 * (size_t)nT);
+    for (size_t i = 0; i < ptets.size(); i++) ptets[i] = inv[tetsIn[i]];
+    tets = ptets.data();
+  }
   Plan pl;
   make_plan(nV, nT, tets, world, rank, pl);
   const int nLV = (int)pl.l2g.size(), nLT = (int)pl.localTets.size();
   std::vector<int> g2l((size_t)nV, -1);
   for (int i = 0; i < nLV; i++) g2l[pl.l2g[i]] = i;
   std::vector<double> lx(3 * (size_t)nLV);
-  for (int i = 0; i < nLV; i++)
-    for (int k = 0; k < 3; k++) lx[3 * (size_t)i + k] = x0[3 * (size_t)pl.l2g[i] + k];
+  for (int i = 0; i < nLV; i++) {
+    const int callers = order.empty() ? pl.l2g[i] : order[pl.l2g[i]];
+    for (int k = 0; k < 3; k++) lx[3 * (size_t)i + k] = x0[3 * (size_t)callers + k];
+  }
   std::vector<int> lt(4 * (size_t)nLT);
   for (int e = 0; e < nLT; e++)
     for (int k = 0; k < 4; k++) lt[4 * (size_t)e + k] = g2l[tets[4 * (size_t)pl.localTets[e] + k]];
   std::vector<int> fv(fixedVerts, fixedVerts + nFixed);
   std::sort(fv.begin(), fv.end());
-  std::vector<int> cd;
+  std::vector<int> cd, fl;
   for (int i = 0; i < nFixed; i++) {
     if (fv[i] < 0 || fv[i] >= nV) { fb_set_error("fixed vertex %d out of range [0, %d)", fv[i], nV); return FB_ERR_INVALID_ARGUMENT; }
     if (i && fv[i] == fv[i - 1]) { fb_set_error("fixed vertex %d listed twice", fv[i]); return FB_ERR_INVALID_ARGUMENT; }
-    const int l = g2l[fv[i]];
-    if (l < 0) continue;
-    cd.push_back(3 * l); cd.push_back(3 * l + 1); cd.push_back(3 * l + 2);
+    const int l = g2l[order.empty() ? fv[i] : inv[fv[i]]];
+    if (l >= 0) fl.push_back(l);
   }
+  std::sort(fl.begin(), fl.end());  // ascending LOCAL ids (the partition ordering need not follow the caller's numbering)
+  for (size_t i = 0; i < fl.size(); i++) { cd.push_back(3 * fl[i]); cd.push_back(3 * fl[i] + 1); cd.push_back(3 * fl[i] + 2); }
   fb_context *c = nullptr;
   FB_TRY(fb_create_local(&c, nLV, lx.data(), nLT, lt.data(), (int)cd.size(), cd.data(), nullptr, nullptr, nullptr, prm));
   FbDist *d = new FbDist();
@@ -530,9 +663,12 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
   d->p2p = 0; d->comm = nullptr; d->remoteIdx = nullptr; d->pushTicket = nullptr; d->pushFlag = nullptr; d->pushPtr = nullptr; d->pushEnt = nullptr; d->solveCount = 0; d->nOpened = 0;
   d->rank = rank; d->world = world; d->nV_global = nV; d->nT_global = nT;
   d->vbeg = pl.bounds[rank]; d->vend = pl.bounds[rank + 1];
-  d->l2g = pl.l2g;
+  d->reordered = order.empty() ? 0 : 1;
   d->owned.resize((size_t)nLV);
   for (int i = 0; i < nLV; i++) d->owned[i] = (pl.l2g[i] >= d->vbeg && pl.l2g[i] < d->vend) ? 1 : 0;
+  d->l2g = pl.l2g;  // local vertex -> the CALLER's vertex id
+  if (!order.empty())
+    for (int i = 0; i < nLV; i++) d->l2g[i] = order[pl.l2g[i]];
   d->nNbr = (int)pl.nbr.size();
   d->nbrRank = pl.nbr;
   d->sendOff.assign((size_t)d->nNbr + 1, 0);
@@ -599,6 +735,7 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
 }
 
 int fb_partition_peer_memory(const fb_context *c) { return fb_dist_p2p(c); }
+int fb_partition_reordered(const fb_context *c) { return (c && c->dist) ? c->dist->reordered : 0; }
 
 int fb_partition_range(const fb_context *c, int *b, int *e) {
   if (!c) return FB_ERR_INVALID_ARGUMENT;

@@ -246,6 +246,13 @@ int fb_create_partitioned(fb_context **out, int num_vertices, const double *rest
                           const int *fixed_vertices, const fb_params *params, int rank, int world,
                           const void *comm_id128);
 int fb_partition_range(const fb_context *ctx, int *vertex_begin, int *vertex_end);
+/* The row blocks are contiguous ranges of the caller's vertex numbering when that cuts few tets (structured meshes: the
+ * benchmark cube gets slabs), otherwise of a Cuthill-McKee ordering of the vertex graph computed on the host (METIS is not
+ * required): fb_partition_ordering returns that choice, order[new] = caller's vertex id (identity when *reordered = 0);
+ * fb_partition_range and fb_plan_partition's vertex_begin/end are positions in it.  All vertex ids and vectors crossing
+ * the ABI stay in the caller's numbering. */
+int fb_partition_ordering(int num_vertices, int num_tets, const int *tets, int world, int *order, int *reordered);
+int fb_partition_reordered(const fb_context *ctx);
 /* 1 when the ranks exchange the PCG scalars and the halo of d through peer-memory stores over NVLink (CUDA IPC mappings,
  * flags in each rank's comm block), 0 when they go through NCCL calls between kernels (FEMBRAIN_B200_P2P=0, or the
  * mapping could not be set up). */
@@ -256,8 +263,7 @@ int fb_partition_peer_memory(const fb_context *ctx);
  * inspection hooks (CSR, maps, rhs, ...) describe the rank's LOCAL system. */
 /* Host-only view of the partition (runs without a GPU): what rank `rank` of `world` owns and exchanges.
  * counts[7] = {vertex_begin, vertex_end, local vertices, local tets, neighbours, total send vertices, total recv vertices};
- * every other output may be NULL; sizes come from a first call: l2g[counts[2]] (ascending global vertex ids of the local
- * mesh), local_tets[counts[3]], nbr_ranks/send_counts/recv_counts[counts[4]], send_global[counts[5]],
+ * every other output may be NULL; sizes come from a first call: l2g[counts[2]] (the local mesh's vertices in local order: ascending position in the partition ordering, as caller's vertex ids), local_tets[counts[3]], nbr_ranks/send_counts/recv_counts[counts[4]], send_global[counts[5]],
  * recv_global[counts[6]] (concatenated per neighbour, ascending global ids). */
 int fb_plan_partition(int num_vertices, int num_tets, const int *tets, int world, int rank, int *counts, int *l2g,
                       int *local_tets, int *nbr_ranks, int *send_counts, int *recv_counts, int *send_global,

@@ -19,7 +19,8 @@ from tests import cases  # noqa: E402
 
 
 def main():
-    nx = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+    arg = sys.argv[1] if len(sys.argv) > 1 else "12"
+    nx = int(arg) if arg.isdigit() else arg
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -29,7 +30,11 @@ def main():
     dist.broadcast(idt, 0)
     comm_id = bytes(idt.cpu().numpy().tobytes())
 
-    v, t, fixed, load = cases.cube_case(nx)
+    if isinstance(nx, int):
+        v, t, fixed, load = cases.cube_case(nx)
+    else:  # a mesh from the reference's data directory (unstructured numbering: the partition is cut from a Cuthill-McKee ordering)
+        v, t, fixed = cases.golden_mesh(nx)
+        load = int(np.argmax(v[:, 1] * 1000 + v[:, 0]))
     r = 3 * len(v)
     f = cases.point_load(r, load)
     part = fb.Simulation(v, t, fixed, partition=(rank, world, comm_id), device=local)
@@ -86,7 +91,7 @@ def main():
     dist.broadcast(flag, 0)
     dist.barrier()
     if rank == 0:
-        print("DIST_CHECK", "OK" if ok else "FAILED", f"world={world} nx={nx} rows [{b},{e}) rhs_local={lrhs.size} peer_memory={part.peer_memory}", flush=True)
+        print("DIST_CHECK", "OK" if ok else "FAILED", f"world={world} nx={nx} rows [{b},{e}) rhs_local={lrhs.size} peer_memory={part.peer_memory} reordered={part.reordered}", flush=True)
     part.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag[0]) == 1 else 1)

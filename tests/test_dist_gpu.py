@@ -19,9 +19,10 @@ def _gpu_count():
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
-def test_partitioned_two_gpus_match_single_gpu():
+@pytest.mark.parametrize("mesh", ["12", "eggshell"])  # structured cube (slabs) / unstructured numbering (Cuthill-McKee ordering)
+def test_partitioned_two_gpus_match_single_gpu(mesh):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(root, "tests", "dist_check.py"), "12"]
+           "--master-port", "29533", os.path.join(root, "tests", "dist_check.py"), mesh]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert out.returncode == 0 and "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, nx, out_q):
+def _worker(rank, world, port, mesh, out_q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -30,10 +30,18 @@ def _worker(rank, world, port, nx, out_q):
         import fembrain_b200 as fb
         from oracle import pyoracle
 
-        v, t, fixed, load = cases.cube_case(nx)
+        if isinstance(mesh, int):
+            v, t, fixed, load = cases.cube_case(mesh)
+        else:
+            v, t, fixed = cases.golden_mesh(mesh)  # unstructured numbering: the plan is cut from a Cuthill-McKee ordering
         nV = len(v)
         plan = fb.plan_partition(nV, t, world, rank)
         b, e, l2g = plan["begin"], plan["end"], plan["l2g"]
+        order, reordered = fb.partition_ordering(nV, t, world)
+        assert reordered == (not isinstance(mesh, int)) or isinstance(mesh, int)
+        assert np.array_equal(np.sort(order), np.arange(nV))  # a permutation, identical on every rank
+        pos = np.empty(nV, np.int64)
+        pos[order] = np.arange(nV)  # caller's vertex id -> position in the partition ordering
         # 1. ranges tile [0, nV) and every rank computes the same boundaries
         rng = torch.tensor([b, e])
         allr = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
@@ -41,13 +49,14 @@ def _worker(rank, world, port, nx, out_q):
         bounds = [int(a[0]) for a in allr] + [int(allr[-1][1])]
         assert bounds[0] == 0 and bounds[-1] == nV and all(int(allr[i][1]) == int(allr[i + 1][0]) for i in range(world - 1))
         # 2. local mesh = exactly the tets touching an owned vertex; l2g = their vertices, ascending
-        touch = ((t >= b) & (t < e)).any(axis=1)
+        touch = ((pos[t] >= b) & (pos[t] < e)).any(axis=1)
         assert np.array_equal(plan["local_tets"], np.nonzero(touch)[0])
-        assert np.array_equal(l2g, np.unique(t[touch]))
+        mine = np.unique(t[touch])
+        assert np.array_equal(l2g, mine[np.argsort(pos[mine])])  # local order = ascending position in the ordering
         # 3. halo lists are mirror images across ranks (send of a to b == recv of b from a), ghosts are complete
-        ghosts = l2g[(l2g < b) | (l2g >= e)]
-        got = np.sort(np.concatenate([plan["recv"][p] for p in plan["neighbours"]])) if plan["neighbours"] else np.zeros(0, np.int32)
-        assert np.array_equal(got, ghosts)
+        ghosts = l2g[(pos[l2g] < b) | (pos[l2g] >= e)]
+        got = np.concatenate([plan["recv"][p] for p in plan["neighbours"]]) if plan["neighbours"] else np.zeros(0, np.int32)
+        assert np.array_equal(np.sort(got), np.sort(ghosts))
         for p in plan["neighbours"]:
             mine = torch.from_numpy(plan["send"][p].astype(np.int64))
             theirs = torch.zeros(len(plan["recv"][p]), dtype=torch.int64)
@@ -64,7 +73,7 @@ def _worker(rank, world, port, nx, out_q):
         g2l = -np.ones(nV, np.int64)
         g2l[l2g] = np.arange(len(l2g))
         xl = np.zeros(3 * len(l2g))
-        own = (l2g >= b) & (l2g < e)
+        own = (pos[l2g] >= b) & (pos[l2g] < e)
         for k in range(3):
             xl[3 * np.nonzero(own)[0] + k] = xg[3 * l2g[own] + k]  # owned entries only; ghosts arrive by exchange
         reqs, bufs = [], {}
@@ -79,14 +88,15 @@ def _worker(rank, world, port, nx, out_q):
             for k in range(3):
                 xl[3 * ridx + k] = bufs[p][:, k].numpy()
         yl = np.zeros(3 * nV)
-        for gv in range(b, e):
+        owned_ids = order[b:e]
+        for gv in owned_ids:
             for k in range(3):
                 i = 3 * gv + k
                 cols = ja[ia[i]:ia[i + 1]]
                 lc = 3 * g2l[cols // 3] + cols % 3
                 assert (g2l[cols // 3] >= 0).all()  # every column of an owned row is local (owned or ghost)
                 yl[i] = a[ia[i]:ia[i + 1]] @ xl[lc]
-        part = torch.tensor([float(yl[3 * b:3 * e] @ xg[3 * b:3 * e])], dtype=torch.float64)
+        part = torch.tensor([float(yl @ xg)], dtype=torch.float64)  # yl is zero outside the owned rows
         dist.all_reduce(part)
         yt = torch.from_numpy(yl)
         dist.all_reduce(yt)
@@ -99,16 +109,41 @@ def _worker(rank, world, port, nx, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_partition_plan_and_halo_exchange_over_gloo(world):
+@pytest.mark.parametrize("world,mesh", [(2, 7), (3, 7), (3, "beam3")])
+def test_partition_plan_and_halo_exchange_over_gloo(world, mesh):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 7, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mesh, q)) for r in range(world)]
     [p.start() for p in procs]
     res = [q.get(timeout=180) for _ in range(world)]
     [p.join(timeout=60) for p in procs]
     assert all(r[1] == "ok" for r in res), res
+
+
+def test_unstructured_numbering_is_reordered_and_the_cut_shrinks():
+    """blobtree/eggshell.veg (numbering as FemBrain's polygonizer + TetGen left it): row blocks of the caller's numbering make
+    nearly every vertex a ghost of every rank; the Cuthill-McKee ordering chosen on the host cuts that by more than half."""
+    import fembrain_b200 as fb
+
+    v, t, fixed = cases.golden_mesh("eggshell")
+    nV = len(v)
+    inc = np.bincount(t.ravel(), minlength=nV)
+    for world in (2, 4, 8):
+        order, reordered = fb.partition_ordering(nV, t, world)
+        assert reordered and np.array_equal(np.sort(order), np.arange(nV))
+        bounds = np.searchsorted(np.cumsum(inc), inc.sum() * np.arange(1, world) / world)  # the caller's numbering, same rule
+        owner = np.searchsorted(bounds, np.arange(nV), side="right")
+        ghosts_identity = sum(len(np.unique(t[(owner[t] == r).any(axis=1)])) - int((owner == r).sum()) for r in range(world))
+        ghosts, owned = 0, 0
+        for r in range(world):
+            p = fb.plan_partition(nV, t, world, r)
+            ghosts += len(p["l2g"]) - (p["end"] - p["begin"])
+            owned += p["end"] - p["begin"]
+        assert owned == nV
+        assert ghosts < 0.5 * ghosts_identity, (world, ghosts, ghosts_identity)
+    cube_v, cube_t, _, _ = cases.cube_case(33)
+    assert not fb.partition_ordering(len(cube_v), cube_t, 2)[1]  # slabs of the structured cube are kept
 
 
 def test_partition_plan_balances_incidences():
@@ -118,9 +153,10 @@ def test_partition_plan_balances_incidences():
     inc = np.bincount(t.ravel(), minlength=len(v))
     for world in (2, 4, 8):
         loads = []
+        order, _ = fb.partition_ordering(len(v), t, world)
         for r in range(world):
             p = fb.plan_partition(len(v), t, world, r)
-            loads.append(inc[p["begin"]:p["end"]].sum())
+            loads.append(inc[order[p["begin"]:p["end"]]].sum())
         assert sum(loads) == inc.sum()
         assert max(loads) <= 1.25 * inc.sum() / world
     one = fb.plan_partition(len(v), t, 1, 0)

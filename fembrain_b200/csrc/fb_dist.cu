@@ -222,7 +222,7 @@ void choose_ordering(int nV, int nT, const int *tets, int world, std::vector<int
   std::vector<int> bounds;
   make_bounds(nV, nT, tets, world, bounds);
   const long long cutI = count_cut_tets(bounds, nT, tets);
-  if (cutI * 20 <= (long long)nT) return;  // <= 5 % of the tets are cut: nothing to gain
+  if (cutI * 100 <= 15ll * nT) return;  // <= 15 % of the tets are cut (a banded numbering: slabs): keep it, skip the graph work
   std::vector<int> cm;
   cuthill_mckee(nV, nT, tets, cm);
   if ((int)cm.size() != nV) return;

@@ -488,7 +488,7 @@ def _main(saved_stdout):
     ap.add_argument("--cpu-cg-iters", type=int, default=40, help="PCG iterations in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="configs[3]: step a batch of this many independent meshes (use with --nx 33)")
-    ap.add_argument("--streams", type=int, default=4, help="host threads / concurrent contexts per GPU in --batch mode")
+    ap.add_argument("--streams", type=int, default=8, help="host threads / concurrent contexts per GPU in --batch mode (B200, 32 meshes of 196,608 tets on one GPU: 75.2 / 81.1 / 79.7 mesh-steps/s with 4 / 8 / 16)")
     ap.add_argument("--partitioned", action="store_true",
                     help="N>1: split ONE mesh by row blocks across the ranks (NCCL halo exchange, strong scaling) instead of one mesh per rank")
     args = ap.parse_args()

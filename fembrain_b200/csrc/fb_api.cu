@@ -220,7 +220,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   c->prm = p;
   c->nV = nV; c->nT = nT; c->r = 3 * nV;
   c->haptic_rings = 5;  // m_hapticForceNeighorhoodSize, DEF/Deformable.cpp ctor
-  c->segs.beg[0] = 0; c->segs.end[0] = nV;
+  c->row_lo = 0; c->row_hi = nV;
   int st = FB_OK;
 #define CR(call) do { st = (call); if (st != FB_OK) { free_all(c); return st; } } while (0)
 #define CRC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fb_set_error("%s -> %s", #call, cudaGetErrorString(e__)); free_all(c); return e__ == cudaErrorMemoryAllocation ? FB_ERR_OUT_OF_MEMORY : FB_ERR_CUDA; } } while (0)

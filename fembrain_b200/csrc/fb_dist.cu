@@ -681,25 +681,15 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
     d->recvOff[i + 1] = (int)rIdx.size();
   }
   c->dist = d;
-  {  // rows the solver visits: owned rows only, those that read ghost columns (= the send lists) last (FbRowSegs)
+  {  // rows the solver's products visit: the owned rows, contiguous in the local numbering; ghost rows are never multiplied
     int lo = 0, hi = nLV;
     while (lo < nLV && !d->owned[lo]) lo++;
     while (hi > lo && !d->owned[hi - 1]) hi--;
     bool contiguous = true;
     for (int i = lo; i < hi; i++) contiguous &= (d->owned[i] != 0);
     if (!contiguous) { fb_set_error("owned rows are not contiguous in the local numbering"); fb_destroy(c); return FB_ERR_INVALID_ARGUMENT; }
-    std::vector<unsigned char> cut((size_t)nLV, 0);
-    for (size_t k = 0; k < sIdx.size(); k++) cut[sIdx[k]] = 1;
-    int bestBeg = lo, bestEnd = lo, runBeg = lo;  // longest run of rows that read no ghost column
-    for (int i = lo; i <= hi; i++) {
-      if (i == hi || cut[i]) {
-        if (i - runBeg > bestEnd - bestBeg) { bestBeg = runBeg; bestEnd = i; }
-        runBeg = i + 1;
-      }
-    }
-    c->segs.beg[0] = bestBeg; c->segs.end[0] = bestEnd;
-    c->segs.beg[1] = lo;      c->segs.end[1] = bestBeg;
-    c->segs.beg[2] = bestEnd; c->segs.end[2] = hi;
+    c->row_lo = lo;
+    c->row_hi = hi;
   }
   int st = FB_OK;
 #define DCHK(call) do { st = (call); if (st != FB_OK) { fb_destroy(c); return st; } } while (0)

@@ -49,11 +49,6 @@ struct FbScalars {
 
 struct FbDist;  // multi-GPU state (fb_dist.cu)
 
-// Block rows the solver's products visit, in order.  One GPU: [0] = all rows.  Partitioned: [0] = owned rows that read no
-// ghost column, [1] and [2] = the owned rows before / after them (next to the cuts); ghost rows are not visited at all.
-struct FbRowSegs {
-  int beg[3], end[3];
-};
 
 struct fb_context {
   int device;
@@ -134,7 +129,7 @@ struct fb_context {
   int last_iters;        // signed like the reference's return value
   double last_ratio;
   long long launches;
-  FbRowSegs segs;
+  int row_lo, row_hi;    // block rows the solver's products visit: all rows, or the OWNED rows of a partitioned context
   int spmv_group;        // lanes per block row chosen at setup
   int use_rows3;         // 1: k_spmv_rows3 (16 lanes per row, all loads of a row in flight), 0: k_spmv<G>
   int rows3_minb;        // resident CTAs/SM requested for k_spmv_rows3 modes 0-2 (4 or 5)

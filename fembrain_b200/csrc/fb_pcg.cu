@@ -196,7 +196,7 @@ __device__ __forceinline__ void finish_kernel(double (&part)[3], FbScalars *sc, 
 
 // ---- generic row-per-G-lanes SpMV (G = 8 or 32: meshes with very short or very long rows) -------------------
 template <int G, int MODE>
-__global__ void __launch_bounds__(SPMV_TB) k_spmv(FbRowSegs segs, const int *__restrict__ bp, const int *__restrict__ bc,
+__global__ void __launch_bounds__(SPMV_TB) k_spmv(int rowBeg, int rowEnd, const int *__restrict__ bp, const int *__restrict__ bc,
                                                   const double *__restrict__ A, const double *__restrict__ x,
                                                   double *__restrict__ y, const unsigned char *__restrict__ mask,
                                                   const double *__restrict__ b, const double *__restrict__ invD,
@@ -214,9 +214,7 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(FbRowSegs segs, const int *__r
   const int group = blockIdx.x * groupsPerBlock + threadIdx.x / G;
   const int nGroups = gridDim.x * groupsPerBlock;
   double part[3] = {0.0, 0.0, 0.0};
-#pragma unroll 1
-  for (int sg = 0; sg < 3; sg++)
-  for (int v = segs.beg[sg] + group; v < segs.end[sg]; v += nGroups) {
+  for (int v = rowBeg + group; v < rowEnd; v += nGroups) {
     const int rs = __ldg(bp + v), re = __ldg(bp + v + 1);
     const int n3 = 3 * (re - rs);
     const double *a0 = A + 9 * (size_t)rs;
@@ -619,23 +617,15 @@ void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y
   if (peer) pa = *peer; else memset(&pa, 0, sizeof(pa));
   const int grid = c->grid_spmv[MODE];
   // MODE 0 is the plain product of the inspection calls: all rows.  The solver's products visit owned rows only.
-  const FbRowSegs &sg = c->segs;
-  const int lo = (sg.end[1] > sg.beg[1]) ? sg.beg[1] : sg.beg[0], hi = (sg.end[2] > sg.beg[2]) ? sg.end[2] : sg.end[0];
+  const int lo = (MODE == 0) ? 0 : c->row_lo, hi = (MODE == 0) ? c->nV : c->row_hi;
   if (c->use_rows3) {
-    if (MODE == 0)
-      fb_launch(false, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, 0, c->nV, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
-    else
-      fb_launch(c->pdl, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
+    fb_launch(c->pdl && MODE != 0, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
   } else if (MODE != 3) {
     constexpr int M = MODE == 3 ? 1 : MODE;
-    FbRowSegs segs = c->segs;
-    if (MODE == 0) { segs.beg[0] = 0; segs.end[0] = c->nV; }
-    else { segs.beg[0] = lo; segs.end[0] = hi; }
-    segs.beg[1] = segs.end[1] = segs.beg[2] = segs.end[2] = 0;
     switch (c->spmv_group) {
-      case 8: k_spmv<8, M><<<grid, SPMV_TB, 0, c->stream>>>(segs, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
-      case 32: k_spmv<32, M><<<grid, SPMV_TB, 0, c->stream>>>(segs, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
-      default: k_spmv<16, M><<<grid, SPMV_TB, 0, c->stream>>>(segs, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      case 8: k_spmv<8, M><<<grid, SPMV_TB, 0, c->stream>>>(lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      case 32: k_spmv<32, M><<<grid, SPMV_TB, 0, c->stream>>>(lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
+      default: k_spmv<16, M><<<grid, SPMV_TB, 0, c->stream>>>(lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa); break;
     }
   }
   c->launches++;

@@ -595,6 +595,9 @@ int one_wave(const fb_context *c, K kernel, int tb, size_t want) {
   int perSM = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, tb, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
   size_t cap = (size_t)c->sm_count * (size_t)perSM;
+  // (Sizing the grids of a batch's contexts for 1/N of the GPU so that N of them run side by side was tried for config 4:
+  //  32 meshes of 196,608 tets on one GPU, 8 host threads: 79.6 / 81.3 / 72.3 / 65.6 mesh-steps/s for N = 1 / 2 / 4 / 8 —
+  //  no gain, dropped; profiles/r01_batch_graph.txt.)
   if (cap > FB_MAX_PARTIALS) cap = FB_MAX_PARTIALS;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
@@ -672,8 +675,11 @@ void enqueue_iteration_p2p(fb_context *c, int it) {
 }
 
 // the reference's literal order, three kernels (+ NCCL in partitioned contexts without peer mapping)
-void enqueue_iteration_kernels(fb_context *c, int it) {
+// fromCounter: the kernels take the iteration number from the device counter instead of an argument, so that a captured
+// 30-iteration period can be replayed (`it` then only places the refresh)
+void enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) {
   if (fb_dist_p2p(c)) { enqueue_iteration_p2p(c, it); return; }
+  const int itArg = fromCounter ? 0 : it;
   const int n = c->r, vg = c->grid_vec;
   double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
   FbPeerArgs nopeer;
@@ -694,17 +700,17 @@ void enqueue_iteration_kernels(fb_context *c, int it) {
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
   if (it % 30 == 0) {
-    fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
+    fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
     c->launches++;
     launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
     if (defer) { rhoSlots = c->partials; nRhoSlots = c->grid_spmv[2]; }
   } else {
-    fb_launch(c->pdl, c->stream, k_update<false>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, it, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
+    fb_launch(c->pdl, c->stream, k_update<false>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
     c->launches++;
     if (defer) { rhoSlots = slotsV; nRhoSlots = vg; }
   }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
-  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, it, rhoSlots, nRhoSlots, nopeer, nullptr, nopush);
+  fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, itArg, rhoSlots, nRhoSlots, nopeer, nullptr, nopush);
   c->launches++;
   if (c->dist) fb_dist_halo_exchange(c, c->dir);
 }
@@ -787,7 +793,12 @@ int ensure_period_graph(fb_context *c) {
   const long long before = c->launches;
   if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_failed = 1; return FB_OK; }
   int kernels = 0;
-  for (int k = 1; k <= 30; k++) kernels += enqueue_iteration_fused(c, k, false);
+  if (c->pcg_fused) {
+    for (int k = 1; k <= 30; k++) kernels += enqueue_iteration_fused(c, k, false);
+  } else {
+    for (int k = 1; k <= 30; k++) enqueue_iteration_kernels(c, k, true);
+    kernels = (int)(c->launches - before);
+  }
   cudaError_t e = cudaStreamEndCapture(st, &graph);
   c->launches = before;  // captured, not launched
   if (e != cudaSuccess || !graph) { cudaGetLastError(); c->graph_failed = 1; return FB_OK; }
@@ -844,7 +855,14 @@ int fb_spmv_plan(fb_context *c) {
   // at 1M, 497.6 / 525.8 at 10M — the extra reads and the three-sum epilogue of k_spmv_rows3<3> cost what the saved
   // launch gains, and graph replay changes nothing (the gaps are device-side dependencies, not host launch cost).
   c->pcg_fused = c->use_rows3 && mode && (!strcmp(mode, "fused") || !strcmp(mode, "fused_nograph"));
-  c->pcg_graph = c->pcg_fused && !(mode && !strcmp(mode, "fused_nograph"));
+  // CUDA-graph replay of a 30-iteration period of the three-kernel schedule (3 x 30 + 1 kernels per cudaGraphLaunch),
+  // opt-in with FEMBRAIN_B200_PCG_GRAPH=1.  Measured on B200 (profiles/r01_batch_graph.txt): the isolated iteration loop
+  // gains (19.4 -> 17.9 us at 200 k tets, 50.1 -> 48.7 at 1M) but a step does not (13.05 vs 13.07 ms at 200 k tets: the
+  // gaps inside a step are device-side dependencies), nor does the batch of 32 concurrent meshes (81.3 vs 78.9 mesh-steps/s),
+  // which therefore is not bound by the host's launch rate.
+  const char *gr = getenv("FEMBRAIN_B200_PCG_GRAPH");
+  const bool graphKernels = gr && atoi(gr) != 0;
+  c->pcg_graph = c->pcg_fused ? !(mode && !strcmp(mode, "fused_nograph")) : graphKernels;
   const char *pdl = getenv("FEMBRAIN_B200_PDL");
   c->pdl = !(pdl && atoi(pdl) == 0);
   return fb_pcg_plan_persistent(c);
@@ -874,7 +892,7 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
     return finish_solve(c);
   }
   const bool fused = c->pcg_fused && !c->dist;
-  const bool useGraph = fused && c->pcg_graph && !c->profiling;
+  const bool useGraph = c->pcg_graph && !c->dist && !c->profiling;
   if (useGraph) FB_TRY(ensure_period_graph(c));
   // Iterations are enqueued in chunks of one refresh period; the loop condition lives on the device (kernels turn
   // into no-ops once `done` is set).  The host looks at the flag of chunk k-1 while chunk k runs.
@@ -919,7 +937,7 @@ int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
     FB_CUDA(cudaEventRecord(c->ev[3], st));
     FB_TRY(fb_pcg_launch_persistent(c));
   } else {
-    const bool useGraph = fused && c->pcg_graph;
+    const bool useGraph = c->pcg_graph && !c->dist;
     if (useGraph) FB_TRY(ensure_period_graph(c));
     int it = 1;
     auto run = [&](int count) {

@@ -401,8 +401,19 @@ def run_batch(args):
         ang = 2.0 * np.pi * m / max(args.batch, 1)
         f = np.zeros(r)
         f[corner], f[corner + 2] = 1e4 * np.cos(ang), 1e4 * np.sin(ang)
-        sims.append(fb.Simulation(v, t, fixed, device=local))
-        forces.append(torch.from_numpy(f).cuda())
+        if args.group > 0:
+            forces.append(f)
+        else:
+            sims.append(fb.Simulation(v, t, fixed, device=local))
+            forces.append(torch.from_numpy(f).cuda())
+    if args.group > 0:
+        # fb_create_batch: `group` meshes per context as one block-diagonal system, PCG scalars and stopping rule per mesh
+        grouped = []
+        for g0 in range(0, len(mine), args.group):
+            n = min(args.group, len(mine) - g0)
+            sims.append(fb.Simulation(batch=[(v, t, fixed)] * n, device=local))
+            grouped.append(torch.from_numpy(np.concatenate(forces[g0:g0 + n])).cuda())
+        forces = grouped
     torch.cuda.synchronize()
     nthreads = max(1, min(args.streams, len(sims)))
     iters = [[] for _ in sims]
@@ -413,7 +424,7 @@ def run_batch(args):
                 sims[k].set_external_forces_dev(forces[k].data_ptr())
                 sims[k].do_timestep()
                 if record:
-                    iters[k].append(sims[k].last_cg_iterations)
+                    iters[k].append(int(sims[k].batch_cg_iterations()[0][0]) if args.group > 0 else sims[k].last_cg_iterations)
 
     def region(nsteps, record):
         if world > 1:
@@ -445,6 +456,9 @@ def run_batch(args):
         cfg = config_dict(nx, nT, world, False)
         cfg["workload"] = f"batch of {args.batch} independent meshes, each " + cfg["workload"] + " (load direction rotated per mesh)"
         cfg["parallelism"] = f"{args.batch // world} meshes per GPU on {nthreads} host threads/streams, no communication"
+        if args.group > 0:
+            cfg["parallelism"] = (f"{args.batch // world} meshes per GPU in batch contexts of {args.group} (fb_create_batch: block-diagonal "
+                                  f"system, PCG scalars and stopping rule per mesh), {nthreads} host threads/streams, no communication")
         cfg["timing"] = "host wall clock between device synchronisations (many streams), max over ranks"
         args.emit({
             "metric": "fem_mesh_steps_per_s", "value": value, "unit": "mesh-steps/s", "n_gpus": world, "steps": args.steps,
@@ -489,6 +503,7 @@ def _main(saved_stdout):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="configs[3]: step a batch of this many independent meshes (use with --nx 33)")
     ap.add_argument("--streams", type=int, default=8, help="host threads / concurrent contexts per GPU in --batch mode (B200, 32 meshes of 196,608 tets on one GPU: 75.2 / 81.1 / 79.7 mesh-steps/s with 4 / 8 / 16)")
+    ap.add_argument("--group", type=int, default=0, help="--batch mode: meshes per batch context (fb_create_batch); 0 = one context per mesh")
     ap.add_argument("--partitioned", action="store_true",
                     help="N>1: split ONE mesh by row blocks across the ranks (NCCL halo exchange, strong scaling) instead of one mesh per rank")
     args = ap.parse_args()

@@ -98,6 +98,8 @@ def load_library():
         "fb_deformable_pick_vertices": (ci, [vp, vp, vp, ci, vp, vp, vp]), "fb_deformable_pick_vertex": (ci, [vp, vp, vp, vp, vp]),
         "fb_force_assembly_seconds": (cd, [vp]), "fb_system_solve_seconds": (cd, [vp]), "fb_step_seconds": (cd, [vp]),
         "fb_last_cg_iterations": (ci, [vp]), "fb_last_cg_residual_ratio": (cd, [vp]),
+        "fb_create_batch": (ci, [pp, ci, vp, vp, vp, vp, vp, vp, prm]), "fb_batch_count": (ci, [vp]),
+        "fb_batch_offsets": (ci, [vp, vp, vp]), "fb_batch_last_cg_iterations": (ci, [vp, vp, vp]),
         "fb_partition_ordering": (ci, [ci, ci, vp, ci, vp, C.POINTER(ci)]), "fb_partition_reordered": (ci, [vp]),
         "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]), "fb_trim_memory": (ci, []),
         "fb_get_stiffness_csr": (ci, [vp, vp, vp]), "fb_get_mass_csr": (ci, [vp, vp, vp, vp]),
@@ -238,11 +240,25 @@ class Simulation:
     """One deformable model on one B200: the C-ABI context behind the reference's integrator interface."""
 
     def __init__(self, verts=None, tets=None, fixed_verts=(), constrained_dofs=None, materials=None, partition=None, veg_path=None,
-                 **params):
+                 batch=None, **params):
+        """batch = [(verts, tets, fixed_verts), ...]: fb_create_batch — independent meshes in one context; every vector of the
+        API is then the concatenation in list order."""
         self._lib = load_library()
         self._h = C.c_void_p()
         p = default_params(**params)
         self.params = p
+        if batch is not None:
+            vs = [_f64(m[0]).reshape(-1, 3) for m in batch]
+            ts = [_i32(m[1]).reshape(-1, 4) for m in batch]
+            fs = [_i32(m[2]).reshape(-1) for m in batch]
+            nv, nt, nf = (_i32([len(a) for a in arrs]) for arrs in (vs, ts, fs))
+            v, t = np.ascontiguousarray(np.concatenate(vs)), np.ascontiguousarray(np.concatenate(ts))
+            f = np.ascontiguousarray(np.concatenate(fs)) if sum(len(a) for a in fs) else np.zeros(1, np.int32)
+            st = self._lib.fb_create_batch(C.byref(self._h), len(batch), _ptr(nv), _ptr(v), _ptr(nt), _ptr(t), _ptr(nf), _ptr(f), C.byref(p))
+            self._check(st, "fb_create_batch")
+            self.nV, self.nT = len(v), len(t)
+            self.r = self._lib.fb_num_dofs(self._h)
+            return
         if veg_path is not None:
             fx = _i32(fixed_verts)
             st = self._lib.fb_create_from_veg(C.byref(self._h), str(veg_path).encode(), len(fx), _ptr(fx), C.byref(p))
@@ -278,6 +294,23 @@ class Simulation:
         if st != FB_OK:
             detail = self._lib.fb_last_error_string().decode() or self._lib.fb_status_string(st).decode()
             raise FemBrainError(st, where, detail)
+
+    @property
+    def batch_count(self):
+        return int(self._lib.fb_batch_count(self._h))
+
+    def batch_offsets(self):
+        n = self.batch_count
+        vo, to = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.int32)
+        self._check(self._lib.fb_batch_offsets(self._h, _ptr(vo), _ptr(to)), "fb_batch_offsets")
+        return vo, to
+
+    def batch_cg_iterations(self):
+        """Per mesh: the reference's return value (+iterations / -iterations if not converged) and rho_final / rho_0."""
+        n = self.batch_count
+        it, ra = np.zeros(n, np.int32), np.zeros(n)
+        self._check(self._lib.fb_batch_last_cg_iterations(self._h, _ptr(it), _ptr(ra)), "fb_batch_last_cg_iterations")
+        return it, ra
 
     @property
     def peer_memory(self):

@@ -27,6 +27,7 @@ UNITS = {
     "fb_pcg.cu": [],
     "fb_pcg_persistent.cu": [],
     "fb_dist.cu": [],
+    "fb_batch.cu": [],
     "fb_veg.cu": ["-fmad=false"],
     "fb_deformable.cu": ["-fmad=false"],
 }

@@ -47,7 +47,8 @@ struct FbScalars {
 
 #define FB_MAX_PARTIALS 4096
 
-struct FbDist;  // multi-GPU state (fb_dist.cu)
+struct FbDist;   // multi-GPU state (fb_dist.cu)
+struct FbBatch;  // a batch of independent meshes in one context (fb_batch.cu)
 
 
 struct fb_context {
@@ -149,6 +150,7 @@ struct fb_context {
   int prof_samples;
 
   FbDist *dist;
+  FbBatch *batch;
 };
 
 // ---- fb_api.cu -----------------------------------------------------------------------------------
@@ -182,6 +184,9 @@ void fb_pcg_release(fb_context *c);
 // ---- fb_pcg_persistent.cu --------------------------------------------------------------------------
 int fb_pcg_plan_persistent(fb_context *c);
 int fb_pcg_launch_persistent(fb_context *c);
+// ---- fb_batch.cu -----------------------------------------------------------------------------------
+int fb_batch_pcg_solve(fb_context *c, double eps, int max_it);  // every mesh of the batch, own scalars and stopping rule each
+void fb_batch_destroy(fb_context *c);
 // ---- fb_dist.cu ------------------------------------------------------------------------------------
 int fb_dist_halo_exchange(fb_context *c, double *vec);
 int fb_dist_allreduce_scalar(fb_context *c, const double *dev_part, double *dev_total);

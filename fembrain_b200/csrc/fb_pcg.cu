@@ -99,47 +99,6 @@ __device__ __forceinline__ bool block_reduce_to_total(double (&v)[N], double *sl
   return true;
 }
 
-// Deferred variant: the per-CTA sum goes to its slot and the CONSUMER kernel adds the slots (cta_sum_slots), every CTA
-// redundantly and in the same fixed order.  This takes the ticket atomics and the serial last-CTA pass off the tail of
-// the producer (the SpMV) — the slots are L2-resident and read in parallel by all CTAs of the next kernel.
-template <int TB>
-__device__ __forceinline__ void block_reduce_to_slot(double v, double *slots) {
-  __shared__ double wsum1[TB / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if (lane == 0) wsum1[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    double s = (lane < TB / 32) ? wsum1[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) slots[blockIdx.x] = s;
-  }
-}
-
-// same association order as the last-CTA pass of block_reduce_to_total: thread t adds slots t, t+TB, ..., then the tree
-template <int TB>
-__device__ __forceinline__ double cta_sum_slots(const double *__restrict__ slots, int n) {
-  __shared__ double wsum2[TB / 32];
-  __shared__ double bcast;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += TB) s += __ldcg(slots + i);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0) wsum2[warp] = s;
-  __syncthreads();
-  if (warp == 0) {
-    double z = (lane < TB / 32) ? wsum2[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) z += __shfl_down_sync(0xffffffffu, z, o);
-    if (lane == 0) bcast = z;
-  }
-  __syncthreads();
-  return bcast;
-}
-
 // what the lanes holding a finished row do with it, per MODE:
 // 0: y = A x                                   generic product (no mask, no sums)
 // 1: y = mask(A x); sum x.y                    q = A d with d.q                 (kernels schedule)
@@ -883,6 +842,7 @@ void fb_pcg_release(fb_context *c) {
 // Solves Keff x = rhs on the constrained DOFs, x0 = 0.  On return c->last_iters holds the
 // reference's return value: +iterations if converged, -iterations otherwise (CGSolver.cpp:189).
 int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
+  if (c->batch) return fb_batch_pcg_solve(c, eps, maxIt);
   cudaStream_t st = c->stream;
   if (c->r == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
   c->nprof = 0;
@@ -926,6 +886,7 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
 }
 
 int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
+  if (c->batch) { fb_set_error("fb_bench_cg_iteration on a batch context"); return FB_ERR_NOT_SUPPORTED; }
   // time `repeats` full CG iterations on the current system with the stopping rule disabled (eps = 0)
   if (c->r == 0 || repeats <= 0) { *sec = 0.0; return FB_OK; }
   cudaStream_t st = c->stream;

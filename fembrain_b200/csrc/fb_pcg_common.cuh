@@ -57,6 +57,47 @@ __device__ __forceinline__ void load_row_chunk(const double *__restrict__ A, int
 }
 
 
+// Deferred variant: the per-CTA sum goes to its slot and the CONSUMER kernel adds the slots (cta_sum_slots), every CTA
+// redundantly and in the same fixed order.  This takes the ticket atomics and the serial last-CTA pass off the tail of
+// the producer (the SpMV) — the slots are L2-resident and read in parallel by all CTAs of the next kernel.
+template <int TB>
+__device__ __forceinline__ void block_reduce_to_slot(double v, double *slots) {
+  __shared__ double wsum1[TB / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) wsum1[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double s = (lane < TB / 32) ? wsum1[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) slots[blockIdx.x] = s;
+  }
+}
+
+// same association order as the last-CTA pass of block_reduce_to_total: thread t adds slots t, t+TB, ..., then the tree
+template <int TB>
+__device__ __forceinline__ double cta_sum_slots(const double *__restrict__ slots, int n) {
+  __shared__ double wsum2[TB / 32];
+  __shared__ double bcast;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += TB) s += __ldcg(slots + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) wsum2[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double z = (lane < TB / 32) ? wsum2[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_down_sync(0xffffffffu, z, o);
+    if (lane == 0) bcast = z;
+  }
+  __syncthreads();
+  return bcast;
+}
+
 // ---- peer-memory exchange between the ranks of a partitioned context (one process per GPU, NVLink/NVSwitch) --------
 // Every rank owns a small "comm block" in device memory, mapped into all other ranks with CUDA IPC.  A producer kernel
 // stores its value into slot [rank] of EVERY rank's block, fences at system scope, then stores the epoch into flag

@@ -235,6 +235,22 @@ int fb_bench_spmv(fb_context *ctx, int repeats, double *seconds_per_launch);
 int fb_bench_assembly(fb_context *ctx, int repeats, double *seconds_per_launch);
 int fb_bench_cg_iteration(fb_context *ctx, int repeats, double *seconds_per_iteration);
 
+/* ---- a batch of independent meshes in one context (BASELINE config 4) ----------------------------
+ * In the reference every mesh is its own Deformable with its own integrator and CG solver.  A batch context holds `count`
+ * meshes as ONE block-diagonal system: setup, assembly, right-hand side and state update are the single-mesh code on the
+ * concatenated mesh (values bit-identical to a context per mesh); PCG keeps the scalars, the iteration count and the
+ * stopping rule of CGSolver::SolveLinearSystemWithJacobiPreconditioner (VEGA/sparseSolver/CGSolver.cpp:129-190) PER MESH,
+ * and every kernel launch covers all meshes that are still iterating.  Inputs are concatenated in mesh order: vertices,
+ * tets and fixed vertices with MESH-LOCAL vertex ids.  Every vector of the force/state API is the concatenation in the
+ * same order (fb_batch_offsets gives the first vertex / tet of every mesh, count + 1 entries each).  fb_step returns
+ * FB_ERR_SOLVER_NOT_CONVERGED if any mesh did not converge; fb_last_cg_iterations is the largest count (negative in that
+ * case), fb_batch_last_cg_iterations the reference's return value per mesh. */
+int fb_create_batch(fb_context **out, int count, const int *num_vertices, const double *rest_positions, const int *num_tets,
+                    const int *tets, const int *num_fixed_vertices, const int *fixed_vertices, const fb_params *params);
+int fb_batch_count(const fb_context *ctx);
+int fb_batch_offsets(const fb_context *ctx, int *vertex_offsets, int *tet_offsets);
+int fb_batch_last_cg_iterations(const fb_context *ctx, int *iterations, double *residual_ratios);
+
 /* ---- partitioned (multi-GPU) contexts: one process per GPU, row-block partition -----------------
  * No reference counterpart (the reference is single-threaded CPU code).  Every rank
  * passes the same global mesh; the context keeps rows [vertex_begin, vertex_end) of this rank plus

@@ -25,18 +25,19 @@ struct FbBatch {
   int count;                 // meshes
   std::vector<int> vtx;      // [count+1] first vertex of every mesh in the concatenated numbering
   std::vector<int> tet;      // [count+1] first tet
-  int nChunks;
+  int nW, nU;                // product units (one warp each) and vector units (one CTA trip each)
   // device
-  int *chunkRow;             // [nChunks+1] block-row boundaries
-  int *chunkMesh;            // [nChunks]
-  int *meshChunk;            // [count+1] chunk range of every mesh
+  int4 *wmeta;               // [nW] {first block row, end block row, mesh, 0} of every product unit
+  int4 *umeta;               // [nU] the same for the vector units
+  int *meshW, *meshU;        // [count+1] unit ranges of every mesh
   double *rho;               // [2][count]
   double *rho0;              // [count]
   int *iters;                // [count] iterations completed
   int *done;                 // [count]
-  unsigned int *ticket;      // [count] chunks of the mesh that have finished the direction update
+  unsigned int *ticket;      // [count] vector units of the mesh that have finished the direction update
   int *active;               // [1] meshes still iterating
-  double *slotsA, *slotsB;   // [nChunks] per-chunk sums (d.q / sum r^2 invD)
+  double *slotsA;            // [nW] per-unit sums of the products (d.q; after a refresh sum r^2 invD)
+  double *slotsB;            // [nU * warps per CTA] per-warp sums of the vector kernels (sum r^2 invD)
   std::vector<int> itersHost;
   std::vector<double> ratioHost;
 };
@@ -44,113 +45,158 @@ struct FbBatch {
 namespace {
 
 constexpr int BT_TB = 256;
-constexpr int BT_ROWS = 128;  // block rows per chunk: 8 rows per 16-lane group
+constexpr int BT_WARPS = BT_TB / 32;
+constexpr int BT_WROWS = 32;   // block rows per product unit: 16 rows for each 16-lane half of the warp
+constexpr int BT_UROWS = 256;  // block rows per vector unit: 768 scalars, 3 per thread, all requested at once
+constexpr int BT_UITEMS = 3 * BT_UROWS / BT_TB;
+constexpr int BT_SD = 2048;    // meshes whose `done` flag is staged in shared memory by the product kernel
 
 struct BatchArgs {
-  const int *chunkRow, *chunkMesh, *meshChunk;
+  const int4 *wmeta, *umeta;
+  const int *meshW, *meshU;
   double *rho, *rho0;
   int *iters, *done, *active;
   unsigned int *ticket;
   double *slotsA, *slotsB;
-  int count, maxIt;
+  int count, maxIt, nW, nU;
   double eps2;
 };
 
-// rows [r0, r1) of y = mask(A x) (MODE 1, returns sum x.y) or y = mask(b - A x) (MODE 2, returns sum y^2 invD); 16 lanes per
-// block row, all loads of a row in flight (the loop body of k_spmv_rows3)
-template <int MODE>
-__device__ __forceinline__ double batch_rows(int r0, int r1, const int *__restrict__ bp, const int *__restrict__ bc,
-                                             const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
-                                             const unsigned char *__restrict__ mask, const double *__restrict__ b,
-                                             const double *__restrict__ invD) {
-  const int lane = threadIdx.x & (TILE_G - 1);
-  const unsigned gmask = 0xffffu << (threadIdx.x & 16);
-  const int groups = BT_TB / TILE_G;
-  double part = 0.0;
-  for (int v = r0 + threadIdx.x / TILE_G; v < r1; v += groups) {
-    const int rs = __ldg(bp + v), re = __ldg(bp + v + 1);
-    const int n3 = 3 * (re - rs);
-    const size_t row = 3 * (size_t)v + (lane < 3 ? lane : 0);
-    double xr = 0.0, br = 0.0, wr = 0.0;
-    unsigned char mk = 0;
-    if (lane < 3) {
-      mk = __ldg(mask + row);
-      if (MODE == 1) xr = __ldg(x + row);
-      if (MODE == 2) { br = __ldg(b + row); wr = __ldg(invD + row); }
-    }
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    for (int base = 0; base < n3; base += TILE_CHUNK) {
-      RowVals val;
-      int col[3];
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-      for (int p = 0; p < 3; p++) {
-        const int t = base + lane + TILE_G * p;
-        col[p] = (t < n3) ? __ldg(bc + rs + t / 3) : -1;
-      }
-      load_row_chunk(A, rs, n3, base, lane, val);
-#pragma unroll
-      for (int p = 0; p < 3; p++) {
-        const int t = base + lane + TILE_G * p;
-        const double xv = (col[p] >= 0) ? __ldg(x + 3 * (size_t)col[p] + (t % 3)) : 0.0;
-        acc0 = fma(val.v[p][0], xv, acc0); acc1 = fma(val.v[p][1], xv, acc1); acc2 = fma(val.v[p][2], xv, acc2);
-      }
-    }
-#pragma unroll
-    for (int o = TILE_G / 2; o > 0; o >>= 1) {
-      acc0 += __shfl_xor_sync(gmask, acc0, o, TILE_G);
-      acc1 += __shfl_xor_sync(gmask, acc1, o, TILE_G);
-      acc2 += __shfl_xor_sync(gmask, acc2, o, TILE_G);
-    }
-    if (lane < 3) {
-      double s = (lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2);
-      if (MODE == 1) {
-        if (mk) s = 0.0;
-        y[row] = s;
-        part = fma(xr, s, part);
-      } else {
-        const double rres = mk ? 0.0 : (br - s);
-        y[row] = rres;
-        part += (rres * rres) * wr;
-      }
-    }
-  }
-  return part;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-// q = A d with per-chunk d.q (MODE 1) / r = b - A x with per-chunk sum r^2 invD (MODE 2)
+// q = A d with per-unit d.q (MODE 1) / r = b - A x with per-unit sum r^2 invD (MODE 2).  One resident wave of CTAs; every
+// WARP walks product units w, w + nWarps, ... on its own (no block barrier in the loop): 16 lanes per block row, all loads of a
+// row in flight, the next row's pointers — and the next unit's — requested one step ahead (the loop body of k_spmv_rows3).
 template <int MODE>
-__global__ void __launch_bounds__(BT_TB) kb_spmv(BatchArgs a, const int *__restrict__ bp, const int *__restrict__ bc,
-                                                 const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
-                                                 const unsigned char *__restrict__ mask, const double *__restrict__ b,
-                                                 const double *__restrict__ invD) {
+__global__ void __launch_bounds__(BT_TB, 4) kb_spmv(BatchArgs a, const int *__restrict__ bp, const int *__restrict__ bc,
+                                                    const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
+                                                    const unsigned char *__restrict__ mask, const double *__restrict__ b,
+                                                    const double *__restrict__ invD) {
   pdl_wait();
   pdl_trigger();
-  const int ch = blockIdx.x;
-  if (a.done[a.chunkMesh[ch]]) return;
-  const double part = batch_rows<MODE>(a.chunkRow[ch], a.chunkRow[ch + 1], bp, bc, A, x, y, mask, b, invD);
-  block_reduce_to_slot<BT_TB>(part, MODE == 1 ? a.slotsA : a.slotsB);  // slot [blockIdx.x] = [ch]
-}
-
-// r = b (x0 = 0), d = invD r, x = 0, q = 0, per-chunk sum r^2 invD                                  (CGSolver.cpp:139-147)
-__global__ void __launch_bounds__(BT_TB) kb_init(BatchArgs a, const double *__restrict__ b, const double *__restrict__ invD,
-                                                 double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
-                                                 double *__restrict__ q) {
-  const int ch = blockIdx.x;
-  double part = 0.0;
-  for (size_t i = 3 * (size_t)a.chunkRow[ch] + threadIdx.x; i < 3 * (size_t)a.chunkRow[ch + 1]; i += BT_TB) {
-    const double bi = b[i], di = invD[i];
-    x[i] = 0.0; r[i] = bi; q[i] = 0.0; d[i] = di * bi;
-    part += (bi * bi) * di;
+  __shared__ unsigned char sdone[BT_SD];
+  for (int i = threadIdx.x; i < a.count && i < BT_SD; i += BT_TB) sdone[i] = (unsigned char)a.done[i];
+  __syncthreads();
+  const int lane = threadIdx.x & (TILE_G - 1), half = (threadIdx.x >> 4) & 1;
+  const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+  const int nWarps = gridDim.x * BT_WARPS;
+  int w = blockIdx.x * BT_WARPS + (threadIdx.x >> 5);
+  int4 meta = make_int4(0, 0, 0, 0);
+  int rs = 0, re = 0;
+  if (w < a.nW) {
+    meta = __ldg(a.wmeta + w);
+    if (meta.x + half < meta.y) { rs = __ldg(bp + meta.x + half); re = __ldg(bp + meta.x + half + 1); }
   }
-  block_reduce_to_slot<BT_TB>(part, a.slotsB);
+  while (w < a.nW) {
+    const int wn = w + nWarps;
+    int4 metaN = make_int4(0, 0, 0, 0);
+    if (wn < a.nW) metaN = __ldg(a.wmeta + wn);
+    const int m = meta.z;
+    const bool fin = (m < BT_SD) ? (sdone[m] != 0) : (a.done[m] != 0);
+    if (!fin) {
+      double part = 0.0;
+      const int r1 = meta.y;
+      int v = meta.x + half;
+      while (v < r1) {
+        const int vn = v + 2;
+        int rsn = 0, ren = 0;
+        if (vn < r1) { rsn = __ldg(bp + vn); ren = __ldg(bp + vn + 1); }
+        const int n3 = 3 * (re - rs);
+        const size_t row = 3 * (size_t)v + (lane < 3 ? lane : 0);
+        double xr = 0.0, br = 0.0, wr = 0.0;
+        unsigned char mk = 0;
+        if (lane < 3) {
+          mk = __ldg(mask + row);
+          if (MODE == 1) xr = __ldg(x + row);
+          if (MODE == 2) { br = __ldg(b + row); wr = __ldg(invD + row); }
+        }
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+        for (int base = 0; base < n3; base += TILE_CHUNK) {
+          RowVals val;
+          int col[3];
+#pragma unroll
+          for (int p = 0; p < 3; p++) {
+            const int t = base + lane + TILE_G * p;
+            col[p] = (t < n3) ? __ldg(bc + rs + t / 3) : -1;
+          }
+          load_row_chunk(A, rs, n3, base, lane, val);
+#pragma unroll
+          for (int p = 0; p < 3; p++) {
+            const int t = base + lane + TILE_G * p;
+            const double xv = (col[p] >= 0) ? __ldg(x + 3 * (size_t)col[p] + (t % 3)) : 0.0;
+            acc0 = fma(val.v[p][0], xv, acc0); acc1 = fma(val.v[p][1], xv, acc1); acc2 = fma(val.v[p][2], xv, acc2);
+          }
+        }
+#pragma unroll
+        for (int o = TILE_G / 2; o > 0; o >>= 1) {
+          acc0 += __shfl_xor_sync(gmask, acc0, o, TILE_G);
+          acc1 += __shfl_xor_sync(gmask, acc1, o, TILE_G);
+          acc2 += __shfl_xor_sync(gmask, acc2, o, TILE_G);
+        }
+        if (lane < 3) {
+          double s = (lane == 0) ? acc0 : ((lane == 1) ? acc1 : acc2);
+          if (MODE == 1) {
+            if (mk) s = 0.0;
+            y[row] = s;
+            part = fma(xr, s, part);
+          } else {
+            const double rres = mk ? 0.0 : (br - s);
+            y[row] = rres;
+            part += (rres * rres) * wr;
+          }
+        }
+        v = vn; rs = rsn; re = ren;
+      }
+      // the first row of the warp's next unit, requested before the (short) reduction below
+      if (wn < a.nW && metaN.x + half < metaN.y) { rs = __ldg(bp + metaN.x + half); re = __ldg(bp + metaN.x + half + 1); }
+      part = warp_sum(part);  // fixed tree: lanes 0-2 of both halves hold the partials, the rest zeros
+      if ((threadIdx.x & 31) == 0) a.slotsA[w] = part;
+    } else if (wn < a.nW && metaN.x + half < metaN.y) {
+      rs = __ldg(bp + metaN.x + half); re = __ldg(bp + metaN.x + half + 1);
+    }
+    w = wn; meta = metaN;
+  }
 }
 
-// per mesh: rho0, loop condition at iteration 1                                                     (CGSolver.cpp:147-150)
-__global__ void kb_begin(BatchArgs a) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= a.count) return;
-  double total = 0.0;
-  for (int s = a.meshChunk[m]; s < a.meshChunk[m + 1]; s++) total += a.slotsB[s];
+// vector units [u0, u1) of this CTA: contiguous, so a CTA changes mesh (and has to add that mesh's slots) rarely
+__device__ __forceinline__ void unit_range(const BatchArgs &a, int *u0, int *u1) {
+  *u0 = (int)((long long)blockIdx.x * a.nU / gridDim.x);
+  *u1 = (int)((long long)(blockIdx.x + 1) * a.nU / gridDim.x);
+}
+
+// r = b (x0 = 0), d = invD r, x = 0, q = 0, per-warp sum r^2 invD                                   (CGSolver.cpp:139-147)
+__global__ void __launch_bounds__(BT_TB, 4) kb_init(BatchArgs a, const double *__restrict__ b, const double *__restrict__ invD,
+                                                    double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
+                                                    double *__restrict__ q) {
+  int u0, u1;
+  unit_range(a, &u0, &u1);
+  for (int u = u0; u < u1; u++) {
+    const int4 meta = __ldg(a.umeta + u);
+    const int i0 = 3 * meta.x + (int)threadIdx.x, iend = 3 * meta.y;  // 3 nV fits an int (checked by fb_create_batch)
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < BT_UITEMS; k++) {
+      const int i = i0 + k * BT_TB;
+      if (i < iend) {
+        const double bi = b[i], di = invD[i];
+        x[i] = 0.0; r[i] = bi; q[i] = 0.0; d[i] = di * bi;
+        part += (bi * bi) * di;
+      }
+    }
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) a.slotsB[(size_t)u * BT_WARPS + (threadIdx.x >> 5)] = part;
+  }
+}
+
+// per mesh (one CTA each): rho0, loop condition at iteration 1                                      (CGSolver.cpp:147-150)
+__global__ void __launch_bounds__(BT_TB) kb_begin(BatchArgs a) {
+  const int m = blockIdx.x;
+  const double total = cta_sum_slots<BT_TB>(a.slotsB + (size_t)a.meshU[m] * BT_WARPS, (a.meshU[m + 1] - a.meshU[m]) * BT_WARPS);
+  if (threadIdx.x != 0) return;
   a.rho[m] = total;       // rho[0][m]
   a.rho0[m] = total;
   a.iters[m] = 0;
@@ -160,69 +206,131 @@ __global__ void kb_begin(BatchArgs a) {
   if (fin) atomicSub(a.active, 1);
 }
 
-// x += alpha d; REFRESH ? nothing more : (r -= alpha q; per-chunk sum r^2 invD)                     (CGSolver.cpp:155-174)
+// x += alpha d; REFRESH ? nothing more : (r -= alpha q; per-warp sum r^2 invD)                      (CGSolver.cpp:155-174)
+// A unit's operands are requested BEFORE the mesh's scalars are known, so their latency overlaps the slot sum.
 template <bool REFRESH>
-__global__ void __launch_bounds__(BT_TB) kb_update(BatchArgs a, const double *__restrict__ d, const double *__restrict__ q,
-                                                   const double *__restrict__ invD, double *__restrict__ x,
-                                                   double *__restrict__ r) {
+__global__ void __launch_bounds__(BT_TB, 4) kb_update(BatchArgs a, const double *__restrict__ d, const double *__restrict__ q,
+                                                      const double *__restrict__ invD, double *__restrict__ x,
+                                                      double *__restrict__ r) {
   pdl_wait();
   pdl_trigger();
-  const int ch = blockIdx.x, m = a.chunkMesh[ch];
-  if (a.done[m]) return;
-  const int it = a.iters[m] + 1;
-  const double dq = cta_sum_slots<BT_TB>(a.slotsA + a.meshChunk[m], a.meshChunk[m + 1] - a.meshChunk[m]);
-  const double alpha = a.rho[((it - 1) & 1) * a.count + m] / dq;
-  double part = 0.0;
-  for (size_t i = 3 * (size_t)a.chunkRow[ch] + threadIdx.x; i < 3 * (size_t)a.chunkRow[ch + 1]; i += BT_TB) {
-    x[i] = fma(alpha, d[i], x[i]);
+  int u0, u1;
+  unit_range(a, &u0, &u1);
+  int cur = -1;
+  bool fin = true;
+  double alpha = 0.0;
+  for (int u = u0; u < u1; u++) {
+    const int4 meta = __ldg(a.umeta + u);
+    const int i0 = 3 * meta.x + (int)threadIdx.x, iend = 3 * meta.y;  // 3 nV fits an int (checked by fb_create_batch)
+    double dv[BT_UITEMS], xv[BT_UITEMS], qv[BT_UITEMS], wv[BT_UITEMS], rv[BT_UITEMS];
+#pragma unroll
+    for (int k = 0; k < BT_UITEMS; k++) {
+      const int i = i0 + k * BT_TB;
+      dv[k] = xv[k] = qv[k] = wv[k] = rv[k] = 0.0;
+      if (i < iend) {
+        dv[k] = d[i]; xv[k] = x[i];
+        if (!REFRESH) { qv[k] = q[i]; wv[k] = invD[i]; rv[k] = r[i]; }
+      }
+    }
+    if (meta.z != cur) {  // uniform over the CTA
+      cur = meta.z;
+      fin = a.done[cur] != 0;
+      if (!fin) {
+        const int it = a.iters[cur] + 1;
+        const double dq = cta_sum_slots<BT_TB>(a.slotsA + a.meshW[cur], a.meshW[cur + 1] - a.meshW[cur]);
+        alpha = a.rho[((it - 1) & 1) * a.count + cur] / dq;
+      }
+    }
+    if (fin) continue;
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < BT_UITEMS; k++) {
+      const int i = i0 + k * BT_TB;
+      if (i < iend) {
+        x[i] = fma(alpha, dv[k], xv[k]);
+        if (!REFRESH) {
+          const double ri = fma(-alpha, qv[k], rv[k]);
+          r[i] = ri;
+          part += (ri * ri) * wv[k];
+        }
+      }
+    }
     if (!REFRESH) {
-      const double ri = fma(-alpha, q[i], r[i]);
-      r[i] = ri;
-      part += (ri * ri) * invD[i];
+      part = warp_sum(part);
+      if ((threadIdx.x & 31) == 0) a.slotsB[(size_t)u * BT_WARPS + (threadIdx.x >> 5)] = part;
     }
   }
-  if (!REFRESH) block_reduce_to_slot<BT_TB>(part, a.slotsB);
 }
 
 // beta = rho'/rho; d = invD r + beta d; per mesh: iteration++ and the loop condition                (CGSolver.cpp:176-183, 150)
-__global__ void __launch_bounds__(BT_TB) kb_direction(BatchArgs a, const double *__restrict__ r, const double *__restrict__ invD,
-                                                      double *__restrict__ d) {
+// fromProduct: rho' was summed by the refresh product (slotsA, product units) instead of kb_update (slotsB)
+__global__ void __launch_bounds__(BT_TB, 4) kb_direction(BatchArgs a, const double *__restrict__ r, const double *__restrict__ invD,
+                                                         double *__restrict__ d, int fromProduct) {
   pdl_wait();
   pdl_trigger();
-  const int ch = blockIdx.x, m = a.chunkMesh[ch];
-  if (a.done[m]) return;
-  const int it = a.iters[m] + 1;
-  const int nch = a.meshChunk[m + 1] - a.meshChunk[m];
-  const double rhoNew = cta_sum_slots<BT_TB>(a.slotsB + a.meshChunk[m], nch);
-  const double rhoOld = a.rho[((it - 1) & 1) * a.count + m];
-  const double beta = rhoNew / rhoOld;
-  for (size_t i = 3 * (size_t)a.chunkRow[ch] + threadIdx.x; i < 3 * (size_t)a.chunkRow[ch + 1]; i += BT_TB)
-    d[i] = fma(invD[i], r[i], beta * d[i]);
-  // bookkeeping by the mesh's last chunk to finish, so that no chunk of this launch can still be reading iters / done
-  __shared__ bool last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last = (atomicAdd(&a.ticket[m], 1u) == (unsigned)nch - 1u);
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    a.ticket[m] = 0u;
-    a.rho[(it & 1) * a.count + m] = rhoNew;
-    a.iters[m] = it;
-    if (!((rhoNew > a.eps2 * a.rho0[m]) && (it + 1 <= a.maxIt))) {
-      a.done[m] = 1;
-      atomicSub(a.active, 1);
+  int u0, u1;
+  unit_range(a, &u0, &u1);
+  int cur = -1, it = 0;
+  unsigned int mine = 0u;  // units of mesh `cur` finished by this CTA
+  bool fin = true;
+  double beta = 0.0, rhoNew = 0.0;
+  for (int u = u0; u <= u1; u++) {
+    int4 meta = make_int4(0, 0, -1, 0);  // u == u1: only hands in the tickets of the last mesh
+    if (u < u1) meta = __ldg(a.umeta + u);
+    const int i0 = 3 * meta.x + (int)threadIdx.x, iend = 3 * meta.y;  // 3 nV fits an int (checked by fb_create_batch)
+    double rv[BT_UITEMS], wv[BT_UITEMS], dv[BT_UITEMS];
+#pragma unroll
+    for (int k = 0; k < BT_UITEMS; k++) {
+      const int i = i0 + k * BT_TB;
+      rv[k] = wv[k] = dv[k] = 0.0;
+      if (i < iend) { rv[k] = r[i]; wv[k] = invD[i]; dv[k] = d[i]; }
     }
+    if (meta.z != cur) {  // uniform over the CTA
+      // Bookkeeping by the CTA that hands in the mesh's last units: every CTA reads iters / rho / done of a mesh before it
+      // hands in its tickets for that mesh, so nobody can still be reading them.
+      __syncthreads();
+      if (threadIdx.x == 0 && cur >= 0 && !fin && mine) {
+        __threadfence();
+        const unsigned int total = (unsigned int)(a.meshU[cur + 1] - a.meshU[cur]);
+        if (atomicAdd(&a.ticket[cur], mine) + mine == total) {
+          a.ticket[cur] = 0u;
+          a.rho[(it & 1) * a.count + cur] = rhoNew;
+          a.iters[cur] = it;
+          if (!((rhoNew > a.eps2 * a.rho0[cur]) && (it + 1 <= a.maxIt))) {
+            a.done[cur] = 1;
+            atomicSub(a.active, 1);
+          }
+        }
+      }
+      cur = meta.z;
+      mine = 0u;
+      fin = true;
+      if (cur >= 0) {
+        fin = a.done[cur] != 0;
+        if (!fin) {
+          it = a.iters[cur] + 1;
+          rhoNew = fromProduct ? cta_sum_slots<BT_TB>(a.slotsA + a.meshW[cur], a.meshW[cur + 1] - a.meshW[cur])
+                               : cta_sum_slots<BT_TB>(a.slotsB + (size_t)a.meshU[cur] * BT_WARPS, (a.meshU[cur + 1] - a.meshU[cur]) * BT_WARPS);
+          beta = rhoNew / a.rho[((it - 1) & 1) * a.count + cur];
+        }
+      }
+    }
+    if (fin) continue;
+#pragma unroll
+    for (int k = 0; k < BT_UITEMS; k++) {
+      const int i = i0 + k * BT_TB;
+      if (i < iend) d[i] = fma(wv[k], rv[k], beta * dv[k]);
+    }
+    mine++;
   }
 }
 
 void batch_args(const fb_context *c, double eps, int maxIt, BatchArgs *a) {
   const FbBatch *b = c->batch;
-  a->chunkRow = b->chunkRow; a->chunkMesh = b->chunkMesh; a->meshChunk = b->meshChunk;
+  a->wmeta = b->wmeta; a->umeta = b->umeta; a->meshW = b->meshW; a->meshU = b->meshU;
   a->rho = b->rho; a->rho0 = b->rho0; a->iters = b->iters; a->done = b->done; a->active = b->active; a->ticket = b->ticket;
   a->slotsA = b->slotsA; a->slotsB = b->slotsB;
-  a->count = b->count; a->maxIt = maxIt; a->eps2 = eps * eps;
+  a->count = b->count; a->maxIt = maxIt; a->nW = b->nW; a->nU = b->nU; a->eps2 = eps * eps;
 }
 
 }  // namespace
@@ -230,7 +338,7 @@ void batch_args(const fb_context *c, double eps, int maxIt, BatchArgs *a) {
 void fb_batch_destroy(fb_context *c) {
   FbBatch *b = c->batch;
   if (!b) return;
-  void *ptrs[] = {b->chunkRow, b->chunkMesh, b->meshChunk, b->rho, b->rho0, b->iters, b->done, b->ticket, b->active, b->slotsA, b->slotsB};
+  void *ptrs[] = {b->wmeta, b->umeta, b->meshW, b->meshU, b->rho, b->rho0, b->iters, b->done, b->ticket, b->active, b->slotsA, b->slotsB};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete b;
@@ -245,10 +353,12 @@ int fb_batch_pcg_solve(fb_context *c, double eps, int maxIt) {
   if (c->r == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
   BatchArgs a;
   batch_args(c, eps, maxIt, &a);
-  const int grid = b->nChunks;
+  const int wave = 4 * c->sm_count;  // one resident wave: 4 CTAs of 256 threads per SM
+  const int gridP = std::max(1, std::min(wave, (b->nW + BT_WARPS - 1) / BT_WARPS));
+  const int gridV = std::max(1, std::min(wave, b->nU));
   FB_CUDA(cudaMemcpyAsync(b->active, &b->count, sizeof(int), cudaMemcpyHostToDevice, st));
-  kb_init<<<grid, BT_TB, 0, st>>>(a, c->rhs, c->invD, c->x, c->res, c->dir, c->Ad);
-  kb_begin<<<(b->count + 127) / 128, 128, 0, st>>>(a);
+  kb_init<<<gridV, BT_TB, 0, st>>>(a, c->rhs, c->invD, c->x, c->res, c->dir, c->Ad);
+  kb_begin<<<b->count, BT_TB, 0, st>>>(a);
   c->launches += 2;
   const int CH = 30;
   int *activeHost[2] = {reinterpret_cast<int *>(&c->sc_host[0]), reinterpret_cast<int *>(&c->sc_host[1])};  // pinned
@@ -259,15 +369,16 @@ int fb_batch_pcg_solve(fb_context *c, double eps, int maxIt) {
     for (; it <= end; it++) {
       // a mesh that has stopped is skipped by every kernel; meshes that stop at different iterations keep their own
       // refresh phase because `it` is common to all meshes that are still iterating (all started at 1)
-      fb_launch(c->pdl, st, kb_spmv<1>, grid, BT_TB, a, c->bp, c->bc, c->Keff, c->dir, c->Ad, c->rowmask, c->rhs, c->invD);
+      fb_launch(c->pdl, st, kb_spmv<1>, gridP, BT_TB, a, c->bp, c->bc, c->Keff, c->dir, c->Ad, c->rowmask, c->rhs, c->invD);
       if (it % 30 == 0) {
-        fb_launch(c->pdl, st, kb_update<true>, grid, BT_TB, a, c->dir, c->Ad, c->invD, c->x, c->res);
-        fb_launch(c->pdl, st, kb_spmv<2>, grid, BT_TB, a, c->bp, c->bc, c->Keff, c->x, c->res, c->rowmask, c->rhs, c->invD);
+        fb_launch(c->pdl, st, kb_update<true>, gridV, BT_TB, a, c->dir, c->Ad, c->invD, c->x, c->res);
+        fb_launch(c->pdl, st, kb_spmv<2>, gridP, BT_TB, a, c->bp, c->bc, c->Keff, c->x, c->res, c->rowmask, c->rhs, c->invD);
+        fb_launch(c->pdl, st, kb_direction, gridV, BT_TB, a, c->res, c->invD, c->dir, 1);
         c->launches++;
       } else {
-        fb_launch(c->pdl, st, kb_update<false>, grid, BT_TB, a, c->dir, c->Ad, c->invD, c->x, c->res);
+        fb_launch(c->pdl, st, kb_update<false>, gridV, BT_TB, a, c->dir, c->Ad, c->invD, c->x, c->res);
+        fb_launch(c->pdl, st, kb_direction, gridV, BT_TB, a, c->res, c->invD, c->dir, 0);
       }
-      fb_launch(c->pdl, st, kb_direction, grid, BT_TB, a, c->res, c->invD, c->dir);
       c->launches += 3;
     }
     FB_CUDA(cudaMemcpyAsync(activeHost[slot], b->active, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -352,35 +463,44 @@ int fb_create_batch(fb_context **out, int count, const int *numVertices, const d
   int st = fb_create_local(&c, nV, restPositions, nT, ct.data(), (int)cd.size(), cd.data(), nullptr, nullptr, nullptr, prm);
   if (st != FB_OK) { delete b; return st; }
   c->batch = b;
-  // chunks of BT_ROWS block rows, never across two meshes
-  std::vector<int> chunkRow, chunkMesh, meshChunk((size_t)count + 1, 0);
+  // product units of BT_WROWS block rows and vector units of BT_UROWS, never across two meshes
+  std::vector<int4> wmeta, umeta;
+  std::vector<int> meshW((size_t)count + 1, 0), meshU((size_t)count + 1, 0);
+  int wrows = BT_WROWS;
+  if (const char *e = getenv("FEMBRAIN_B200_BATCH_WROWS")) wrows = std::max(2, atoi(e));  // experiments
   for (int m = 0; m < count; m++) {
-    meshChunk[m] = (int)chunkMesh.size();
-    for (int r0 = b->vtx[m]; r0 < b->vtx[m + 1]; r0 += BT_ROWS) { chunkRow.push_back(r0); chunkMesh.push_back(m); }
+    meshW[m] = (int)wmeta.size();
+    meshU[m] = (int)umeta.size();
+    const int e = b->vtx[m + 1];
+    for (int r0 = b->vtx[m]; r0 < e; r0 += wrows) wmeta.push_back(make_int4(r0, std::min(r0 + wrows, e), m, 0));
+    for (int r0 = b->vtx[m]; r0 < e; r0 += BT_UROWS) umeta.push_back(make_int4(r0, std::min(r0 + BT_UROWS, e), m, 0));
   }
-  meshChunk[count] = (int)chunkMesh.size();
-  chunkRow.push_back(nV);
-  b->nChunks = (int)chunkMesh.size();
-  // (a chunk ends where the next one starts: the last chunk of a mesh at the first row of the next mesh)
-  b->chunkRow = b->chunkMesh = b->meshChunk = b->iters = b->done = b->active = nullptr;
+  meshW[count] = (int)wmeta.size();
+  meshU[count] = (int)umeta.size();
+  b->nW = (int)wmeta.size();
+  b->nU = (int)umeta.size();
+  b->wmeta = b->umeta = nullptr;
+  b->meshW = b->meshU = b->iters = b->done = b->active = nullptr;
   b->rho = b->rho0 = b->slotsA = b->slotsB = nullptr;
   b->ticket = nullptr;
 #define BCHK(call) do { st = (call); if (st != FB_OK) { fb_destroy(c); return st; } } while (0)
 #define BCUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fb_set_error("%s -> %s", #call, cudaGetErrorString(e__)); fb_destroy(c); return FB_ERR_CUDA; } } while (0)
-  BCHK(fb_dev_alloc(c, &b->chunkRow, chunkRow.size()));
-  BCHK(fb_dev_alloc(c, &b->chunkMesh, chunkMesh.size()));
-  BCHK(fb_dev_alloc(c, &b->meshChunk, meshChunk.size()));
+  BCHK(fb_dev_alloc(c, &b->wmeta, wmeta.size()));
+  BCHK(fb_dev_alloc(c, &b->umeta, umeta.size()));
+  BCHK(fb_dev_alloc(c, &b->meshW, meshW.size()));
+  BCHK(fb_dev_alloc(c, &b->meshU, meshU.size()));
   BCHK(fb_dev_alloc(c, &b->rho, 2 * (size_t)count));
   BCHK(fb_dev_alloc(c, &b->rho0, (size_t)count));
   BCHK(fb_dev_alloc(c, &b->iters, (size_t)count));
   BCHK(fb_dev_alloc(c, &b->done, (size_t)count));
   BCHK(fb_dev_alloc(c, &b->ticket, (size_t)count));
   BCHK(fb_dev_alloc(c, &b->active, 1));
-  BCHK(fb_dev_alloc(c, &b->slotsA, (size_t)b->nChunks));
-  BCHK(fb_dev_alloc(c, &b->slotsB, (size_t)b->nChunks));
-  BCUDA(cudaMemcpyAsync(b->chunkRow, chunkRow.data(), sizeof(int) * chunkRow.size(), cudaMemcpyHostToDevice, c->stream));
-  BCUDA(cudaMemcpyAsync(b->chunkMesh, chunkMesh.data(), sizeof(int) * chunkMesh.size(), cudaMemcpyHostToDevice, c->stream));
-  BCUDA(cudaMemcpyAsync(b->meshChunk, meshChunk.data(), sizeof(int) * meshChunk.size(), cudaMemcpyHostToDevice, c->stream));
+  BCHK(fb_dev_alloc(c, &b->slotsA, (size_t)b->nW));
+  BCHK(fb_dev_alloc(c, &b->slotsB, (size_t)b->nU * BT_WARPS));
+  BCUDA(cudaMemcpyAsync(b->wmeta, wmeta.data(), sizeof(int4) * wmeta.size(), cudaMemcpyHostToDevice, c->stream));
+  BCUDA(cudaMemcpyAsync(b->umeta, umeta.data(), sizeof(int4) * umeta.size(), cudaMemcpyHostToDevice, c->stream));
+  BCUDA(cudaMemcpyAsync(b->meshW, meshW.data(), sizeof(int) * meshW.size(), cudaMemcpyHostToDevice, c->stream));
+  BCUDA(cudaMemcpyAsync(b->meshU, meshU.data(), sizeof(int) * meshU.size(), cudaMemcpyHostToDevice, c->stream));
   BCUDA(cudaMemsetAsync(b->iters, 0, sizeof(int) * (size_t)count, c->stream));
   BCUDA(cudaMemsetAsync(b->done, 0, sizeof(int) * (size_t)count, c->stream));
   BCUDA(cudaMemsetAsync(b->ticket, 0, sizeof(unsigned int) * (size_t)count, c->stream));

@@ -395,6 +395,8 @@ def run_batch(args):
     v, t, fixed, f0 = workload(nx)
     nT, r = len(t), 3 * len(v)
     mine = [m for m in range(args.batch) if m % world == rank]
+    if args.group < 0:
+        args.group = max(1, len(mine))
     sims, forces = [], []
     corner = 3 * (len(v) - 1)
     for m in mine:  # same mesh, load direction rotated about y with the mesh index
@@ -503,7 +505,7 @@ def _main(saved_stdout):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="configs[3]: step a batch of this many independent meshes (use with --nx 33)")
     ap.add_argument("--streams", type=int, default=8, help="host threads / concurrent contexts per GPU in --batch mode (B200, 32 meshes of 196,608 tets on one GPU: 75.2 / 81.1 / 79.7 mesh-steps/s with 4 / 8 / 16)")
-    ap.add_argument("--group", type=int, default=0, help="--batch mode: meshes per batch context (fb_create_batch); 0 = one context per mesh")
+    ap.add_argument("--group", type=int, default=-1, help="--batch mode: meshes per batch context (fb_create_batch: one block-diagonal system, PCG scalars and stopping rule per mesh); -1 = all meshes of the rank in one context (B200, 32 meshes of 196,608 tets: 109 mesh-steps/s), 0 = one context per mesh on --streams host threads (79.6)")
     ap.add_argument("--partitioned", action="store_true",
                     help="N>1: split ONE mesh by row blocks across the ranks (NCCL halo exchange, strong scaling) instead of one mesh per rank")
     args = ap.parse_args()

@@ -10,9 +10,12 @@
 //   * PCG keeps one set of scalars PER MESH (rho, rho0, alpha, beta, iteration count, loop flag): each mesh runs the
 //     reference's recurrences, refresh period and stopping rule on its own and stops on its own; the kernels just cover
 //     all meshes that are still iterating in one launch.
-// Rows are cut into chunks of BT_ROWS block rows that never straddle two meshes; one CTA per chunk in every kernel.  Dot
-// products: per-chunk sums in fixed slots, added per mesh in slot order by every consumer CTA of that mesh — deterministic,
-// no atomics on floating-point data.
+// Work units never straddle two meshes.  Products (q = A d, r = b - A x): units of 32 block rows, one WARP per unit, one resident
+// wave of CTAs whose warps walk the units without any block barrier.  Vector kernels: units of 256 block rows, every CTA takes
+// a contiguous run of them, so it adds a mesh's slots (alpha, beta) once per mesh it touches.  Dot products: per-unit / per-warp
+// sums in fixed slots, added per mesh in slot order by every consumer CTA of that mesh — deterministic, no atomics on
+// floating-point data.  Measured (B200, 32 meshes of 196,608 tets, profiles/r01_batch_context.txt): 109 mesh-steps/s against
+// 79.6 for a context per mesh on 8 streams; the product kernel reads 1.30 GB per launch at 5.2 TB/s (ncu).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -36,6 +39,7 @@ struct FbBatch {
   int *done;                 // [count]
   unsigned int *ticket;      // [count] vector units of the mesh that have finished the direction update
   int *active;               // [1] meshes still iterating
+  int *wnext;                // [1] next product unit to hand out (dynamic distribution)
   double *slotsA;            // [nW] per-unit sums of the products (d.q; after a refresh sum r^2 invD)
   double *slotsB;            // [nU * warps per CTA] per-warp sums of the vector kernels (sum r^2 invD)
   std::vector<int> itersHost;
@@ -55,10 +59,11 @@ struct BatchArgs {
   const int4 *wmeta, *umeta;
   const int *meshW, *meshU;
   double *rho, *rho0;
-  int *iters, *done, *active;
+  int *iters, *done, *active, *wnext;
   unsigned int *ticket;
   double *slotsA, *slotsB;
   int count, maxIt, nW, nU;
+  int wnext0;  // > 0: product units beyond the first two per warp are handed out through *wnext, which starts here
   double eps2;
 };
 
@@ -84,7 +89,12 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_spmv(BatchArgs a, const int *__re
   const int lane = threadIdx.x & (TILE_G - 1), half = (threadIdx.x >> 4) & 1;
   const unsigned gmask = 0xffffu << (threadIdx.x & 16);
   const int nWarps = gridDim.x * BT_WARPS;
+  // Units of a warp: its own index, that + nWarps, then (wnext0 > 0) whatever the shared counter hands out next, so that a warp
+  // which drew short or skipped units takes more of them.  The counter is read two units ahead (lane 0, broadcast at the end
+  // of the unit in between) and the unit record one unit ahead: neither latency is ever waited for.
+  const bool dyn = a.wnext0 > 0;
   int w = blockIdx.x * BT_WARPS + (threadIdx.x >> 5);
+  int wn = w + nWarps;
   int4 meta = make_int4(0, 0, 0, 0);
   int rs = 0, re = 0;
   if (w < a.nW) {
@@ -92,9 +102,10 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_spmv(BatchArgs a, const int *__re
     if (meta.x + half < meta.y) { rs = __ldg(bp + meta.x + half); re = __ldg(bp + meta.x + half + 1); }
   }
   while (w < a.nW) {
-    const int wn = w + nWarps;
     int4 metaN = make_int4(0, 0, 0, 0);
     if (wn < a.nW) metaN = __ldg(a.wmeta + wn);
+    int wnn = wn + nWarps;
+    if (dyn && (threadIdx.x & 31) == 0) wnn = atomicAdd(a.wnext, 1);
     const int m = meta.z;
     const bool fin = (m < BT_SD) ? (sdone[m] != 0) : (a.done[m] != 0);
     if (!fin) {
@@ -158,7 +169,8 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_spmv(BatchArgs a, const int *__re
     } else if (wn < a.nW && metaN.x + half < metaN.y) {
       rs = __ldg(bp + metaN.x + half); re = __ldg(bp + metaN.x + half + 1);
     }
-    w = wn; meta = metaN;
+    if (dyn) wnn = __shfl_sync(0xffffffffu, wnn, 0);
+    w = wn; wn = wnn; meta = metaN;
   }
 }
 
@@ -172,6 +184,7 @@ __device__ __forceinline__ void unit_range(const BatchArgs &a, int *u0, int *u1)
 __global__ void __launch_bounds__(BT_TB, 4) kb_init(BatchArgs a, const double *__restrict__ b, const double *__restrict__ invD,
                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ d,
                                                     double *__restrict__ q) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.wnext = a.wnext0;
   int u0, u1;
   unit_range(a, &u0, &u1);
   for (int u = u0; u < u1; u++) {
@@ -214,6 +227,7 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_update(BatchArgs a, const double 
                                                       double *__restrict__ r) {
   pdl_wait();
   pdl_trigger();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.wnext = a.wnext0;  // for the next product (this kernel runs between two of them)
   int u0, u1;
   unit_range(a, &u0, &u1);
   int cur = -1;
@@ -221,6 +235,7 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_update(BatchArgs a, const double 
   double alpha = 0.0;
   for (int u = u0; u < u1; u++) {
     const int4 meta = __ldg(a.umeta + u);
+    if (meta.z == cur && fin) continue;  // further units of a mesh that has stopped
     const int i0 = 3 * meta.x + (int)threadIdx.x, iend = 3 * meta.y;  // 3 nV fits an int (checked by fb_create_batch)
     double dv[BT_UITEMS], xv[BT_UITEMS], qv[BT_UITEMS], wv[BT_UITEMS], rv[BT_UITEMS];
 #pragma unroll
@@ -268,6 +283,7 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_direction(BatchArgs a, const doub
                                                          double *__restrict__ d, int fromProduct) {
   pdl_wait();
   pdl_trigger();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.wnext = a.wnext0;
   int u0, u1;
   unit_range(a, &u0, &u1);
   int cur = -1, it = 0;
@@ -277,6 +293,7 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_direction(BatchArgs a, const doub
   for (int u = u0; u <= u1; u++) {
     int4 meta = make_int4(0, 0, -1, 0);  // u == u1: only hands in the tickets of the last mesh
     if (u < u1) meta = __ldg(a.umeta + u);
+    if (meta.z == cur && fin) continue;
     const int i0 = 3 * meta.x + (int)threadIdx.x, iend = 3 * meta.y;  // 3 nV fits an int (checked by fb_create_batch)
     double rv[BT_UITEMS], wv[BT_UITEMS], dv[BT_UITEMS];
 #pragma unroll
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(BT_TB, 4) kb_direction(BatchArgs a, const doub
 void batch_args(const fb_context *c, double eps, int maxIt, BatchArgs *a) {
   const FbBatch *b = c->batch;
   a->wmeta = b->wmeta; a->umeta = b->umeta; a->meshW = b->meshW; a->meshU = b->meshU;
-  a->rho = b->rho; a->rho0 = b->rho0; a->iters = b->iters; a->done = b->done; a->active = b->active; a->ticket = b->ticket;
+  a->rho = b->rho; a->rho0 = b->rho0; a->iters = b->iters; a->done = b->done; a->active = b->active; a->wnext = b->wnext; a->ticket = b->ticket;
   a->slotsA = b->slotsA; a->slotsB = b->slotsB;
   a->count = b->count; a->maxIt = maxIt; a->nW = b->nW; a->nU = b->nU; a->eps2 = eps * eps;
 }
@@ -338,7 +355,7 @@ void batch_args(const fb_context *c, double eps, int maxIt, BatchArgs *a) {
 void fb_batch_destroy(fb_context *c) {
   FbBatch *b = c->batch;
   if (!b) return;
-  void *ptrs[] = {b->wmeta, b->umeta, b->meshW, b->meshU, b->rho, b->rho0, b->iters, b->done, b->ticket, b->active, b->slotsA, b->slotsB};
+  void *ptrs[] = {b->wmeta, b->umeta, b->meshW, b->meshU, b->rho, b->rho0, b->iters, b->done, b->ticket, b->active, b->wnext, b->slotsA, b->slotsB};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete b;
@@ -356,6 +373,9 @@ int fb_batch_pcg_solve(fb_context *c, double eps, int maxIt) {
   const int wave = 4 * c->sm_count;  // one resident wave: 4 CTAs of 256 threads per SM
   const int gridP = std::max(1, std::min(wave, (b->nW + BT_WARPS - 1) / BT_WARPS));
   const int gridV = std::max(1, std::min(wave, b->nU));
+  // hand-out through the counter: measured no gain over the static walk (108.5 vs 109.1 mesh-steps/s), opt-in
+  static const bool dynamicUnits = getenv("FEMBRAIN_B200_BATCH_DYNAMIC") && atoi(getenv("FEMBRAIN_B200_BATCH_DYNAMIC")) != 0;
+  a.wnext0 = dynamicUnits ? 2 * gridP * BT_WARPS : 0;
   FB_CUDA(cudaMemcpyAsync(b->active, &b->count, sizeof(int), cudaMemcpyHostToDevice, st));
   kb_init<<<gridV, BT_TB, 0, st>>>(a, c->rhs, c->invD, c->x, c->res, c->dir, c->Ad);
   kb_begin<<<b->count, BT_TB, 0, st>>>(a);
@@ -480,7 +500,7 @@ int fb_create_batch(fb_context **out, int count, const int *numVertices, const d
   b->nW = (int)wmeta.size();
   b->nU = (int)umeta.size();
   b->wmeta = b->umeta = nullptr;
-  b->meshW = b->meshU = b->iters = b->done = b->active = nullptr;
+  b->meshW = b->meshU = b->iters = b->done = b->active = b->wnext = nullptr;
   b->rho = b->rho0 = b->slotsA = b->slotsB = nullptr;
   b->ticket = nullptr;
 #define BCHK(call) do { st = (call); if (st != FB_OK) { fb_destroy(c); return st; } } while (0)
@@ -495,6 +515,7 @@ int fb_create_batch(fb_context **out, int count, const int *numVertices, const d
   BCHK(fb_dev_alloc(c, &b->done, (size_t)count));
   BCHK(fb_dev_alloc(c, &b->ticket, (size_t)count));
   BCHK(fb_dev_alloc(c, &b->active, 1));
+  BCHK(fb_dev_alloc(c, &b->wnext, 1));
   BCHK(fb_dev_alloc(c, &b->slotsA, (size_t)b->nW));
   BCHK(fb_dev_alloc(c, &b->slotsB, (size_t)b->nU * BT_WARPS));
   BCUDA(cudaMemcpyAsync(b->wmeta, wmeta.data(), sizeof(int4) * wmeta.size(), cudaMemcpyHostToDevice, c->stream));

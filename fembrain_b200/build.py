@@ -28,6 +28,7 @@ UNITS = {
     "fb_pcg_persistent.cu": [],
     "fb_dist.cu": [],
     "fb_batch.cu": [],
+    "fb_sym.cu": [],
     "fb_veg.cu": ["-fmad=false"],
     "fb_deformable.cu": ["-fmad=false"],
 }

@@ -103,6 +103,7 @@ void free_all(fb_context *c) {
   fb_pcg_release(c);
   fb_dist_destroy(c);
   fb_batch_destroy(c);
+  fb_sym_release(c);
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,

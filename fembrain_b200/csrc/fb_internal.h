@@ -49,6 +49,7 @@ struct FbScalars {
 
 struct FbDist;   // multi-GPU state (fb_dist.cu)
 struct FbBatch;  // a batch of independent meshes in one context (fb_batch.cu)
+struct FbSym;    // upper-triangle storage for the solver's products (fb_sym.cu)
 
 
 struct fb_context {
@@ -151,6 +152,8 @@ struct fb_context {
 
   FbDist *dist;
   FbBatch *batch;
+  FbSym *sym;
+  int sym_want;  // FEMBRAIN_B200_SPMV=sym: products of the three-kernel schedule from the block-upper triangle (plan built at the first solve)
 };
 
 // ---- fb_api.cu -----------------------------------------------------------------------------------
@@ -187,6 +190,13 @@ int fb_pcg_launch_persistent(fb_context *c);
 // ---- fb_batch.cu -----------------------------------------------------------------------------------
 int fb_batch_pcg_solve(fb_context *c, double eps, int max_it);  // every mesh of the batch, own scalars and stopping rule each
 void fb_batch_destroy(fb_context *c);
+// ---- fb_sym.cu -------------------------------------------------------------------------------------
+int fb_sym_plan(fb_context *c);   // FB_OK with c->sym == nullptr: not applicable, keep the full-matrix kernels
+int fb_sym_pack(fb_context *c);   // U <- upper(Keff), start of every solve
+void fb_sym_launch(fb_context *c, int mode, const double *x, double *y, const double *b, double *slots);
+int fb_sym_grid(const fb_context *c, int mode);
+size_t fb_sym_bytes_per_product(const fb_context *c);
+void fb_sym_release(fb_context *c);
 // ---- fb_dist.cu ------------------------------------------------------------------------------------
 int fb_dist_halo_exchange(fb_context *c, double *vec);
 int fb_dist_allreduce_scalar(fb_context *c, const double *dev_part, double *dev_total);

@@ -655,16 +655,20 @@ void enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) 
   const double *dqSlots = defer ? c->partials : nullptr;
   const double *rhoSlots = nullptr;
   int nRhoSlots = 0;
-  launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, dqOut);
+  const bool sym = c->sym_want && c->sym;
+  const int nDq = sym ? fb_sym_grid(c, 1) : c->grid_spmv[1];
+  if (sym) fb_sym_launch(c, 1, c->dir, c->Ad, c->rhs, c->partials);
+  else launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, dqOut);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
   if (it % 30 == 0) {
-    fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
+    fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, nDq, nopeer);
     c->launches++;
-    launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
-    if (defer) { rhoSlots = c->partials; nRhoSlots = c->grid_spmv[2]; }
+    if (sym) fb_sym_launch(c, 2, c->x, c->res, c->rhs, c->partials);
+    else launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
+    if (defer) { rhoSlots = c->partials; nRhoSlots = sym ? fb_sym_grid(c, 2) : c->grid_spmv[2]; }
   } else {
-    fb_launch(c->pdl, c->stream, k_update<false>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, c->grid_spmv[1], nopeer);
+    fb_launch(c->pdl, c->stream, k_update<false>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, nDq, nopeer);
     c->launches++;
     if (defer) { rhoSlots = slotsV; nRhoSlots = vg; }
   }
@@ -728,6 +732,13 @@ int start_solve(fb_context *c, double eps, int maxIt) {
   memset(&pa, 0, sizeof(pa));
   const bool p2p = fb_dist_p2p(c) != 0;
   if (c->dist) fb_dist_next_solve(c);
+  // products from the block-upper triangle (fb_sym.cu): single-GPU three-kernel schedule only
+  if (c->sym_want && (c->dist || c->batch || c->pers_grid > 0 || c->pcg_fused || c->pcg_graph)) c->sym_want = 0;
+  if (c->sym_want && !c->sym) {
+    FB_TRY(fb_sym_plan(c));
+    if (!c->sym) c->sym_want = 0;
+  }
+  if (c->sym_want) FB_TRY(fb_sym_pack(c));
   if (p2p) {
     fb_dist_peer_args(c, &pa);
     pa.epoch = fb_dist_epoch(c, 0, FB_COMM_RHO);
@@ -780,6 +791,7 @@ int ensure_period_graph(fb_context *c) {
 int fb_spmv_plan(fb_context *c) {
   const char *env = getenv("FEMBRAIN_B200_SPMV");
   c->use_rows3 = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
+  c->sym_want = env && !strcmp(env, "sym");
   const size_t n = (size_t)c->r;
   // vector kernels: at most one resident wave, one 16-byte item per thread on small meshes.  Fatter CTAs (2/4/8 items per
   // thread, fewer CTAs adding the producer's slots) were measured slower: 51.3 / 52.8 / 55.7 us per iteration at 1M tets,

@@ -416,24 +416,33 @@ def run_batch(args):
             sims.append(fb.Simulation(batch=[(v, t, fixed)] * n, device=local))
             grouped.append(torch.from_numpy(np.concatenate(forces[g0:g0 + n])).cuda())
         forces = grouped
+    # end-to-end arm: the same forces from pinned host memory every step, every mesh's displacements read back
+    f_pinned = [x.cpu().pin_memory() for x in forces]
+    q_pinned = [torch.empty_like(x) for x in f_pinned]
+    q_pinned = [x.pin_memory() for x in q_pinned]
     torch.cuda.synchronize()
     nthreads = max(1, min(args.streams, len(sims)))
     iters = [[] for _ in sims]
 
-    def worker(tid, nsteps, record):
+    def worker(tid, nsteps, record, e2e):
         for _ in range(nsteps):
             for k in range(tid, len(sims), nthreads):
-                sims[k].set_external_forces_dev(forces[k].data_ptr())
+                if e2e:
+                    sims[k].set_external_forces_ptr(f_pinned[k].data_ptr())
+                else:
+                    sims[k].set_external_forces_dev(forces[k].data_ptr())
                 sims[k].do_timestep()
+                if e2e:
+                    sims[k].get_state_ptr(q_pinned[k].data_ptr())
                 if record:
                     iters[k].append(int(sims[k].batch_cg_iterations()[0][0]) if args.group > 0 else sims[k].last_cg_iterations)
 
-    def region(nsteps, record):
+    def region(nsteps, record, e2e=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        th = [threading.Thread(target=worker, args=(i, nsteps, record)) for i in range(nthreads)]
+        th = [threading.Thread(target=worker, args=(i, nsteps, record, e2e)) for i in range(nthreads)]
         [x.start() for x in th]
         [x.join() for x in th]
         torch.cuda.synchronize()
@@ -446,9 +455,19 @@ def run_batch(args):
 
     region(args.warmup, False)
     l0 = sum(s_.kernel_launches for s_ in sims)
+    for s_ in sims:
+        s_.set_profiling(True)
     with ClockSampler(local) as clk:
         sec = region(args.steps, True)
     launches = sum(s_.kernel_launches for s_ in sims) - l0
+    prof = [s_.spmv_profile() for s_ in sims]
+    for s_ in sims:
+        s_.set_profiling(False)
+    # the same steps end to end: state back to rest, warm-up, K timed steps with host buffers
+    for s_ in sims:
+        s_.reset_to_rest()
+    region(args.warmup, False, True)
+    sec_e2e = region(args.steps, False, True)
     if world > 1:
         ll = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(ll)
@@ -462,13 +481,31 @@ def run_batch(args):
             cfg["parallelism"] = (f"{args.batch // world} meshes per GPU in batch contexts of {args.group} (fb_create_batch: block-diagonal "
                                   f"system, PCG scalars and stopping rule per mesh), {nthreads} host threads/streams, no communication")
         cfg["timing"] = "host wall clock between device synchronisations (many streams), max over ranks"
-        args.emit({
+        h2d = sum(x.numel() * 8 for x in f_pinned)
+        line = {
             "metric": "fem_mesh_steps_per_s", "value": value, "unit": "mesh-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clk.summary(),
+            "e2e": {"value": args.batch * args.steps / sec_e2e, "unit": "mesh-steps/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": h2d * world, "ms_per_step": 1e3 * sec_e2e / args.steps},
             "mtets_steps_per_s": value * nT / 1e6, "gpu_launches": launches,
             "cg_iterations_per_step_mesh0": iters[0] if iters else [],
-        })
+        }
+        tot_s = sum(m * n for m, n, _ in prof)
+        tot_n = sum(n for _, n, _ in prof)
+        if tot_n > 0:
+            peak, peak_src = measured_peak_gbs()
+            mean_s, bytes_launch = tot_s / tot_n, float(np.mean([b for _, _, b in prof]))
+            kern = "kb_spmv<1> (q = Keff d + per-mesh d.q over all meshes of a batch context)" if args.group > 0 else "k_spmv_rows3<1>"
+            line["roofline"] = {
+                "kernel": kern + ", CUDA-event pairs around every 16th PCG iteration's launch inside the timed steps (rank 0)",
+                "bound": "hbm", "achieved": bytes_launch / mean_s / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": bytes_launch / mean_s / 1e9 / peak, "traffic": ncu_traffic(f"batch{args.group}x{nx}") if args.group > 0 else None,
+                "algorithmic_bytes_per_launch": bytes_launch, "mean_launch_seconds": mean_s, "samples": tot_n,
+                "bytes_model": "per context: 8 B/nnz values + 4 B per 3x3 block column + 52 B per block row, all meshes iterating",
+                "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this kernel; null when none exists for this batch shape)",
+            }
+        args.emit(line)
     for s_ in sims:
         s_.close()
     if world > 1:

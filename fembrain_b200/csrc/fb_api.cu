@@ -821,6 +821,7 @@ int fb_get_spmv_profile(fb_context *c, double *mean, int *samples, double *bytes
   // 8 B value per scalar nonzero + 4 B block column per 3x3 block + per block row: 4 B row pointer,
   // 24 B of x (compulsory read), 24 B of y (write) [+ 3 B mask + 24 B d re-read for the fused dot]
   if (bytes) *bytes = 8.0 * (double)c->nnzK + 4.0 * (double)c->nB + 52.0 * (double)c->nV;
+  if (bytes && c->sym_want && c->sym) *bytes = (double)fb_sym_bytes_per_product(c);  // upper triangle + lower-block records
   return FB_OK;
 }
 

@@ -383,13 +383,19 @@ int fb_batch_pcg_solve(fb_context *c, double eps, int maxIt) {
   const int CH = 30;
   int *activeHost[2] = {reinterpret_cast<int *>(&c->sc_host[0]), reinterpret_cast<int *>(&c->sc_host[1])};  // pinned
   int it = 1, slot = 0, pending = 0;
+  int activeSeen = b->count;  // as of the last poll (one chunk behind)
   bool finished = false;
+  c->nprof = 0;
   while (!finished && it <= maxIt) {
     const int end = (it + CH - 1 < maxIt) ? it + CH - 1 : maxIt;
     for (; it <= end; it++) {
       // a mesh that has stopped is skipped by every kernel; meshes that stop at different iterations keep their own
       // refresh phase because `it` is common to all meshes that are still iterating (all started at 1)
+      // fb_set_profiling: event pairs around every 16th product while (as far as the host knows) all meshes still iterate
+      const bool sample = c->profiling && (it % 16 == 1) && c->nprof < 64 && activeSeen == b->count;
+      if (sample) cudaEventRecord(c->evProf[2 * c->nprof], st);
       fb_launch(c->pdl, st, kb_spmv<1>, gridP, BT_TB, a, c->bp, c->bc, c->Keff, c->dir, c->Ad, c->rowmask, c->rhs, c->invD);
+      if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], st); c->nprof++; }
       if (it % 30 == 0) {
         fb_launch(c->pdl, st, kb_update<true>, gridV, BT_TB, a, c->dir, c->Ad, c->invD, c->x, c->res);
         fb_launch(c->pdl, st, kb_spmv<2>, gridP, BT_TB, a, c->bp, c->bc, c->Keff, c->x, c->res, c->rowmask, c->rhs, c->invD);
@@ -407,7 +413,8 @@ int fb_batch_pcg_solve(fb_context *c, double eps, int maxIt) {
     if (pending == 2) {
       const int prev = slot ^ 1;
       FB_CUDA(cudaEventSynchronize(c->evChunk[prev]));
-      if (*activeHost[prev] <= 0) finished = true;
+      activeSeen = *activeHost[prev];
+      if (activeSeen <= 0) finished = true;
       pending--;
     }
     slot ^= 1;
@@ -421,6 +428,11 @@ int fb_batch_pcg_solve(fb_context *c, double eps, int maxIt) {
   FB_CUDA(cudaMemcpyAsync(b->itersHost.data(), b->iters, sizeof(int) * (size_t)M, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   FB_CUDA(cudaGetLastError());
+  for (int i = 0; i < c->nprof; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->evProf[2 * i], c->evProf[2 * i + 1]) == cudaSuccess) { c->prof_sum_s += 1e-3 * ms; c->prof_samples++; }
+  }
+  c->nprof = 0;
   int worst = 0;
   bool anyFailed = false;
   double worstRatio = 0.0;

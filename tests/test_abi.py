@@ -80,3 +80,26 @@ def test_invalid_arguments_are_status_codes_not_crashes():
     assert lib.fb_num_dofs(None) == 0
     lib.fb_destroy(None)
     assert b"argument" in lib.fb_status_string(1)
+
+
+def test_batch_entry_points_validate_before_touching_the_device():
+    """fb_create_batch checks counts, mesh-local vertex ids and fixed-vertex lists on the host, so these fail the same way
+    with or without a GPU (and never reach fb_create_local)."""
+    import numpy as np
+
+    v, t, fixed, _ = cases.cube_case(3)
+    with pytest.raises(fb.FemBrainError) as e:
+        fb.Simulation(batch=[(v, t, fixed), (v, t + 1000, fixed)])
+    assert e.value.status == api.FB_ERR_BAD_MESH and "mesh 1" in str(e.value)
+    with pytest.raises(fb.FemBrainError) as e:
+        fb.Simulation(batch=[(v, t, np.array([0, 0], np.int32))])
+    assert e.value.status == api.FB_ERR_INVALID_ARGUMENT and "twice" in str(e.value)
+    with pytest.raises(fb.FemBrainError) as e:
+        fb.Simulation(batch=[(v, t, np.array([len(v)], np.int32))])
+    assert e.value.status == api.FB_ERR_INVALID_ARGUMENT
+    lib = fb.load_library()
+    h = ctypes.c_void_p()
+    assert lib.fb_create_batch(ctypes.byref(h), 0, None, None, None, None, None, None, None) == api.FB_ERR_INVALID_ARGUMENT
+    assert lib.fb_batch_count(None) == 0
+    assert lib.fb_batch_offsets(None, None, None) == api.FB_ERR_INVALID_ARGUMENT
+    assert lib.fb_batch_last_cg_iterations(None, None, None) == api.FB_ERR_INVALID_ARGUMENT

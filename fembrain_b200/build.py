@@ -29,6 +29,7 @@ UNITS = {
     "fb_dist.cu": [],
     "fb_batch.cu": [],
     "fb_sym.cu": [],
+    "fb_tma.cu": [],
     "fb_veg.cu": ["-fmad=false"],
     "fb_deformable.cu": ["-fmad=false"],
 }

@@ -104,6 +104,7 @@ void free_all(fb_context *c) {
   fb_dist_destroy(c);
   fb_batch_destroy(c);
   fb_sym_release(c);
+  fb_tma_release(c);
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,
@@ -270,7 +271,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   c->rowmask = c->fixed;
   CR(fb_apply_constraints(c, nC, cdofs));
   CR(fb_dev_alloc(c, &c->T, (size_t)c->nnzK));
-  CR(fb_dev_alloc(c, &c->Keff, (size_t)c->nnzK));
+  CR(fb_dev_alloc(c, &c->Keff, (size_t)c->nnzK + 4));  // + slack: fb_tma.cu copies whole 16-byte lines around a row tile
   if (p.keep_raw_stiffness) CR(fb_dev_alloc(c, &c->Kraw, (size_t)c->nnzK));
   CR(fb_build_gather_plan(c));  // two-phase scratch (1248 B/tet) is allocated on first use, only if this plan is off
   double **vecs[] = {&c->q, &c->qvel, &c->qaccel, &c->fext, &c->fint, &c->qres, &c->rhs, &c->x, &c->res, &c->dir, &c->Ad, &c->invD, &c->tmp};

@@ -50,6 +50,7 @@ struct FbScalars {
 struct FbDist;   // multi-GPU state (fb_dist.cu)
 struct FbBatch;  // a batch of independent meshes in one context (fb_batch.cu)
 struct FbSym;    // upper-triangle storage for the solver's products (fb_sym.cu)
+struct FbTma;    // row tiles for the bulk-copy staged products (fb_tma.cu)
 
 
 struct fb_context {
@@ -153,6 +154,8 @@ struct fb_context {
   FbDist *dist;
   FbBatch *batch;
   FbSym *sym;
+  FbTma *tma;
+  int tma_want;  // FEMBRAIN_B200_SPMV=tma: products with the matrix staged through shared memory by cp.async.bulk (experimental)
   int sym_want;  // FEMBRAIN_B200_SPMV=sym: products of the three-kernel schedule from the block-upper triangle (plan built at the first solve)
 };
 
@@ -197,6 +200,12 @@ void fb_sym_launch(fb_context *c, int mode, const double *x, double *y, const do
 int fb_sym_grid(const fb_context *c, int mode);
 size_t fb_sym_bytes_per_product(const fb_context *c);
 void fb_sym_release(fb_context *c);
+// ---- fb_tma.cu -------------------------------------------------------------------------------------
+int fb_tma_plan(fb_context *c);   // FB_OK with c->tma == nullptr: not applicable, keep the default kernels
+void fb_tma_launch(fb_context *c, int mode, const double *x, double *y, const double *b, double *slots);
+int fb_tma_grid(const fb_context *c);
+int fb_tma_failed(fb_context *c);
+void fb_tma_release(fb_context *c);
 // ---- fb_dist.cu ------------------------------------------------------------------------------------
 int fb_dist_halo_exchange(fb_context *c, double *vec);
 int fb_dist_allreduce_scalar(fb_context *c, const double *dev_part, double *dev_total);

@@ -655,9 +655,10 @@ void enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) 
   const double *dqSlots = defer ? c->partials : nullptr;
   const double *rhoSlots = nullptr;
   int nRhoSlots = 0;
-  const bool sym = c->sym_want && c->sym;
-  const int nDq = sym ? fb_sym_grid(c, 1) : c->grid_spmv[1];
+  const bool sym = c->sym_want && c->sym, tma = c->tma_want && c->tma;
+  const int nDq = sym ? fb_sym_grid(c, 1) : (tma ? fb_tma_grid(c) : c->grid_spmv[1]);
   if (sym) fb_sym_launch(c, 1, c->dir, c->Ad, c->rhs, c->partials);
+  else if (tma) fb_tma_launch(c, 1, c->dir, c->Ad, c->rhs, c->partials);
   else launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, dqOut);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
   if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
@@ -665,8 +666,9 @@ void enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) 
     fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, nDq, nopeer);
     c->launches++;
     if (sym) fb_sym_launch(c, 2, c->x, c->res, c->rhs, c->partials);
+    else if (tma) fb_tma_launch(c, 2, c->x, c->res, c->rhs, c->partials);
     else launch_spmv_mode<2>(c, c->Keff, c->x, c->res, c->rhs, rhoOut);
-    if (defer) { rhoSlots = c->partials; nRhoSlots = sym ? fb_sym_grid(c, 2) : c->grid_spmv[2]; }
+    if (defer) { rhoSlots = c->partials; nRhoSlots = sym ? fb_sym_grid(c, 2) : (tma ? fb_tma_grid(c) : c->grid_spmv[2]); }
   } else {
     fb_launch(c->pdl, c->stream, k_update<false>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, nDq, nopeer);
     c->launches++;
@@ -719,6 +721,10 @@ int finish_solve(fb_context *c) {
   const bool notConverged = rhoFinal > s.eps2 * s.rho0;
   c->last_iters = s.iters * (notConverged ? -1 : 1);
   c->last_ratio = (s.rho0 != 0.0) ? rhoFinal / s.rho0 : 0.0;
+  if (c->tma_want && c->tma && fb_tma_failed(c)) {
+    fb_set_error("bulk-copy staged SpMV: an mbarrier wait ran out (FEMBRAIN_B200_SPMV=tma is experimental)");
+    return FB_ERR_CUDA;
+  }
   if (c->dist && s.comm_error) {
     fb_set_error("peer-memory exchange timed out (a rank stopped publishing)");
     return FB_ERR_COMM;
@@ -739,6 +745,12 @@ int start_solve(fb_context *c, double eps, int maxIt) {
     if (!c->sym) c->sym_want = 0;
   }
   if (c->sym_want) FB_TRY(fb_sym_pack(c));
+  // products with the matrix staged through shared memory by the bulk-copy engine (fb_tma.cu, experimental): same scope
+  if (c->tma_want && (c->dist || c->batch || c->pers_grid > 0 || c->pcg_fused || c->pcg_graph)) c->tma_want = 0;
+  if (c->tma_want && !c->tma) {
+    FB_TRY(fb_tma_plan(c));
+    if (!c->tma) c->tma_want = 0;
+  }
   if (p2p) {
     fb_dist_peer_args(c, &pa);
     pa.epoch = fb_dist_epoch(c, 0, FB_COMM_RHO);
@@ -792,6 +804,7 @@ int fb_spmv_plan(fb_context *c) {
   const char *env = getenv("FEMBRAIN_B200_SPMV");
   c->use_rows3 = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
   c->sym_want = env && !strcmp(env, "sym");
+  c->tma_want = env && !strcmp(env, "tma");
   const size_t n = (size_t)c->r;
   // vector kernels: at most one resident wave, one 16-byte item per thread on small meshes.  Fatter CTAs (2/4/8 items per
   // thread, fewer CTAs adding the producer's slots) were measured slower: 51.3 / 52.8 / 55.7 us per iteration at 1M tets,

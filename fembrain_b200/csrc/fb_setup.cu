@@ -146,8 +146,8 @@ int fb_build_topology(fb_context *c) {
   c->nB = nB;
   c->nnzK = 9ll * nB;
 
-  status = fb_dev_alloc(c, &c->bp, (size_t)c->nV + 1);
-  if (!status) status = fb_dev_alloc(c, &c->bc, (size_t)nB);
+  status = fb_dev_alloc(c, &c->bp, (size_t)c->nV + 1 + 8);  // + slack for 16-byte-line bulk copies (fb_tma.cu)
+  if (!status) status = fb_dev_alloc(c, &c->bc, (size_t)nB + 8);
   if (!status) status = fb_dev_alloc(c, &c->brow, (size_t)nB);
   if (!status) status = fb_dev_alloc(c, &c->diag, (size_t)c->nV);
   if (!status) status = fb_dev_alloc(c, &c->seg, (size_t)nB + 1);

@@ -155,6 +155,7 @@ struct fb_context {
   FbBatch *batch;
   FbSym *sym;
   FbTma *tma;
+  int l2_evict;  // FEMBRAIN_B200_L2EVICT=1
   int tma_want;  // FEMBRAIN_B200_SPMV=tma: products with the matrix staged through shared memory by cp.async.bulk (experimental)
   int sym_want;  // FEMBRAIN_B200_SPMV=sym: products of the three-kernel schedule from the block-upper triangle (plan built at the first solve)
 };

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(SPMV_TB) k_spmv(int rowBeg, int rowEnd, const 
 // (b) two launches, interior rows first and the rows next to the cuts (which wait, add both sums and publish) second:
 // 279 vs 268 ms per step on 2 GPUs at 10M tets — the halo has already landed when the product starts, so there is no
 // wait to hide, and the second launch's own latency chain is added to every iteration.
-template <int MODE, int MINB>
+template <int MODE, int MINB, bool EVICT = false>
 __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int rowBeg, int nV, const int *__restrict__ bp, const int *__restrict__ bc,
                                                               const double *__restrict__ A, const double *__restrict__ x,
                                                               double *__restrict__ y, const unsigned char *__restrict__ mask,
@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int rowBeg, int nV
     if (sc->done) return;
     if (pa.enabled && pa.haloMask) peer_wait_halo(pa, sc);  // the neighbours' d has landed in my ghost entries
   }
+  const unsigned long long policy = EVICT ? l2_policy_evict_first() : 0ull;
   const int lane = threadIdx.x & (TILE_G - 1);
   const unsigned gmask = 0xffffu << (threadIdx.x & 16);
   const int groupsPerBlock = SPMV_TB / TILE_G;
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(SPMV_TB, MINB) k_spmv_rows3(int rowBeg, int nV
         const int t = base + lane + TILE_G * p;
         col[p] = (t < n3) ? __ldg(bc + rs + t / 3) : -1;
       }
-      load_row_chunk(A, rs, n3, base, lane, val);
+      if (EVICT) load_row_chunk_hint(A, rs, n3, base, lane, val, policy);
+      else load_row_chunk(A, rs, n3, base, lane, val);
 #pragma unroll
       for (int p = 0; p < 3; p++) {
         const int t = base + lane + TILE_G * p;
@@ -581,7 +583,10 @@ void launch_spmv_mode(fb_context *c, const double *A, const double *x, double *y
   // MODE 0 is the plain product of the inspection calls: all rows.  The solver's products visit owned rows only.
   const int lo = (MODE == 0) ? 0 : c->row_lo, hi = (MODE == 0) ? c->nV : c->row_hi;
   if (c->use_rows3) {
-    fb_launch(c->pdl && MODE != 0, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
+    if (c->l2_evict && MODE != 0)
+      fb_launch(c->pdl != 0, c->stream, k_spmv_rows3<MODE, 4, true>, grid, SPMV_TB, lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
+    else
+      fb_launch(c->pdl && MODE != 0, c->stream, k_spmv_rows3<MODE, 4>, grid, SPMV_TB, lo, hi, c->bp, c->bc, A, x, y, c->rowmask, b, c->invD, c->sc, c->partials, outp, pa);
   } else if (MODE != 3) {
     constexpr int M = MODE == 3 ? 1 : MODE;
     switch (c->spmv_group) {
@@ -805,6 +810,8 @@ int fb_spmv_plan(fb_context *c) {
   c->use_rows3 = (c->spmv_group == 16) && !(env && !strcmp(env, "rows"));
   c->sym_want = env && !strcmp(env, "sym");
   c->tma_want = env && !strcmp(env, "tma");
+  const char *ev = getenv("FEMBRAIN_B200_L2EVICT");
+  c->l2_evict = ev && atoi(ev) != 0;  // matrix loads of k_spmv_rows3 with an L2 evict-first hint (not measured yet)
   const size_t n = (size_t)c->r;
   // vector kernels: at most one resident wave, one 16-byte item per thread on small meshes.  Fatter CTAs (2/4/8 items per
   // thread, fewer CTAs adding the producer's slots) were measured slower: 51.3 / 52.8 / 55.7 us per iteration at 1M tets,

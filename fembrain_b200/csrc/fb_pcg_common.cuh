@@ -43,6 +43,33 @@ struct RowVals {
   double v[3][3];  // [pass][k]
 };
 
+// The same streaming load with an L2 eviction hint (createpolicy + .L2::cache_hint): matrix lines marked evict-first leave L2
+// before the PCG vectors (d, q, r, x, 1/diag: 21 MB at 1M tets) do, so the vector kernels and the x gathers of the next
+// product can find them there.  Opt-in (FEMBRAIN_B200_L2EVICT=1), not measured yet.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ld_stream_hint(const double *p, unsigned long long policy) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void load_row_chunk_hint(const double *__restrict__ A, int rs, int n3, int base, int lane, RowVals &o,
+                                                    unsigned long long policy) {
+  const double *a0 = A + 9 * (size_t)rs + base;
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int t = base + lane + TILE_G * p;
+    const bool ok = t < n3;
+    const double *q = a0 + lane + TILE_G * p;
+    o.v[p][0] = ok ? ld_stream_hint(q, policy) : 0.0;
+    o.v[p][1] = ok ? ld_stream_hint(q + n3, policy) : 0.0;
+    o.v[p][2] = ok ? ld_stream_hint(q + 2 * (size_t)n3, policy) : 0.0;
+  }
+}
+
 __device__ __forceinline__ void load_row_chunk(const double *__restrict__ A, int rs, int n3, int base, int lane, RowVals &o) {
   const double *a0 = A + 9 * (size_t)rs + base;
 #pragma unroll

@@ -27,9 +27,11 @@ print(json.dumps({"in_step_spmv_us": m * 1e6, "in_step_gbs": b / m / 1e9, "iso_s
 
 if __name__ == "__main__":
     nx = sys.argv[1] if len(sys.argv) > 1 else "56"
-    variants = sys.argv[2:] or ["rows", "tiled", "rows3_4", "rows3_5", "rows3_6", "rows3_8"]
+    variants = sys.argv[2:] or ["default", "rows", "l2evict", "tma", "sym"]
     for var in variants:
         env = dict(os.environ, FEMBRAIN_B200_SPMV=var)
+        if var == "l2evict":  # default kernel, matrix loads with the L2 evict-first hint
+            env = dict(os.environ, FEMBRAIN_B200_L2EVICT="1")
         out = subprocess.run([sys.executable, "-c", CHILD, nx], env=env, capture_output=True, text=True)
         line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:]
         print(var, line, flush=True)

@@ -16,7 +16,9 @@ pytestmark = [pytest.mark.gpu,
 MESHES = {
     "cube7": lambda: cases.cube_case(7)[:3],
     "cube13": lambda: cases.cube_case(13)[:3],
-    "cube30": lambda: cases.cube_case(30)[:3],   # more tiles than CTAs: the stage ring wraps
+    "cube30": lambda: cases.cube_case(30)[:3],   # 843 row tiles: about three per CTA
+    "cube40": lambda: cases.cube_case(40)[:3],   # 2000 row tiles on 296 CTAs: the three-stage ring wraps (not run in round 1;
+                                                 # the 1M-tet timing run wrapped it 6 times per CTA with the default's iteration count)
     "eggshell": lambda: cases.golden_mesh("eggshell"),
 }
 

@@ -479,7 +479,11 @@ int fb_create_batch(fb_context **out, int count, const int *numVertices, const d
   for (int m = 0; m < count; m++) {
     const int off = b->vtx[m], nv = numVertices[m];
     for (size_t i = 4 * (size_t)b->tet[m]; i < 4 * (size_t)b->tet[m + 1]; i++) {
-      if (tets[i] < 0 || tets[i] >= nv) { delete b; fb_set_error("mesh %d: tetrahedron %zu references a vertex outside [0, %d)", m, i / 4 - (size_t)b->tet[m], nv); return FB_ERR_BAD_MESH; }
+      if (tets[i] < 0 || tets[i] >= nv) {
+        fb_set_error("mesh %d: tetrahedron %zu references a vertex outside [0, %d)", m, i / 4 - (size_t)b->tet[m], nv);
+        delete b;
+        return FB_ERR_BAD_MESH;
+      }
       ct[i] = tets[i] + off;
     }
     std::vector<int> fv(fixedVertices + fo, fixedVertices + fo + numFixed[m]);

@@ -98,6 +98,7 @@ def load_library():
         "fb_deformable_pick_vertices": (ci, [vp, vp, vp, ci, vp, vp, vp]), "fb_deformable_pick_vertex": (ci, [vp, vp, vp, vp, vp]),
         "fb_force_assembly_seconds": (cd, [vp]), "fb_system_solve_seconds": (cd, [vp]), "fb_step_seconds": (cd, [vp]),
         "fb_last_cg_iterations": (ci, [vp]), "fb_last_cg_residual_ratio": (cd, [vp]),
+        "fb_veg_save": (ci, [C.c_char_p, ci, ci, vp, ci, vp, vp, vp, vp]),
         "fb_create_batch": (ci, [pp, ci, vp, vp, vp, vp, vp, vp, prm]), "fb_batch_count": (ci, [vp]),
         "fb_batch_offsets": (ci, [vp, vp, vp]), "fb_batch_last_cg_iterations": (ci, [vp, vp, vp]),
         "fb_partition_ordering": (ci, [ci, ci, vp, ci, vp, C.POINTER(ci)]), "fb_partition_reordered": (ci, [vp]),
@@ -222,6 +223,19 @@ def veg_load(path, _fn="fb_veg_load"):
         for p in ptrs:
             lib.fb_veg_free(p)
     return v, t, E, nu, rho
+
+
+VEG_STYLE_FEMBRAIN, VEG_STYLE_VEGA = 0, 1
+
+
+def veg_save(path, verts, tets, E=None, nu=None, density=None, style=VEG_STYLE_VEGA):
+    """fb_veg_save: VolMeshIO::writeVega (style FEMBRAIN) or VolumetricMesh::save (style VEGA) file formats."""
+    lib = load_library()
+    v, t = _f64(verts).reshape(-1, 3), _i32(tets).reshape(-1, 4)
+    mats = [None if a is None else _f64(a).reshape(-1) for a in (E, nu, density)]
+    st = lib.fb_veg_save(str(path).encode(), style, len(v), _ptr(v), len(t), _ptr(t), *[None if a is None else _ptr(a) for a in mats])
+    if st != FB_OK:
+        raise FemBrainError(st, "fb_veg_save", lib.fb_last_error_string().decode())
 
 
 def _f64(a):

@@ -241,6 +241,84 @@ int fb_veg_load(const char *path, int *num_vertices, int *num_tets, double **ver
 
 void fb_veg_free(void *p) { free(p); }
 
+int fb_veg_save(const char *path, int style, int nV, const double *vertices, int nT, const int *tets, const double *E,
+                const double *nu, const double *density) {
+  if (!path || nV < 0 || nT < 0 || (nV > 0 && !vertices) || (nT > 0 && !tets) || (style != FB_VEG_STYLE_FEMBRAIN && style != FB_VEG_STYLE_VEGA)) {
+    fb_set_error("bad arguments to fb_veg_save");
+    return FB_ERR_INVALID_ARGUMENT;
+  }
+  const bool haveMat = E && nu && density;
+  if (style == FB_VEG_STYLE_VEGA && !haveMat && (E || nu || density)) {
+    fb_set_error("fb_veg_save: E, nu and density must be given together");
+    return FB_ERR_INVALID_ARGUMENT;
+  }
+  for (size_t i = 0; i < 4 * (size_t)nT; i++)
+    if (tets[i] < 0 || tets[i] >= nV) { fb_set_error("fb_veg_save: tetrahedron %zu references a vertex outside [0, %d)", i / 4, nV); return FB_ERR_BAD_MESH; }
+  // VolMeshIO::writeVega refuses an empty mesh (VolMeshIO.cpp:175-176)
+  if (style == FB_VEG_STYLE_FEMBRAIN && (nV == 0 || nT == 0)) { fb_set_error("fb_veg_save: empty mesh"); return FB_ERR_BAD_MESH; }
+  FILE *f = fopen(path, "w");
+  if (!f) { fb_set_error("fb_veg_save: cannot write %s", path); return FB_ERR_INVALID_ARGUMENT; }
+  if (style == FB_VEG_STYLE_FEMBRAIN) {
+    fprintf(f, "# Vega Mesh File, Generated by FemBrain.\n# %d vertices, %d elements\n\n*VERTICES\n%d 3 0 0\n", nV, nT, nV);
+    // operator<<(double) with the stream defaults = %g
+    for (int i = 0; i < nV; i++) fprintf(f, "%d %g %g %g\n", i + 1, vertices[3 * (size_t)i], vertices[3 * (size_t)i + 1], vertices[3 * (size_t)i + 2]);
+    fprintf(f, "\n*ELEMENTS\nTET\n%d 4 0\n", nT);
+    for (int i = 0; i < nT; i++) {
+      const int *t = tets + 4 * (size_t)i;
+      fprintf(f, "%d %d %d %d %d\n", i + 1, t[0] + 1, t[1] + 1, t[2] + 1, t[3] + 1);
+    }
+    fprintf(f, "\n*MATERIAL BODY\nENU, 1000, 10000000, 0.45\n\n*REGION\nallElements, BODY\n");
+  } else {
+    fprintf(f, "# Vega mesh file.\n# %d vertices, %d elements\n\n*VERTICES\n%d 3 0 0\n", nV, nT, nV);
+    for (int i = 0; i < nV; i++)
+      fprintf(f, "%d %.15G %.15G %.15G\n", i + 1, vertices[3 * (size_t)i], vertices[3 * (size_t)i + 1], vertices[3 * (size_t)i + 2]);
+    fprintf(f, "\n*ELEMENTS\nTET\n%d 4 0\n", nT);
+    for (int i = 0; i < nT; i++) {
+      const int *t = tets + 4 * (size_t)i;
+      fprintf(f, "%d %d %d %d %d\n", i + 1, t[0] + 1, t[1] + 1, t[2] + 1, t[3] + 1);
+    }
+    fprintf(f, "\n");
+    if (haveMat && nT > 0) {
+      // distinct (density, E, nu) triples in order of first appearance; element -> material
+      std::vector<int> first;           // element that introduced material k
+      std::vector<int> mat((size_t)nT);
+      for (int el = 0; el < nT; el++) {
+        int k = 0;
+        for (; k < (int)first.size(); k++) {
+          const int e0 = first[(size_t)k];
+          if (density[e0] == density[el] && E[e0] == E[el] && nu[e0] == nu[el]) break;
+        }
+        if (k == (int)first.size()) first.push_back(el);
+        mat[(size_t)el] = k;
+      }
+      const int nM = (int)first.size();
+      for (int k = 0; k < nM; k++) {
+        const int e0 = first[(size_t)k];
+        fprintf(f, "*MATERIAL material_%d\nENU, %.15G, %.15G, %.15G\n\n", k, density[e0], E[e0], nu[e0]);
+      }
+      if (nM > 1) {
+        for (int k = 0; k < nM; k++) {
+          fprintf(f, "*SET set_%d\n", k);
+          int count = 0;
+          for (int el = 0; el < nT; el++) {
+            if (mat[(size_t)el] != k) continue;
+            fprintf(f, "%d, ", el + 1);
+            if (++count == 8) { fprintf(f, "\n"); count = 0; }
+          }
+          if (count != 0) fprintf(f, "\n");
+          fprintf(f, "\n");
+        }
+        for (int k = 0; k < nM; k++) fprintf(f, "*REGION\nset_%d, material_%d\n\n", k, k);
+      } else {
+        fprintf(f, "*REGION\nallElements, material_0\n\n");
+      }
+    }
+  }
+  const bool bad = ferror(f) != 0;
+  if (fclose(f) != 0 || bad) { fb_set_error("fb_veg_save: write to %s failed", path); return FB_ERR_INVALID_ARGUMENT; }
+  return FB_OK;
+}
+
 // TetMesh(char* filename, int specialFileType = 0), src/3rdparty/vegafem/volumetricMesh/tetMesh.cpp:45-127: TetGen's
 // <base>.node ("numVertices 3", then "index x y z", 1-indexed and consecutive) and <base>.ele ("numElements 4", then
 // "index v0 v1 v2 v3", vertices 1-indexed); comment and blank lines skipped as everywhere in the parser; one material

@@ -168,6 +168,21 @@ void fb_veg_free(void *array);
  * Same output conventions as fb_veg_load (release with fb_veg_free).  Host-only. */
 int fb_tetgen_load(const char *basename, int *num_vertices, int *num_tets, double **vertices, int **tets, double **E, double **nu,
                    double **density);
+/* .veg writers.  Host-only.
+ * FB_VEG_STYLE_FEMBRAIN = VolMeshIO::writeVega (DEF/VolMeshIO.cpp:171-224), the writer behind every "Generated by FemBrain" model
+ * in data/models/blobtree: coordinates in the default ostream format (6 significant digits, printf %g), 1-based ids, and ALWAYS
+ * the fixed material "ENU, 1000, 10000000, 0.45" on allElements — E / nu / density are ignored, as that writer has none.
+ * FB_VEG_STYLE_VEGA = VolumetricMesh::save (VEGA/volumetricMesh/volumetricMesh.cpp:646-757): %.15G coordinates; one *MATERIAL
+ * per distinct (density, E, nu) triple in order of first appearance (named material_<k>); with one material a single region
+ * "allElements, material_0", otherwise one *SET set_<k> (1-based element ids, 8 per line) and one *REGION per material.
+ * E / nu / density are per-element arrays as fb_veg_load returns them; all three NULL = no *MATERIAL / *REGION section (the
+ * loaders then apply the reference's default material).  Reading the result back with fb_veg_load or the reference's loader
+ * gives the same elements and per-element materials, and the reference's own TetMesh::save of that file reproduces it byte
+ * for byte (tests/test_veg.py). */
+#define FB_VEG_STYLE_FEMBRAIN 0
+#define FB_VEG_STYLE_VEGA 1
+int fb_veg_save(const char *path, int style, int num_vertices, const double *vertices, int num_tets, const int *tets,
+                const double *E, const double *nu, const double *density);
 /* TetMesh(char* filename) + the setup chain of fb_create_with_materials */
 int fb_create_from_veg(fb_context **out, const char *path, int num_fixed_vertices, const int *fixed_vertices, const fb_params *params);
 /* GPUPoly::applyFemDisplacements + ApplyVertexDeformations (implicit/OclPolygonizer.cpp:1543-1584, data/opencl/Polygonizer.cl:1417-1427):

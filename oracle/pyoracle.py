@@ -65,6 +65,8 @@ def _lib(kind: str):
         lib.fbport_get_external_forces.restype = None
         lib.fbport_get_external_forces.argtypes = [vp, vp]
     if kind == "ref":
+        lib.fbref_save_veg.restype = ci
+        lib.fbref_save_veg.argtypes = [vp, C.c_char_p]
         lib.fbref_create_from_veg.restype = vp
         lib.fbref_create_from_veg.argtypes = [C.c_char_p, ci, vp, cd, cd, cd]
         lib.fbref_num_vertices.restype = ci
@@ -144,6 +146,11 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def save_veg(self, path):
+        """The reference's own writer (TetMesh::save) on the mesh it loaded (ref only)."""
+        assert self.kind == "ref"
+        return self._lib.fbref_save_veg(self._h, str(path).encode())
 
     def mesh(self):
         """(verts, tets, E, nu, rho) as the reference holds them after loading a .veg (ref only)."""

@@ -110,6 +110,9 @@ void *fbref_create_from_veg(const char *path, int nFixedVerts, const int *fixedV
   return s;
 }
 
+/* TetMesh::save -> VolumetricMesh::save (volumetricMesh.cpp:646-757): the reference's own .veg writer on the mesh it holds */
+int fbref_save_veg(void *p, const char *path) { return ((RefSim *)p)->mesh->save((char *)path); }
+
 int fbref_num_vertices(void *p) { return ((RefSim *)p)->nV; }
 int fbref_num_tets(void *p) { return ((RefSim *)p)->nT; }
 /* mesh as the reference holds it after loading: vertices, 0-based tets, per-element E / nu / density */

@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — the reference's headline metric on its own configuration, on B200.
+"""bench.py — the reference's headline metric on its own configurations, on B200.
 
-Metric (BASELINE.json): implicit FEM steps/s (one VolumeConservingIntegrator::DoTimestep = corotational
-assembly + Jacobi-PCG solve), with assembly Mtets/s and the SpMV's achieved HBM GB/s beside it.
-Workload at N=1 (BASELINE.json configs[1]): CreateTruthCube(56,56,56, 0.2) = 998,250 tets, E=1e7, nu=0.46,
-rho=1000, h=0.0333, dampK=0.01, y=0 plane fixed, pick-mode haptic load (1e4,0,0) on the far corner node,
-FP64, starting from rest.  At N>1 every rank steps its own copy of that mesh (config-4 style
-batch of independent meshes: no data-path collective, weak scaling); `--partitioned` instead splits ONE mesh
-by row blocks across the ranks with NCCL halo exchange (config 5, strong scaling).
+Metric (BASELINE.json): implicit FEM steps/s (one VolumeConservingIntegrator::DoTimestep = corotational assembly +
+Jacobi-PCG solve), with assembly Mtets/s and the SpMV's achieved HBM GB/s beside it.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx 56]
+Workload of the headline line (BASELINE.json configs[2], the configuration the 30 steps/s target is quoted on):
+CreateTruthCube(120,120,120, 0.2) = 10,110,954 tets, E=1e7, nu=0.46, rho=1000, h=0.0333, dampK=0.01, y=0 plane fixed,
+pick-mode haptic load (1e4,0,0) on the far corner node, FP64, from rest.
+  N = 1 : that mesh on one GPU.
+  N > 1 : THE SAME mesh split by row blocks over the N ranks (fb_create_partitioned: halo of the search direction and the
+          two dot products exchanged through peer memory over NVLink, NCCL as the fallback) — strong scaling; rank 0 also
+          steps the whole mesh on its own GPU and the line carries a `parity_check` block (non-zero exit if it fails).
+Every line also carries, measured in the same run:
+  config5_50M   CreateTruthCube(204) = 50,192,562 tets on the same N GPUs (BASELINE.json configs[4])
+  config4_batch 32 independent 196,608-tet meshes per GPU in one batch context per GPU (configs[3]; N = 8: the 256 meshes)
+  config2_1M    (N = 1) the 998,250-tet cube of configs[1]
+  cpu_baseline  (N = 1) the unmodified reference's DoTimestep on the host, bounded sample
+`--replicas` restores round 1's N > 1 behaviour (every rank steps its own copy: weak scaling, no communication).
 
-One JSON line on stdout (rank 0).  `value` = steps/s of the whole job with forces resident in HBM;
-`e2e` = the same through the C ABI with HOST buffers (pinned force upload + displacement download
-inside the timed region every step).
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx 120]
+
+One JSON line on stdout (rank 0).  `value` = steps/s of the whole job with forces resident in HBM; `e2e` = the same
+through the C ABI with HOST buffers (pinned force upload + displacement download inside the timed region every step).
 """
 from __future__ import annotations
 
@@ -33,6 +41,10 @@ if ROOT not in sys.path:
 
 METRIC = "fem_steps_per_s"
 UNIT = "steps/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
 
 
 def measured_peak_gbs():
@@ -101,6 +113,9 @@ def workload(nx):
     return v, t, fixed, f
 
 
+CONFIG_NAMES = {56: "BASELINE.json configs[1]", 120: "BASELINE.json configs[2]", 33: "BASELINE.json configs[3] mesh", 204: "BASELINE.json configs[4]"}
+
+
 def config_dict(nx, nT, n_gpus, partitioned):
     # matrix bytes per GPU in the solver's own format (8.44 B per nonzero, ~22.5 nonzeros per tet on the cube) against the 126 MB L2
     mat_mb = 8.44 * 22.5 * (nT / (n_gpus if partitioned else 1)) / 1e6
@@ -109,407 +124,536 @@ def config_dict(nx, nT, n_gpus, partitioned):
                f"L2-resident from one SpMV to the next, as it does in production use")
     return {
         "workload": f"CreateTruthCube({nx},{nx},{nx},0.2): {nT} tets, corotational FEM + Jacobi-PCG, FP64, y=0 fixed, "
-                    f"point load (1e4,0,0), from rest" + (" [BASELINE.json configs[1]]" if nx == 56 else ""),
+                    f"point load (1e4,0,0), from rest" + (f" [{CONFIG_NAMES[nx]}]" if nx in CONFIG_NAMES else ""),
         "tets_per_gpu": nT if not partitioned else nT // n_gpus,
-        "parallelism": ("row-block partition + NCCL halo" if partitioned else
-                        ("independent mesh per GPU, no communication" if n_gpus > 1 else "single GPU")),
+        "parallelism": (f"row-block partition of ONE mesh over {n_gpus} GPUs (slabs), halo of d + two dot products per PCG iteration "
+                        f"exchanged through peer memory over NVLink (NCCL fallback)" if partitioned else
+                        ("independent mesh per GPU, no communication (--replicas)" if n_gpus > 1 else "single GPU")),
         "l2_policy": l2,
         "cg": "eps 1e-6, max 10000, x0 = 0, exact residual every 30 iterations (reference defaults)",
     }
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(nx, cg_sample_iters, iters_per_step, steps, warmup, log=lambda *a: None):
-    """Times the reference's own CPU code (oracle/_ref) — or the plain-C port when _ref is absent — on the
-    same workload, bounded: per step the FULL assembly (GetForceAndMatrix) plus `cg_sample_iters` PCG
-    iterations on the constrained matrix, extrapolated to `iters_per_step` iterations (the PCG cost is
-    linear in the iteration count).  Single-threaded: the reference path has no threads."""
+# CPU side: the unmodified reference (oracle/_ref) — or the pinned plain-C port when _ref is absent
+def _oracle_kind():
     from oracle import pyoracle
 
-    kind = "ref" if pyoracle.available("ref") else "port"
-    if kind == "port" and not pyoracle.available("port"):
+    if pyoracle.available("ref"):
+        return "ref"
+    if not pyoracle.available("port"):
         pyoracle.build("port")
+    return "port"
+
+
+def reference_steps(nx, n_steps, budget_s, t_origin=None):
+    """The reference's own setup chain and its stock VolumeConservingIntegrator::DoTimestep
+    (PS_VolumeConservingIntegrator.cpp:46-260) on CreateTruthCube(nx), from rest, n_steps times (fewer if the wall-clock
+    budget runs out: the number actually run is reported).  Single-threaded: the reference path has no threads
+    (SURVEY.md §2b).  Assembly and solve times are the reference's own PerformanceCounters."""
+    from oracle import pyoracle
+
+    t_origin = time.perf_counter() if t_origin is None else t_origin
+    kind = _oracle_kind()
     v, t, fixed, f = workload(nx)
     t0 = time.perf_counter()
     o = pyoracle.Oracle(v, t, fixed, kind=kind)
     t_setup = time.perf_counter() - t0
-    log(f"[cpu] {kind} setup {t_setup:.1f} s")
-    u = np.zeros(o.r)
-    b = f[np.setdiff1d(np.arange(o.r), np.concatenate([3 * fixed, 3 * fixed + 1, 3 * fixed + 2]))]
-    per_step = []
-    t_asm_l, t_it_l = [], []
-    for s in range(warmup + steps):
+    log(f"[cpu] {kind} setup of nx={nx} ({len(t)} tets): {t_setup:.1f} s")
+    o.set_external_forces(f)
+    secs, asm, sol = [], [], []
+    for s in range(n_steps):
+        if secs and (time.perf_counter() - t_origin) + 1.3 * max(secs) > budget_s:
+            break
         t0 = time.perf_counter()
-        o.force_and_matrix(u)
-        t_asm = time.perf_counter() - t0
-        o.load_system_from_K()
-        t0 = time.perf_counter()
-        o.solve_iters(cg_sample_iters, b)
-        t_cg = time.perf_counter() - t0
-        t_iter = t_cg / cg_sample_iters
-        if s >= warmup:
-            per_step.append(t_asm + iters_per_step * t_iter)
-            t_asm_l.append(t_asm); t_it_l.append(t_iter)
-    sec = float(np.mean(per_step))
-    return {
-        "kind": "reference" if kind == "ref" else "port",
-        "cores": 1,
-        "seconds_per_step": sec,
-        "value": 1.0 / sec,
-        "assembly_mtets_per_s": len(t) / float(np.mean(t_asm_l)) / 1e6,
-        "seconds_per_cg_iteration": float(np.mean(t_it_l)),
-        "setup_seconds": t_setup,
-        "sample": (f"same mesh (nx={nx}, {len(t)} tets); per step: full GetForceAndMatrix + {cg_sample_iters} PCG iterations on the "
-                   f"constrained matrix, extrapolated to {iters_per_step} iterations/step; 1 thread of {os.cpu_count()} "
-                   f"(the reference path is single-threaded)"),
-    }
-
-
-# committed iteration counts of the bench workload (from rest, steps 1..): measured on B200 by this
-# bench (matches the CPU oracle to +-1 where the oracle is affordable); used by --impl reference to
-# extrapolate its bounded PCG sample without touching the GPU arm
-def ncu_assembly(nx):
-    """ncu figures of the assembly kernels for this size (profiles/ncu_traffic.json), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            return json.load(fh).get(str(nx), {}).get("assembly")
-    except Exception:
-        return None
-
-
-def ncu_traffic(nx):
-    """dram__bytes_read.sum + dram__bytes_write.sum per SpMV launch from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json), or None when no capture exists for this size."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            return json.load(fh).get(str(nx), {}).get("spmv_bytes_per_launch")
-    except Exception:
-        return None
-
-
-def known_iterations(nx):
-    try:
-        with open(os.path.join(ROOT, "profiles", "bench_iterations.json")) as fh:
-            tab = json.load(fh)
-        return tab.get(str(nx))
-    except Exception:
-        return None
+        rc = o.do_timestep()
+        secs.append(time.perf_counter() - t0)
+        asm.append(o.assembly_time()); sol.append(o.solve_time())
+        log(f"[cpu] step {s}: {secs[-1]:.1f} s (assembly {asm[-1]:.2f}, solve {sol[-1]:.2f}), rc {rc}")
+        if rc != 0:
+            break
+    nnz = o.nnz_K
+    o.close()
+    return {"kind": "reference" if kind == "ref" else "port", "nx": nx, "tets": len(t), "nnz_K": nnz, "steps_run": len(secs),
+            "seconds_per_step": float(np.mean(secs)), "step_seconds": secs, "assembly_seconds": asm, "solve_seconds": sol,
+            "setup_seconds": t_setup, "assembly_mtets_per_s": len(t) / float(np.mean(asm)) / 1e6 if asm and np.mean(asm) > 0 else None}
 
 
 def run_reference(args):
+    """--impl reference: a RUN of the reference's stock DoTimestep on the arm's own mesh, not a model.  At 10M tets one
+    reference step is several minutes, so the number of steps actually run (from rest, no warm-up) is what fits the
+    wall-clock budget and is what the line reports as `steps`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    its = known_iterations(args.nx)
-    iters = int(np.mean(its[args.warmup:args.warmup + args.steps])) if its else 650
-    from oracle import pyoracle  # noqa: F401
-    res = cpu_reference_sample(args.nx, args.cpu_cg_iters, iters, args.steps, args.warmup, log=lambda *a: print(*a, file=sys.stderr))
-    from fembrain_b200 import meshes
-    nT = 6 * (args.nx - 1) ** 3
+    t_origin = time.perf_counter()
+    nx = args.nx
+    nT = 6 * (nx - 1) ** 3
+    want = max(1, args.steps)
+    res = reference_steps(nx, want, args.ref_budget_s, t_origin)
+    n = res["steps_run"]
+    sec = res["seconds_per_step"]
+    sample = (f"stock VolumeConservingIntegrator::DoTimestep of the compiled reference on the same mesh (nx={nx}, {nT} tets), {n} step(s) from rest, "
+              f"no warm-up ({want} requested; wall-clock budget {args.ref_budget_s:.0f} s incl. {res['setup_seconds']:.0f} s of reference constructors); "
+              f"1 thread of {os.cpu_count()} (the reference path is single-threaded); the reference's CG return value is not visible through "
+              f"DoTimestep (mapped to 0, PS_VolumeConservingIntegrator.cpp:198-199): compare with cg_iterations_warmup[:{n}] of the GPU arm")
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.nx, nT, 1, False),
-        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
-        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "assembly_mtets_per_s": res["assembly_mtets_per_s"], "cg_iterations_per_step_assumed": iters,
-        "seconds_per_cg_iteration": res["seconds_per_cg_iteration"], "gpu_launches": 0,
+        "impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": 0,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and not args.replicas else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(nx, nT, 1, False),
+        "cpu_baseline": {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": res["kind"], "sample": sample},
+        "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "assembly_mtets_per_s": res["assembly_mtets_per_s"], "step_seconds": res["step_seconds"],
+        "assembly_seconds": res["assembly_seconds"], "solve_seconds": res["solve_seconds"],
+        "setup_seconds": res["setup_seconds"], "gpu_launches": 0,
     }
+    line["config"]["parallelism"] = "reference CPU path, 1 thread"
     args.emit(line)
     return 0
 
 
+def cpu_baseline_sample(nx_full, nT_full, nnz_full, mean_iters_full, nx_sample):
+    """cpu_baseline of the GPU arm's line: the reference's stock DoTimestep on a SMALLER cube of the same family (bounded:
+    ~10-30 s of CPU work), one step from rest; `value` scales its measured assembly time by the tet ratio and its measured
+    solve time by nnz ratio x iteration ratio to the bench mesh — stated in `sample`.  The full-size run of the reference is
+    `bench.py --impl reference`."""
+    from oracle import pyoracle
+
+    kind = _oracle_kind()
+    v, t, fixed, f = workload(nx_sample)
+    t0 = time.perf_counter()
+    o = pyoracle.Oracle(v, t, fixed, kind=kind)
+    t_setup = time.perf_counter() - t0
+    o.set_external_forces(f)
+    t0 = time.perf_counter()
+    o.do_timestep()
+    t_step = time.perf_counter() - t0
+    t_asm, t_sol = o.assembly_time(), o.solve_time()
+    _, its = o.solve(eps=1e-6)   # the same system again, to read the solver's own iteration count (CGSolver.cpp:189)
+    nnz_s, nT_s = o.nnz_K, len(t)
+    o.close()
+    est = t_asm * nT_full / nT_s + t_sol * (nnz_full / nnz_s) * (mean_iters_full / max(its, 1)) + (t_step - t_asm - t_sol) * nT_full / nT_s
+    return {"value": 1.0 / est, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
+            "sample": (f"stock DoTimestep of the compiled reference on CreateTruthCube({nx_sample}) = {nT_s} tets, one step from rest: {t_step:.2f} s "
+                       f"(assembly {t_asm:.2f} s, solve {t_sol:.2f} s, {its} PCG iterations; constructors {t_setup:.1f} s); scaled to the bench mesh "
+                       f"({nT_full} tets, {mean_iters_full:.0f} iterations/step) by tets (assembly) and nnz x iterations (solve); 1 thread of "
+                       f"{os.cpu_count()}; the full-size reference run is `bench.py --impl reference`"),
+            "measured_steps_per_s_on_sample": 1.0 / t_step, "assembly_mtets_per_s": nT_s / t_asm / 1e6,
+            "seconds_per_cg_iteration_on_sample": t_sol / max(its, 1), "sample_tets": nT_s}
+
+
+def ncu_table(key, field):
+    """Figures from the committed `ncu --set full` captures (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh).get(str(key), {}).get(field)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Env:
+    """torch / torch.distributed plumbing shared by the GPU legs."""
 
-    import fembrain_b200 as fb
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the CUDA library has no fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import fembrain_b200 as fb
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+        self.torch, self.dist, self.fb = torch, dist, fb
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: the CUDA library has no fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return vals
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
+
+    def sum_over_ranks(self, val):
+        if self.world == 1:
+            return int(val)
+        t = self.torch.tensor([int(val)], dtype=self.torch.int64, device="cuda")
+        self.dist.all_reduce(t)
+        return int(t[0])
+
+    def comm_id(self):
+        idt = self.torch.zeros(128, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            idt.copy_(self.torch.frombuffer(bytearray(self.fb.comm_unique_id()), dtype=self.torch.uint8))
+        self.dist.broadcast(idt, 0)
+        return bytes(idt.cpu().numpy().tobytes())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+class Stepper:
+    """K steps of one context, resident or end to end, timed on the device between barriers."""
+
+    def __init__(self, env, sim, f, partitioned, tets=None):
+        torch = env.torch
+        self.env, self.sim, self.partitioned = env, sim, partitioned
+        self.r = sim.r
+        if partitioned:
+            b, e = sim.partition_range()
+            if sim.reordered:
+                order, _ = env.fb.partition_ordering(sim.nV, tets, env.world)   # (the cube keeps its numbering: slabs)
+                own = f.reshape(-1, 3)[order[b:e]].reshape(-1)
+            else:
+                own = f[3 * b:3 * e]
+            self.f_pinned = torch.from_numpy(np.ascontiguousarray(own)).pin_memory()
+            self.q_pinned = torch.empty(3 * (e - b), dtype=torch.float64).pin_memory()
+            sim.set_external_forces(f)           # resident arm: the force vector stays on every rank
+            self.f_dev = None
+        else:
+            self.f_pinned = torch.from_numpy(f).pin_memory()
+            self.q_pinned = torch.empty(self.r, dtype=torch.float64).pin_memory()
+            self.f_dev = torch.from_numpy(f).cuda()
+        self.h2d = self.f_pinned.numel() * 8
+        self.d2h = self.q_pinned.numel() * 8
         torch.cuda.synchronize()
 
-    nx = args.nx
-    v, t, fixed, f = workload(nx)
-    nT, r = len(t), 3 * len(v)
-    t0 = time.perf_counter()
-    partitioned = args.partitioned and world > 1
-    if partitioned:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(fb.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        sim = fb.Simulation(v, t, fixed, partition=(rank, world, bytes(idt.cpu().numpy().tobytes())), device=local)
-    else:
-        sim = fb.Simulation(v, t, fixed, device=local)
-    t_setup = time.perf_counter() - t0
-
-    f_pinned = torch.from_numpy(f).pin_memory()
-    q_pinned = torch.empty(r, dtype=torch.float64).pin_memory()
-    f_dev = torch.from_numpy(f).cuda()
-    torch.cuda.synchronize()
-
-    def timed_region(n_steps, e2e):
+    def region(self, n_steps, e2e):
+        sim = self.sim
         iters, t_asm, t_solve = [], 0.0, 0.0
-        barrier()
+        self.env.barrier()
         sim.timer_start()
         for _ in range(n_steps):
-            if e2e:
-                sim.set_external_forces_ptr(f_pinned.data_ptr())      # H2D from pinned host memory
-            elif not partitioned:
-                sim.set_external_forces_dev(f_dev.data_ptr())         # resident in HBM
-            # (partitioned: the force vector set before the region stays resident on every rank)
+            if e2e:   # H2D of this step's forces from pinned host memory
+                if self.partitioned:
+                    sim.set_external_forces_owned_ptr(self.f_pinned.data_ptr())
+                else:
+                    sim.set_external_forces_ptr(self.f_pinned.data_ptr())
+            elif not self.partitioned:
+                sim.set_external_forces_dev(self.f_dev.data_ptr())   # resident in HBM
             sim.do_timestep()
-            if e2e:
-                sim.get_state_ptr(q_pinned.data_ptr())                # D2H of the displacement vector
-            iters.append(sim.last_cg_iterations)
+            if e2e:   # D2H of the displacement vector
+                if self.partitioned:
+                    sim.get_state_owned_ptr(self.q_pinned.data_ptr())
+                else:
+                    sim.get_state_ptr(self.q_pinned.data_ptr())
+            iters.append(int(sim.last_cg_iterations))
             t_asm += sim.assembly_time(); t_solve += sim.solve_time()
         sec = sim.timer_stop()
-        barrier()
+        self.env.barrier()
         return sec, iters, t_asm, t_solve
 
-    # warm-up (from rest), then K timed steps resident, then state reset and the same K steps end to end
-    sim.reset_to_rest()
+    def owned_q(self):
+        return self.sim.get_state_owned()[0]
+
+
+def make_sim(env, v, t, fixed, partitioned, comm_id=None):
+    fb = env.fb
     if partitioned:
-        sim.set_external_forces(f)
-    _, it_warm, _, _ = timed_region(args.warmup, False)
+        return fb.Simulation(v, t, fixed, partition=(env.rank, env.world, comm_id), device=env.local)
+    return fb.Simulation(v, t, fixed, device=env.local)
+
+
+def measure_mesh(env, nx, steps, warmup, partitioned, full=True, want_parity=False):
+    """The whole measurement of one cube on the job's GPUs.  Returns (line-dict on rank 0 or None, extras)."""
+    world, rank = env.world, env.rank
+    t0 = time.perf_counter()
+    v, t, fixed, f = workload(nx)
+    t_mesh = time.perf_counter() - t0
+    nT, r = len(t), 3 * len(v)
+    comm_id = env.comm_id() if partitioned else None
+    env.barrier()
+    t0 = time.perf_counter()
+    sim = make_sim(env, v, t, fixed, partitioned, comm_id)
+    env.barrier()
+    t_setup = time.perf_counter() - t0
+    st = Stepper(env, sim, f, partitioned, t)
+
+    sim.reset_to_rest()
+    _, it_warm, _, _ = st.region(warmup, False)
     sim.set_profiling(True)
     l0 = sim.kernel_launches
-    with ClockSampler(local) as clk:
-        sec, iters, t_asm, t_solve = timed_region(args.steps, False)
+    with ClockSampler(env.local) as clk:
+        sec, iters, t_asm, t_solve = st.region(steps, False)
     launches = sim.kernel_launches - l0
     spmv_mean, spmv_samples, spmv_bytes = sim.spmv_profile()
     sim.set_profiling(False)
-    q_end = sim.get_state()[0]
+    q_end_owned = st.owned_q()
+    traj = None
+    if want_parity and partitioned:
+        from tests import dist_parity
+        traj = (it_warm + iters, dist_parity.global_state(sim, r)[0])
 
-    sim.reset_to_rest()
-    timed_region(args.warmup, True)
-    sec_e2e, iters_e2e, _, _ = timed_region(args.steps, True)
-    assert iters_e2e == iters, "e2e arm must do the same work as the resident arm"
-    assert np.array_equal(q_pinned.numpy(), q_end), "e2e arm must end in the same state"
+    e2e = None
+    if full:
+        sim.reset_to_rest()
+        st.region(warmup, True)
+        sec_e2e, iters_e2e, _, _ = st.region(steps, True)
+        same_work = iters_e2e == iters
+        same_state = bool(np.array_equal(st.q_pinned.numpy(), q_end_owned))
+        if world == 1:
+            assert same_work, "e2e arm must do the same work as the resident arm"
+            assert same_state, "e2e arm must end in the same state"
+        e2e = (sec_e2e, same_work, same_state)
 
-    # isolated kernel timings on the final matrices (back to back, matrix >> L2)
-    t_spmv_iso = sim.bench_spmv(50)
-    t_iter_iso = sim.bench_cg_iteration(60) if not partitioned else float("nan")
-    t_asm_iso = sim.bench_assembly(5)
+    iso = None
+    if full:
+        # isolated kernel timings on the final matrices (back to back, matrix >> L2)
+        t_spmv_iso = sim.bench_spmv(50)
+        t_iter_iso = sim.bench_cg_iteration(60) if not partitioned else float("nan")
+        t_asm_iso = sim.bench_assembly(5)
+        iso = (t_spmv_iso, t_iter_iso, t_asm_iso)
 
-    # max over ranks
-    if world > 1:
-        tt = torch.tensor([sec, sec_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        sec, sec_e2e = float(tt[0]), float(tt[1])
-        ll = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(ll)
-        launches = int(ll[0])
+    sec, = env.max_over_ranks(sec)
+    if e2e:
+        e2e = (env.max_over_ranks(e2e[0])[0],) + e2e[1:]
+    launches = env.sum_over_ranks(launches)
+    dev_bytes = sim.device_bytes
+    nnz_local, peer = sim.nnz_K, (bool(sim.peer_memory) if partitioned else None)
+    nnz = env.sum_over_ranks(nnz_local) if partitioned else nnz_local  # (cut rows are counted on both sides: an upper bound)
 
+    out = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        nnz = sim.nnz_K
-        rows = r
-        units = 1 if partitioned else world  # partitioned: one mesh; otherwise independent meshes stepped concurrently
-        value = units * args.steps / sec
-        e2e_value = units * args.steps / sec_e2e
-        achieved = spmv_bytes / spmv_mean / 1e9 if spmv_mean > 0 else None
+        rows_local = sim.local_r
+        units = 1 if (partitioned or world == 1) else world
         mean_it = float(np.mean(iters))
-        # one PCG iteration moves B_spmv + 72 B/row beyond the SpMV (SURVEY §8d), own-format bytes
-        b_iter = spmv_bytes + 72.0 * rows
+        achieved = spmv_bytes / spmv_mean / 1e9 if spmv_mean > 0 else None
+        b_iter = spmv_bytes + 72.0 * rows_local   # one PCG iteration moves B_spmv + 72 B/row beyond the SpMV (SURVEY §8d), own-format bytes
         refresh = sum(i // 30 for i in iters)
         solve_bytes = sum(iters) * b_iter + refresh * spmv_bytes
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "strong" if partitioned else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(nx, nT, world, partitioned),
-            "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * r, "d2h_bytes_per_step": 8 * r,
-                    "ms_per_step": 1e3 * sec_e2e / args.steps},
-            "gpu_launches": launches,
+        out = {
+            "value": units * steps / sec, "ms_per_step": 1e3 * sec / steps,
+            "cg_iterations_per_step": iters, "cg_iterations_warmup": it_warm, "mean_iterations": mean_it,
+            "ms_per_cg_iteration": 1e3 * sec / max(sum(iters), 1),
+            "assembly_mtets_per_s": units * nT * steps / t_asm / 1e6 if t_asm > 0 else None,
+            "assembly_share_of_step": t_asm / sec, "solve_share_of_step": t_solve / sec,
+            "setup_seconds": t_setup, "mesh_generation_seconds": t_mesh, "device_bytes_rank0": dev_bytes, "nnz_K": nnz, "tets": nT,
+            "gpu_launches": launches, "clocks": clk.summary(), "peer_memory": peer,
             "roofline": {
-                "kernel": "k_spmv_rows3<1> (q = Keff d fused with d.q), CUDA-event pairs around every 16th PCG iteration's launch inside the timed steps",
+                "kernel": "k_spmv_rows3<1> (q = Keff d fused with d.q), CUDA-event pairs around every 16th PCG iteration's launch inside the timed steps"
+                          + (" (rank 0's rows; includes the wait for the neighbours' halo)" if partitioned else ""),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(nx),
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_table(nx, "spmv_bytes_per_launch") if not partitioned else None,
                 "algorithmic_bytes_per_launch": spmv_bytes, "mean_launch_seconds": spmv_mean, "samples": spmv_samples,
                 "bytes_model": "8 B/nnz values + 4 B per 3x3 block column + 52 B per block row (rowptr, x read, y write)",
-                "reference_layout_equiv_gbs": ((12.0 * nnz + 20.0 * rows) / spmv_mean / 1e9) if spmv_mean > 0 else None,
-                "isolated_spmv_gbs": spmv_bytes / t_spmv_iso / 1e9,
+                "reference_layout_equiv_gbs": ((12.0 * nnz_local + 20.0 * rows_local) / spmv_mean / 1e9) if spmv_mean > 0 else None,
                 "pcg_iteration_gbs_in_step": solve_bytes / t_solve / 1e9 if t_solve > 0 else None,
-                "pcg_iteration_gbs_isolated": b_iter / t_iter_iso / 1e9,
+                "pcg_iteration_frac_in_step": solve_bytes / t_solve / 1e9 / peak if t_solve > 0 else None,
             },
-            "cg_iterations_per_step": iters, "cg_iterations_warmup": it_warm,
-            "assembly_mtets_per_s": units * nT * args.steps / t_asm / 1e6 if t_asm > 0 else None,
-            "assembly_mtets_per_s_isolated": nT / t_asm_iso / 1e6,
-            "assembly_share_of_step": t_asm / sec, "solve_share_of_step": t_solve / sec,
+        }
+        if e2e:
+            out["e2e"] = {"value": units * steps / e2e[0], "unit": UNIT, "h2d_bytes_per_step": env.world * st.h2d if partitioned else st.h2d * units,
+                          "d2h_bytes_per_step": env.world * st.d2h if partitioned else st.d2h * units, "ms_per_step": 1e3 * e2e[0] / steps,
+                          "same_iterations_as_resident": e2e[1], "same_final_state_as_resident": e2e[2],
+                          "api": ("fb_set_external_forces_owned / fb_step / fb_get_state_owned per rank (each rank moves its own rows)" if partitioned
+                                  else "fb_set_external_forces / fb_step / fb_get_state")}
+        if iso:
+            out["roofline"]["isolated_spmv_gbs"] = spmv_bytes / iso[0] / 1e9
+            if iso[1] == iso[1]:
+                out["roofline"]["pcg_iteration_gbs_isolated"] = b_iter / iso[1] / 1e9
+            comp = 16.0 * nT + 72.0 * (r / 3) + 8.0 * nnz
             # SURVEY §8d: compulsory bytes of one assembly = tet ids + x0, u read, f write + K values written; the kernels are
             # bound by the FP64 pipe (no-FMA arithmetic, bit-identical to the reference), not by these bytes
-            "assembly": {"compulsory_bytes": 16.0 * nT + 72.0 * (rows / 3) + 8.0 * nnz,
-                         "compulsory_gbs": (16.0 * nT + 72.0 * (rows / 3) + 8.0 * nnz) / t_asm_iso / 1e9,
-                         "seconds_isolated": t_asm_iso, "ncu": ncu_assembly(nx)},
-            "setup_seconds": t_setup, "device_bytes": sim.device_bytes, "nnz_K": nnz, "tets": nT,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                cb = cpu_reference_sample(nx, args.cpu_cg_iters, int(round(mean_it)), 1, 0)
-                line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
-                                        "assembly_mtets_per_s": cb["assembly_mtets_per_s"],
-                                        "seconds_per_cg_iteration": cb["seconds_per_cg_iteration"]}
-            except Exception as e:  # the checker is optional plumbing for the bench
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
-        args.emit(line)
+            share = world if partitioned else 1   # a partitioned rank assembles its own rows: ~1/world of the mesh per GPU
+            out["assembly"] = {"compulsory_bytes": comp, "compulsory_gbs_per_gpu": comp / share / iso[2] / 1e9,
+                               "seconds_isolated": iso[2], "mtets_per_s_isolated": nT / iso[2] / 1e6,
+                               "ncu": ncu_table(nx, "assembly")}
+    return out, sim, traj, (v, t, fixed, f)
+
+
+# ------------------------------------------------------------------------------------------------------
+def batch_block(env, per_gpu, steps, warmup, nx=33):
+    """BASELINE.json configs[3]: independent meshes, `per_gpu` of them per GPU in ONE batch context per GPU
+    (fb_create_batch: block-diagonal system, PCG scalars and stopping rule per mesh), no communication."""
+    torch, fb = env.torch, env.fb
+    v, t, fixed, _ = workload(nx)
+    nT, r = len(t), 3 * len(v)
+    total = per_gpu * env.world
+    corner = 3 * (len(v) - 1)
+    forces = []
+    for k in range(per_gpu):   # same mesh, load direction rotated about y with the mesh index (SURVEY.md §8d)
+        m = env.rank * per_gpu + k
+        ang = 2.0 * np.pi * m / max(total, 1)
+        f = np.zeros(r)
+        f[corner], f[corner + 2] = 1e4 * np.cos(ang), 1e4 * np.sin(ang)
+        forces.append(f)
+    t0 = time.perf_counter()
+    sim = fb.Simulation(batch=[(v, t, fixed)] * per_gpu, device=env.local)
+    t_setup = time.perf_counter() - t0
+    f_all = np.concatenate(forces)
+    f_dev = torch.from_numpy(f_all).cuda()
+    f_pin = torch.from_numpy(f_all).pin_memory()
+    q_pin = torch.empty_like(f_pin).pin_memory()
+
+    def region(n, e2e):
+        env.barrier()
+        sim.timer_start()
+        for _ in range(n):
+            if e2e:
+                sim.set_external_forces_ptr(f_pin.data_ptr())
+            else:
+                sim.set_external_forces_dev(f_dev.data_ptr())
+            sim.do_timestep()
+            if e2e:
+                sim.get_state_ptr(q_pin.data_ptr())
+        sec = sim.timer_stop()
+        env.barrier()
+        return env.max_over_ranks(sec)[0]
+
+    region(warmup, False)
+    sim.set_profiling(True)
+    sec = region(steps, False)
+    m_s, n_s, b_s = sim.spmv_profile()
+    sim.set_profiling(False)
+    its = [int(x) for x in sim.batch_cg_iterations()[0][:4]]
+    sim.reset_to_rest()
+    region(warmup, True)
+    sec_e2e = region(steps, True)
     sim.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    if env.rank != 0:
+        return None
+    peak, _ = measured_peak_gbs()
+    return {"workload": f"{total} independent meshes of CreateTruthCube({nx}) = {nT} tets each, {per_gpu} per GPU in one batch context per GPU, "
+                        f"load direction rotated per mesh, no communication" + (" [BASELINE.json configs[3]: 256 meshes over 8 GPUs]" if total == 256 else ""),
+            "metric": "fem_mesh_steps_per_s", "value": total * steps / sec, "unit": "mesh-steps/s", "steps": steps, "warmup": warmup,
+            "ms_per_batch_step": 1e3 * sec / steps, "mtets_steps_per_s": total * steps / sec * nT / 1e6,
+            "e2e": {"value": total * steps / sec_e2e, "unit": "mesh-steps/s", "h2d_bytes_per_step": 8 * r * total, "d2h_bytes_per_step": 8 * r * total},
+            "cg_iterations_last_step_first_meshes": its, "setup_seconds": t_setup,
+            "roofline": {"kernel": "kb_spmv<1> (all meshes of the context that still iterate), event pairs in step, rank 0", "bound": "hbm",
+                         "achieved": b_s / m_s / 1e9 if m_s > 0 else None, "peak": peak, "unit": "GB/s",
+                         "frac": b_s / m_s / 1e9 / peak if m_s > 0 else None, "samples": n_s, "traffic": ncu_table(f"batch{per_gpu}x{nx}", "spmv_bytes_per_launch")}}
+
+
+def run_ours(args):
+    env = Env()
+    world, rank = env.world, env.rank
+    partitioned = world > 1 and not args.replicas
+    nx = args.nx
+    blocks_ok = True
+    main, sim, traj, mesh = measure_mesh(env, nx, args.steps, args.warmup, partitioned, full=True,
+                                         want_parity=partitioned and not args.no_parity)
+    v, t, fixed, f = mesh
+    nT, r = len(t), 3 * len(v)
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak" if (world > 1 and not partitioned) else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(nx, nT, world, partitioned),
+            "solver": "jacobi_pcg (the reference's algorithm; parity path)",
+        }
+        for k in ("clocks", "e2e", "gpu_launches", "roofline", "cg_iterations_per_step", "cg_iterations_warmup", "ms_per_cg_iteration",
+                  "assembly_mtets_per_s", "assembly_share_of_step", "solve_share_of_step", "assembly", "setup_seconds",
+                  "mesh_generation_seconds", "device_bytes_rank0", "nnz_K", "tets", "peer_memory"):
+            if k in main:
+                line[k] = main[k]
+        line["target"] = {"steps_per_s_at_10M_tets_1gpu": 30.0, "note": "north_star target; Jacobi-PCG needs ~950 iterations x 2.5 GB per step on this mesh (>= 0.36 s at the HBM roofline)"}
+
+    # ---- multi-GPU parity inside the driver-run command --------------------------------------------------------------
+    if partitioned and not args.no_parity:
+        from tests import dist_parity
+        ref = None
+        try:
+            if rank == 0:
+                ref = make_sim(env, v, t, fixed, False)
+                ref.set_external_forces(f)
+            res = dist_parity.partition_parity(sim, ref, rank, world, r, traj_part=traj, log=log)
+            blocks_ok &= bool(res["ok"])
+            if rank == 0:
+                res["mesh"] = f"the bench mesh itself (nx={nx}, {nT} tets); trajectory = the {args.warmup}+{args.steps} resident steps of this run"
+                line["parity_check"] = res
+        finally:
+            if ref is not None:
+                ref.close()
+    sim.close()
+    env.fb.trim_memory()
+
+    def guarded(name, fn):
+        """Auxiliary blocks never take the headline down: an exception becomes {"error": ...} (all ranks must agree to go on)."""
+        try:
+            out = fn()
+            ok = 1
+        except Exception as e:  # noqa: BLE001
+            out, ok = {"error": f"{type(e).__name__}: {e}"[:400]}, 0
+        if world > 1:
+            tt = env.torch.tensor([ok], device="cuda")
+            env.dist.all_reduce(tt, op=env.dist.ReduceOp.MIN)
+            ok = int(tt[0])
+        if rank == 0 and out is not None:
+            line[name] = out
+        env.fb.trim_memory()
+        return ok
+
+    # ---- configs[4]: 50M tets on the same GPUs -------------------------------------------------------------------------
+    if not args.no_50m:
+        def block50():
+            m, s50, _, _ = measure_mesh(env, args.nx50, args.steps50, args.warmup50, world > 1, full=False)
+            s50.close()
+            if m is None:
+                return None
+            keep = ("value", "ms_per_step", "cg_iterations_per_step", "cg_iterations_warmup", "ms_per_cg_iteration", "assembly_mtets_per_s",
+                    "setup_seconds", "mesh_generation_seconds", "device_bytes_rank0", "tets", "peer_memory", "gpu_launches", "roofline")
+            out = {k: m[k] for k in keep if k in m}
+            out.update({"workload": config_dict(args.nx50, m["tets"], world, world > 1)["workload"], "unit": UNIT, "steps": args.steps50,
+                        "warmup": args.warmup50, "parallelism": config_dict(args.nx50, m["tets"], world, world > 1)["parallelism"]})
+            return out
+        guarded("config5_50M", block50)
+
+    # ---- configs[3]: batch of independent meshes, 32 per GPU -------------------------------------------------------------
+    if not args.no_batch:
+        guarded("config4_batch", lambda: batch_block(env, args.batch_per_gpu, args.steps_batch, args.warmup_batch))
+
+    # ---- configs[1] and the CPU baseline, single GPU only ------------------------------------------------------------------
+    if world == 1 and not args.no_1m and nx != 56:
+        def block1m():
+            m, s1, _, _ = measure_mesh(env, 56, 10, 3, False, full=True)
+            s1.close()
+            keep = ("value", "ms_per_step", "e2e", "cg_iterations_per_step", "ms_per_cg_iteration", "assembly_mtets_per_s", "setup_seconds", "tets",
+                    "roofline", "assembly")
+            out = {k: m[k] for k in keep if k in m}
+            out.update({"workload": config_dict(56, m["tets"], 1, False)["workload"], "unit": UNIT, "steps": 10, "warmup": 3})
+            return out
+        guarded("config2_1M", block1m)
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_sample(nx, nT, main["nnz_K"], float(np.mean(main["cg_iterations_per_step"])), args.cpu_nx)
+        except Exception as e:  # noqa: BLE001 — the checker is optional plumbing for the bench
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
+
+    if rank == 0:
+        args.emit(line)
+    env.close()
+    return 0 if blocks_ok else 3
 
 
 # ------------------------------------------------------------------------------------------------------
 def run_batch(args):
-    """BASELINE.json configs[3]: a batch of independent meshes spread over the GPUs, no communication.  Every rank owns
-    batch/world contexts (each with its own CUDA stream) and drives them from `--streams` host threads, so the launch gaps
-    of one small mesh are filled by the kernels of another."""
-    import torch
-    import torch.distributed as dist
-
-    import fembrain_b200 as fb
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the CUDA library has no fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nx = args.nx
-    v, t, fixed, f0 = workload(nx)
-    nT, r = len(t), 3 * len(v)
-    mine = [m for m in range(args.batch) if m % world == rank]
-    if args.group < 0:
-        args.group = max(1, len(mine))
-    sims, forces = [], []
-    corner = 3 * (len(v) - 1)
-    for m in mine:  # same mesh, load direction rotated about y with the mesh index (SURVEY.md §8d)
-        ang = 2.0 * np.pi * m / max(args.batch, 1)
-        f = np.zeros(r)
-        f[corner], f[corner + 2] = 1e4 * np.cos(ang), 1e4 * np.sin(ang)
-        if args.group > 0:
-            forces.append(f)
-        else:
-            sims.append(fb.Simulation(v, t, fixed, device=local))
-            forces.append(torch.from_numpy(f).cuda())
-    if args.group > 0:
-        # fb_create_batch: `group` meshes per context as one block-diagonal system, PCG scalars and stopping rule per mesh
-        grouped = []
-        for g0 in range(0, len(mine), args.group):
-            n = min(args.group, len(mine) - g0)
-            sims.append(fb.Simulation(batch=[(v, t, fixed)] * n, device=local))
-            grouped.append(torch.from_numpy(np.concatenate(forces[g0:g0 + n])).cuda())
-        forces = grouped
-    # end-to-end arm: the same forces from pinned host memory every step, every mesh's displacements read back
-    f_pinned = [x.cpu().pin_memory() for x in forces]
-    q_pinned = [torch.empty_like(x) for x in f_pinned]
-    q_pinned = [x.pin_memory() for x in q_pinned]
-    torch.cuda.synchronize()
-    nthreads = max(1, min(args.streams, len(sims)))
-    iters = [[] for _ in sims]
-
-    def worker(tid, nsteps, record, e2e):
-        for _ in range(nsteps):
-            for k in range(tid, len(sims), nthreads):
-                if e2e:
-                    sims[k].set_external_forces_ptr(f_pinned[k].data_ptr())
-                else:
-                    sims[k].set_external_forces_dev(forces[k].data_ptr())
-                sims[k].do_timestep()
-                if e2e:
-                    sims[k].get_state_ptr(q_pinned[k].data_ptr())
-                if record:
-                    iters[k].append(int(sims[k].batch_cg_iterations()[0][0]) if args.group > 0 else sims[k].last_cg_iterations)
-
-    def region(nsteps, record, e2e=False):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=worker, args=(i, nsteps, record, e2e)) for i in range(nthreads)]
-        [x.start() for x in th]
-        [x.join() for x in th]
-        torch.cuda.synchronize()
-        sec = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            sec = float(tt[0])
-        return sec
-
-    region(args.warmup, False)
-    l0 = sum(s_.kernel_launches for s_ in sims)
-    for s_ in sims:
-        s_.set_profiling(True)
-    with ClockSampler(local) as clk:
-        sec = region(args.steps, True)
-    launches = sum(s_.kernel_launches for s_ in sims) - l0
-    prof = [s_.spmv_profile() for s_ in sims]
-    for s_ in sims:
-        s_.set_profiling(False)
-    # the same steps end to end: state back to rest, warm-up, K timed steps with host buffers
-    for s_ in sims:
-        s_.reset_to_rest()
-    region(args.warmup, False, True)
-    sec_e2e = region(args.steps, False, True)
-    if world > 1:
-        ll = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(ll)
-        launches = int(ll[0])
-    if rank == 0:
-        value = args.batch * args.steps / sec
-        cfg = config_dict(nx, nT, world, False)
-        cfg["workload"] = f"batch of {args.batch} independent meshes, each " + cfg["workload"] + " (load direction rotated per mesh)"
-        cfg["parallelism"] = f"{args.batch // world} meshes per GPU on {nthreads} host threads/streams, no communication"
-        if args.group > 0:
-            cfg["parallelism"] = (f"{args.batch // world} meshes per GPU in batch contexts of {args.group} (fb_create_batch: block-diagonal "
-                                  f"system, PCG scalars and stopping rule per mesh), {nthreads} host threads/streams, no communication")
-        cfg["timing"] = "host wall clock between device synchronisations (many streams), max over ranks"
-        h2d = sum(x.numel() * 8 for x in f_pinned)
-        line = {
-            "metric": "fem_mesh_steps_per_s", "value": value, "unit": "mesh-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clk.summary(),
-            "e2e": {"value": args.batch * args.steps / sec_e2e, "unit": "mesh-steps/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": h2d * world, "ms_per_step": 1e3 * sec_e2e / args.steps},
-            "mtets_steps_per_s": value * nT / 1e6, "gpu_launches": launches,
-            "cg_iterations_per_step_mesh0": iters[0] if iters else [],
-        }
-        tot_s = sum(m * n for m, n, _ in prof)
-        tot_n = sum(n for _, n, _ in prof)
-        if tot_n > 0:
-            peak, peak_src = measured_peak_gbs()
-            mean_s, bytes_launch = tot_s / tot_n, float(np.mean([b for _, _, b in prof]))
-            kern = "kb_spmv<1> (q = Keff d + per-mesh d.q over all meshes of a batch context)" if args.group > 0 else "k_spmv_rows3<1>"
-            line["roofline"] = {
-                "kernel": kern + ", CUDA-event pairs around every 16th PCG iteration's launch inside the timed steps (rank 0)",
-                "bound": "hbm", "achieved": bytes_launch / mean_s / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": bytes_launch / mean_s / 1e9 / peak, "traffic": ncu_traffic(f"batch{args.group}x{nx}") if args.group > 0 else None,
-                "algorithmic_bytes_per_launch": bytes_launch, "mean_launch_seconds": mean_s, "samples": tot_n,
-                "bytes_model": "per context: 8 B/nnz values + 4 B per 3x3 block column + 52 B per block row, all meshes iterating",
-                "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this kernel; null when none exists for this batch shape)",
-            }
+    """--batch B: BASELINE.json configs[3] as the headline line (B independent meshes spread over the GPUs)."""
+    env = Env()
+    per = max(1, args.batch // env.world)
+    with ClockSampler(env.local) as clk:
+        blk = batch_block(env, per, args.steps, args.warmup, nx=args.nx if args.nx != 120 else 33)
+    if env.rank == 0:
+        line = {"metric": blk["metric"], "value": blk["value"], "unit": blk["unit"], "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": blk["ms_per_batch_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": blk["workload"], "parallelism": "one batch context per GPU, no communication"},
+                "clocks": clk.summary(), "e2e": blk["e2e"], "roofline": blk["roofline"], "mtets_steps_per_s": blk["mtets_steps_per_s"],
+                "cg_iterations_last_step_first_meshes": blk["cg_iterations_last_step_first_meshes"]}
         args.emit(line)
-    for s_ in sims:
-        s_.close()
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
     return 0
 
 
@@ -537,15 +681,26 @@ def _main(saved_stdout):
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nx", type=int, default=56, help="cube resolution: 56 = configs[1] (1M tets), 120 = configs[2] (10M tets)")
-    ap.add_argument("--cpu-cg-iters", type=int, default=40, help="PCG iterations in the bounded CPU sample")
+    ap.add_argument("--nx", type=int, default=120, help="cube resolution of the headline line: 120 = configs[2] (10.1M tets), 56 = configs[1] (1M tets)")
+    ap.add_argument("--replicas", action="store_true", help="N>1: every rank steps its own copy of the mesh (weak scaling, no communication) instead of ONE partitioned mesh")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the built-in parity check of the partitioned path")
+    ap.add_argument("--no-50m", action="store_true")
+    ap.add_argument("--nx50", type=int, default=204, help="cube resolution of the config5_50M block (204 = 50,192,562 tets)")
+    ap.add_argument("--steps50", type=int, default=3)
+    ap.add_argument("--warmup50", type=int, default=1)
+    ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--batch-per-gpu", type=int, default=32)
+    ap.add_argument("--steps-batch", type=int, default=3)
+    ap.add_argument("--warmup-batch", type=int, default=1)
+    ap.add_argument("--no-1m", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=0, help="configs[3]: step a batch of this many independent meshes (use with --nx 33)")
-    ap.add_argument("--streams", type=int, default=8, help="host threads / concurrent contexts per GPU in --batch mode (B200, 32 meshes of 196,608 tets on one GPU: 75.2 / 81.1 / 79.7 mesh-steps/s with 4 / 8 / 16)")
-    ap.add_argument("--group", type=int, default=-1, help="--batch mode: meshes per batch context (fb_create_batch: one block-diagonal system, PCG scalars and stopping rule per mesh); -1 = all meshes of the rank in one context (B200, 32 meshes of 196,608 tets: 109 mesh-steps/s), 0 = one context per mesh on --streams host threads (79.6)")
-    ap.add_argument("--partitioned", action="store_true",
-                    help="N>1: split ONE mesh by row blocks across the ranks (NCCL halo exchange, strong scaling) instead of one mesh per rank")
+    ap.add_argument("--cpu-nx", type=int, default=40, help="cube resolution of the bounded cpu_baseline sample (40 = 355,914 tets)")
+    ap.add_argument("--ref-budget-s", type=float, default=780.0, help="--impl reference: wall-clock budget for the whole run")
+    ap.add_argument("--batch", type=int, default=0, help="headline = configs[3]: a batch of this many independent meshes (nx 33)")
+    ap.add_argument("--quick", action="store_true", help="headline mesh only (no 50M / batch / 1M / cpu blocks)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_50m = args.no_batch = args.no_1m = args.no_cpu_baseline = True
     if args.warmup < 3 and args.impl == "ours":
         print("note: timing rules ask for >= 3 warm-up steps", file=sys.stderr)
     args.emit = lambda line: emit(saved_stdout, line)

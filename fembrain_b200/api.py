@@ -78,7 +78,7 @@ def load_library():
         "fb_destroy": (None, [vp]),
         "fb_set_fixed_vertices": (ci, [vp, ci, vp]),
         "fb_num_vertices": (ci, [vp]), "fb_num_tets": (ci, [vp]), "fb_num_dofs": (ci, [vp]),
-        "fb_num_constrained_dofs": (ci, [vp]),
+        "fb_num_constrained_dofs": (ci, [vp]), "fb_num_local_dofs": (ci, [vp]),
         "fb_nnz_stiffness": (ll, [vp]), "fb_nnz_mass": (ll, [vp]), "fb_nnz_system": (ll, [vp]),
         "fb_set_external_forces": (ci, [vp, vp]), "fb_add_external_forces": (ci, [vp, vp]),
         "fb_set_external_forces_to_zero": (ci, [vp]), "fb_get_external_forces": (ci, [vp, vp]),
@@ -126,6 +126,8 @@ def load_library():
         "fb_create_partitioned": (ci, [pp, ci, vp, ci, vp, ci, vp, prm, ci, ci, vp]),
         "fb_partition_range": (ci, [vp, C.POINTER(ci), C.POINTER(ci)]),
         "fb_partition_peer_memory": (ci, [vp]),
+        "fb_partition_local_range": (ci, [vp, C.POINTER(ci), C.POINTER(ci)]), "fb_partition_local_to_global": (ci, [vp, vp]),
+        "fb_set_external_forces_owned": (ci, [vp, vp]), "fb_get_state_owned": (ci, [vp, vp, vp, vp]),
         "fb_plan_partition": (ci, [ci, ci, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -340,6 +342,18 @@ class Simulation:
         self._check(self._lib.fb_partition_range(self._h, C.byref(b), C.byref(e)), "fb_partition_range")
         return b.value, e.value
 
+    def local_range(self):
+        """Local vertices [lo, hi) of the inspection hooks' system that this rank owns (all of them on an ordinary context)."""
+        b, e = C.c_int(0), C.c_int(0)
+        self._check(self._lib.fb_partition_local_range(self._h, C.byref(b), C.byref(e)), "fb_partition_local_range")
+        return b.value, e.value
+
+    def local_to_global(self):
+        """Caller's vertex id of every local vertex (identity on an ordinary context)."""
+        l2g = np.zeros(max(self.local_r // 3, 1), np.int32)
+        self._check(self._lib.fb_partition_local_to_global(self._h, _ptr(l2g)), "fb_partition_local_to_global")
+        return l2g[: self.local_r // 3]
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.fb_destroy(self._h)
@@ -380,7 +394,7 @@ class Simulation:
 
     @property
     def rows_sys(self):
-        return self.r - self.num_constrained
+        return self.local_r - self.num_constrained
 
     # -- forces / state ------------------------------------------------------------------------------------
     def set_external_forces(self, f):
@@ -520,9 +534,20 @@ class Simulation:
 
     # -- inspection ---------------------------------------------------------------------------------------------
     def K_csr(self, values=False):
-        ia, ja = np.zeros(self.r + 1, np.int32), np.zeros(self.nnz_K, np.int32)
+        ia, ja = np.zeros(self.local_r + 1, np.int32), np.zeros(self.nnz_K, np.int32)
         self._check(self._lib.fb_get_stiffness_csr(self._h, _ptr(ia), _ptr(ja)), "fb_get_stiffness_csr")
         return ia, ja, None
+
+    def K_row_pointers(self):
+        """ia only (row pointers of K in the reference's CSR layout) — no nnz-sized column array."""
+        ia = np.zeros(self.local_r + 1, np.int32)
+        self._check(self._lib.fb_get_stiffness_csr(self._h, _ptr(ia), None), "fb_get_stiffness_csr")
+        return ia
+
+    @property
+    def local_r(self):
+        """DOFs of the LOCAL system the inspection hooks describe (= r except on a partitioned context)."""
+        return int(self._lib.fb_num_local_dofs(self._h))
 
     def M_csr(self):
         n = self.nnz_M
@@ -579,6 +604,14 @@ class Simulation:
         self._check(self._lib.fb_get_rhs(self._h, _ptr(b)), "fb_get_rhs")
         return b
 
+    def rhs_full(self):
+        """The last step's right-hand side expanded to the LOCAL DOF numbering (zeros at constrained DOFs; InsertRows)."""
+        full = np.zeros(self.local_r)
+        keep = np.ones(self.local_r, bool)
+        keep[self.constrained_dofs()] = False
+        full[keep] = self.rhs()
+        return full
+
     def internal_forces(self):
         f = np.zeros(self.r)
         self._check(self._lib.fb_get_internal_forces(self._h, _ptr(f)), "fb_get_internal_forces")
@@ -629,6 +662,21 @@ class Simulation:
     def set_external_forces_ptr(self, host_ptr: int):
         """SetExternalForces from a caller-owned host buffer (e.g. pinned memory), no numpy copy."""
         self._check(self._lib.fb_set_external_forces(self._h, C.c_void_p(host_ptr)), "fb_set_external_forces")
+
+    def set_external_forces_owned_ptr(self, host_ptr: int):
+        """fb_set_external_forces_owned from a caller-owned host buffer holding this rank's rows only."""
+        self._check(self._lib.fb_set_external_forces_owned(self._h, C.c_void_p(host_ptr)), "fb_set_external_forces_owned")
+
+    def get_state_owned_ptr(self, q_ptr=None, qvel_ptr=None, qaccel_ptr=None):
+        self._check(self._lib.fb_get_state_owned(self._h, C.c_void_p(q_ptr) if q_ptr else None, C.c_void_p(qvel_ptr) if qvel_ptr else None,
+                                                 C.c_void_p(qaccel_ptr) if qaccel_ptr else None), "fb_get_state_owned")
+
+    def get_state_owned(self):
+        """(q, qvel) of this rank's rows [partition_range) — the whole vectors on an ordinary context."""
+        b, e = self.partition_range()
+        q, qv = np.zeros(3 * (e - b)), np.zeros(3 * (e - b))
+        self._check(self._lib.fb_get_state_owned(self._h, _ptr(q), _ptr(qv), None), "fb_get_state_owned")
+        return q, qv
 
     def get_state_ptr(self, q_ptr=None, qvel_ptr=None, qaccel_ptr=None):
         self._check(self._lib.fb_get_state(self._h, C.c_void_p(q_ptr) if q_ptr else None, C.c_void_p(qvel_ptr) if qvel_ptr else None,

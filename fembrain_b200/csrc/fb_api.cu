@@ -194,7 +194,8 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
     fb_set_error("bad mesh arguments (nV=%d, nT=%d)", nV, nT);
     return FB_ERR_INVALID_ARGUMENT;
   }
-  if ((long long)nT * 16 > 0xffffffffll || (long long)nV * 3 > 0x7fffffffll) {
+  // contribution offsets (seg, incidence prefix sums) are 32-bit signed: 16 nT must fit (same bound as fb_create_batch)
+  if ((long long)nT * 16 > 0x7fffffffll || (long long)nV * 3 > 0x7fffffffll) {
     fb_set_error("mesh too large for 32-bit element/DOF ids; partition it");
     return FB_ERR_INVALID_ARGUMENT;
   }
@@ -444,6 +445,7 @@ int fb_num_dofs(const fb_context *c) {
   return c ? c->r : 0;
 }
 int fb_num_constrained_dofs(const fb_context *c) { return c ? c->nC : 0; }
+int fb_num_local_dofs(const fb_context *c) { return c ? c->r : 0; }
 long long fb_nnz_stiffness(const fb_context *c) { return c ? c->nnzK : 0; }
 long long fb_nnz_mass(const fb_context *c) { return c ? 3ll * c->nB : 0; }
 

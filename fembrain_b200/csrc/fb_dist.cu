@@ -112,7 +112,7 @@ __global__ void k_halo_push(HaloPushArgs h, FbPeerArgs pa, const int *__restrict
     *ticket = 0u;
     __threadfence_system();
     for (int j = 0; j < h.nNbr; j++)
-      ((volatile unsigned long long *)pa.comm[h.nbrRank[j]])[FB_COMM_FLAG(FB_COMM_HALO, pa.rank)] = pa.epoch;
+      ((volatile unsigned long long *)pa.comm[h.nbrRank[j]])[FB_COMM_FLAG(pa.parity, FB_COMM_HALO, pa.rank)] = pa.epoch;
   }
 }
 
@@ -315,6 +315,7 @@ void fb_dist_peer_args(fb_context *c, FbPeerArgs *pa) {
   pa->enabled = 1;
   pa->rank = d->rank;
   pa->world = d->world;
+  pa->parity = (int)(d->solveCount & 1ull);
   for (int p = 0; p < d->world; p++) pa->comm[p] = d->peerComm[p];
 }
 
@@ -324,6 +325,11 @@ unsigned long long fb_dist_epoch(fb_context *c, int it, int family) {
 
 void fb_dist_next_solve(fb_context *c) {
   if (c->dist) c->dist->solveCount++;
+}
+
+int fb_dist_reset_tickets(fb_context *c) {
+  if (c->dist && c->dist->pushTicket) FB_CUDA(cudaMemsetAsync(c->dist->pushTicket, 0, sizeof(unsigned int), c->stream));
+  return FB_OK;
 }
 
 unsigned int fb_dist_halo_mask(const fb_context *c) {
@@ -372,43 +378,53 @@ static int setup_p2p(fb_context *c) {
   if (env && atoi(env) == 0) return FB_OK;
   if (d->world < 2) return FB_OK;
   cudaStream_t st = c->stream;
-  {  // every rank takes part in this vote, so no rank can skip the collectives below on its own
-    int eligible = (d->world <= FB_MAX_RANKS && d->nNbr <= FB_MAX_NBR && c->use_rows3) ? 1 : 0, all = 0;
-    int *flag0 = nullptr;
-    FB_CUDA(cudaMalloc(&flag0, sizeof(int)));
-    FB_CUDA(cudaMemcpyAsync(flag0, &eligible, sizeof(int), cudaMemcpyHostToDevice, st));
-    ncclResult_t r0 = ncclAllReduce(flag0, flag0, 1, ncclInt, ncclMin, d->comm_nccl(), st);
-    cudaMemcpyAsync(&all, flag0, sizeof(int), cudaMemcpyDeviceToHost, st);
-    cudaStreamSynchronize(st);
-    cudaFree(flag0);
-    if (r0 != ncclSuccess || !all) return FB_OK;
-  }
-  FB_TRY(fb_dev_alloc_plain(c, &d->comm, (size_t)FB_COMM_WORDS));  // exported with CUDA IPC
-  FB_TRY(fb_dev_alloc(c, &d->pushTicket, 1));
-  FB_TRY(fb_dev_alloc(c, &d->remoteIdx, (size_t)d->sendOff[d->nNbr]));
-  FB_CUDA(cudaMemsetAsync(d->comm, 0, sizeof(double) * FB_COMM_WORDS, st));
-  FB_CUDA(cudaMemsetAsync(d->pushTicket, 0, sizeof(unsigned int), st));
-  // 1. IPC handles of (comm, dir) of every rank
+  // Every buffer the collectives below need is allocated BEFORE the first of them; after this point a rank-local failure
+  // (allocation, IPC export, mapping) only clears `ok` and every rank still runs every collective, so no rank can be left
+  // blocked inside NCCL by a peer that returned early.  The decision is taken once, from the final agreed vote.
   struct Handles { cudaIpcMemHandle_t comm, dir; };
-  Handles mine;
-  int ok = (cudaIpcGetMemHandle(&mine.comm, d->comm) == cudaSuccess) && (cudaIpcGetMemHandle(&mine.dir, c->dir) == cudaSuccess);
-  if (!ok) cudaGetLastError();
+  const int nS = d->sendOff[d->nNbr];
+  int *vote = nullptr, *remoteScratch = nullptr;
   char *devH = nullptr;
-  FB_CUDA(cudaMalloc(&devH, sizeof(Handles) * (size_t)(d->world + 1)));
-  FB_CUDA(cudaMemcpyAsync(devH + sizeof(Handles) * (size_t)d->world, &mine, sizeof(Handles), cudaMemcpyHostToDevice, st));
+  if (cudaMalloc(&vote, 2 * sizeof(int)) != cudaSuccess || cudaMalloc(&devH, sizeof(Handles) * (size_t)(d->world + 1)) != cudaSuccess ||
+      cudaMalloc(&remoteScratch, sizeof(int) * (size_t)(nS + 1)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(vote); cudaFree(devH); cudaFree(remoteScratch);
+    fb_set_error("peer-memory setup: scratch allocation failed");
+    return FB_ERR_OUT_OF_MEMORY;
+  }
+  auto release = [&]() { cudaFree(vote); cudaFree(devH); cudaFree(remoteScratch); };
+  {  // eligibility vote: all ranks take part, all ranks see the same answer
+    int eligible = (d->world <= FB_MAX_RANKS && d->nNbr <= FB_MAX_NBR && c->use_rows3) ? 1 : 0, all = 0;
+    cudaMemcpyAsync(vote, &eligible, sizeof(int), cudaMemcpyHostToDevice, st);
+    ncclResult_t r0 = ncclAllReduce(vote, vote, 1, ncclInt, ncclMin, d->comm_nccl(), st);
+    cudaMemcpyAsync(&all, vote, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    if (r0 != ncclSuccess || !all) { cudaGetLastError(); release(); return FB_OK; }
+  }
+  int ok = 1;
+  if (fb_dev_alloc_plain(c, &d->comm, (size_t)FB_COMM_WORDS) != FB_OK) ok = 0;  // exported with CUDA IPC
+  if (fb_dev_alloc(c, &d->pushTicket, 1) != FB_OK) ok = 0;
+  if (fb_dev_alloc(c, &d->remoteIdx, (size_t)nS) != FB_OK) ok = 0;
+  if (ok && (cudaMemsetAsync(d->comm, 0, sizeof(double) * FB_COMM_WORDS, st) != cudaSuccess ||
+             cudaMemsetAsync(d->pushTicket, 0, sizeof(unsigned int), st) != cudaSuccess)) ok = 0;
+  // 1. IPC handles of (comm, dir) of every rank
+  Handles mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) ok = (cudaIpcGetMemHandle(&mine.comm, d->comm) == cudaSuccess) && (cudaIpcGetMemHandle(&mine.dir, c->dir) == cudaSuccess);
+  if (cudaMemcpyAsync(devH + sizeof(Handles) * (size_t)d->world, &mine, sizeof(Handles), cudaMemcpyHostToDevice, st) != cudaSuccess) ok = 0;
   ncclResult_t nr = ncclAllGather(devH + sizeof(Handles) * (size_t)d->world, devH, sizeof(Handles), ncclChar, d->comm_nccl(), st);
   std::vector<Handles> all((size_t)d->world);
   if (nr == ncclSuccess) cudaMemcpyAsync(all.data(), devH, sizeof(Handles) * (size_t)d->world, cudaMemcpyDeviceToHost, st);
   // 2. the neighbours' local indices of my send vertices = their recv lists for me
+  int *remoteDst = d->remoteIdx ? d->remoteIdx : remoteScratch;
   if (nr == ncclSuccess) nr = ncclGroupStart();
   for (int i = 0; i < d->nNbr && nr == ncclSuccess; i++) {
     const int ns = d->sendOff[i + 1] - d->sendOff[i], nrv = d->recvOff[i + 1] - d->recvOff[i];
     if (nrv) nr = ncclSend(d->recvIdx + d->recvOff[i], (size_t)nrv, ncclInt, d->nbrRank[i], d->comm_nccl(), st);
-    if (ns && nr == ncclSuccess) nr = ncclRecv(d->remoteIdx + d->sendOff[i], (size_t)ns, ncclInt, d->nbrRank[i], d->comm_nccl(), st);
+    if (ns && nr == ncclSuccess) nr = ncclRecv(remoteDst + d->sendOff[i], (size_t)ns, ncclInt, d->nbrRank[i], d->comm_nccl(), st);
   }
   if (nr == ncclSuccess) nr = ncclGroupEnd();
   cudaError_t ce = cudaStreamSynchronize(st);
-  cudaFree(devH);
   if (nr != ncclSuccess || ce != cudaSuccess) { cudaGetLastError(); ok = 0; }
   // 3. map the peers
   d->nOpened = 0;
@@ -426,17 +442,15 @@ static int setup_p2p(fb_context *c) {
     d->opened[d->nOpened++] = ptr;
   }
   // 4. all ranks must agree (a rank that failed would otherwise wait for peers that never publish)
-  int *flag = nullptr;
-  FB_CUDA(cudaMalloc(&flag, sizeof(int)));
-  FB_CUDA(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
-  if (ncclAllReduce(flag, flag, 1, ncclInt, ncclMin, d->comm_nccl(), st) != ncclSuccess) ok = 0;
   int agreed = 0;
-  cudaMemcpyAsync(&agreed, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (cudaMemcpyAsync(vote, &ok, sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) ok = 0;
+  if (ncclAllReduce(vote, vote, 1, ncclInt, ncclMin, d->comm_nccl(), st) != ncclSuccess) ok = 0;
+  cudaMemcpyAsync(&agreed, vote, sizeof(int), cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);
-  cudaFree(flag);
+  cudaGetLastError();
+  release();
   d->p2p = ok && agreed;
-  if (d->p2p) {  // send entries regrouped by local vertex for the push fused into k_direction
-    const int nS = d->sendOff[d->nNbr];
+  if (d->p2p) {  // send entries regrouped by local vertex for the push fused into k_direction (no collectives from here on)
     std::vector<int> sIdx((size_t)nS), rIdx((size_t)nS);
     if (nS) {
       FB_CUDA(cudaMemcpyAsync(sIdx.data(), d->sendIdx, sizeof(int) * (size_t)nS, cudaMemcpyDeviceToHost, st));
@@ -721,6 +735,54 @@ int fb_create_partitioned(fb_context **out, int nV, const double *x0, int nT, co
 #undef DCHK
 #undef DCUDA
   *out = c;
+  return FB_OK;
+}
+
+// ---- owned-range vector API: this rank's rows only, no global-length staging -----------------------------------
+// The owned rows are contiguous in the local numbering (row_lo .. row_hi), so these are single copies of
+// 3 * (vertex_end - vertex_begin) doubles straight between the caller's buffer and the device vectors.
+static int owned_range(fb_context *c, size_t *off, size_t *bytes) {
+  if (!c) { fb_set_error("NULL context"); return FB_ERR_INVALID_ARGUMENT; }
+  if (cudaSetDevice(c->device) != cudaSuccess) { cudaGetLastError(); return FB_ERR_CUDA; }
+  *off = 3 * (size_t)c->row_lo;   // ordinary contexts: row_lo = 0, row_hi = nV (the whole vector)
+  *bytes = sizeof(double) * 3 * (size_t)(c->row_hi - c->row_lo);
+  return FB_OK;
+}
+
+int fb_set_external_forces_owned(fb_context *c, const double *f_owned) {
+  size_t off, bytes;
+  FB_TRY(owned_range(c, &off, &bytes));
+  if (!f_owned) { fb_set_error("f_owned is NULL"); return FB_ERR_INVALID_ARGUMENT; }
+  // forces on ghost vertices are not needed: ghost rows are masked in the solve and their state follows from the
+  // neighbour's search direction (fb_dist.cu header)
+  if (bytes) FB_CUDA(cudaMemcpyAsync(c->fext + off, f_owned, bytes, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+int fb_get_state_owned(fb_context *c, double *q, double *qvel, double *qaccel) {
+  size_t off, bytes;
+  FB_TRY(owned_range(c, &off, &bytes));
+  if (bytes) {
+    if (q) FB_CUDA(cudaMemcpyAsync(q, c->q + off, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (qvel) FB_CUDA(cudaMemcpyAsync(qvel, c->qvel + off, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (qaccel) FB_CUDA(cudaMemcpyAsync(qaccel, c->qaccel + off, bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  return FB_OK;
+}
+
+int fb_partition_local_range(const fb_context *c, int *local_begin, int *local_end) {
+  if (!c) return FB_ERR_INVALID_ARGUMENT;
+  if (local_begin) *local_begin = c->row_lo;
+  if (local_end) *local_end = c->row_hi;
+  return FB_OK;
+}
+
+int fb_partition_local_to_global(const fb_context *c, int *l2g) {
+  if (!c || !l2g) return FB_ERR_INVALID_ARGUMENT;
+  if (c->dist) memcpy(l2g, c->dist->l2g.data(), sizeof(int) * c->dist->l2g.size());
+  else for (int v = 0; v < c->nV; v++) l2g[v] = v;
   return FB_OK;
 }
 

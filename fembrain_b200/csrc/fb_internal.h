@@ -151,6 +151,7 @@ struct fb_context {
   double prof_sum_s;
   int prof_samples;
 
+  int comm_poisoned;     // last solve returned FB_ERR_COMM: reset the last-block tickets before the next one
   FbDist *dist;
   FbBatch *batch;
   FbSym *sym;
@@ -222,6 +223,7 @@ struct FbPeerArgs;
 void fb_dist_peer_args(fb_context *c, FbPeerArgs *out);        // rank/world/comm pointers, epochs zeroed
 unsigned long long fb_dist_epoch(fb_context *c, int it, int family);  // epoch of (current solve, iteration, family)
 void fb_dist_next_solve(fb_context *c);
+int fb_dist_reset_tickets(fb_context *c);
 unsigned int fb_dist_halo_mask(const fb_context *c);
 int fb_dist_halo_push(fb_context *c, const double *vec, unsigned long long epoch);
 struct FbPushArgs;

@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(VEC_TB) k_direction(int n, const double *__res
     if (push.nNbr) {  // every CTA's stores are out: raise this rank's halo flag in each neighbour's comm block
       __threadfence_system();
       for (int j = 0; j < push.nNbr; j++)
-        ((volatile unsigned long long *)pa.comm[push.nbrRank[j]])[FB_COMM_FLAG(FB_COMM_HALO, pa.rank)] = push.epoch;
+        ((volatile unsigned long long *)pa.comm[push.nbrRank[j]])[FB_COMM_FLAG(pa.parity, FB_COMM_HALO, pa.rank)] = push.epoch;
     }
     sc->ticket_b = 0u;
     if (rhoSlots || pa.enabled) sc->rho[it & 1] = rhoNew;
@@ -641,8 +641,8 @@ void enqueue_iteration_p2p(fb_context *c, int it) {
 // the reference's literal order, three kernels (+ NCCL in partitioned contexts without peer mapping)
 // fromCounter: the kernels take the iteration number from the device counter instead of an argument, so that a captured
 // 30-iteration period can be replayed (`it` then only places the refresh)
-void enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) {
-  if (fb_dist_p2p(c)) { enqueue_iteration_p2p(c, it); return; }
+int enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) {
+  if (fb_dist_p2p(c)) { enqueue_iteration_p2p(c, it); return FB_OK; }
   const int itArg = fromCounter ? 0 : it;
   const int n = c->r, vg = c->grid_vec;
   double *slotsV = c->partials + 3 * (size_t)FB_MAX_PARTIALS;
@@ -666,7 +666,7 @@ void enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) 
   else if (tma) fb_tma_launch(c, 1, c->dir, c->Ad, c->rhs, c->partials);
   else launch_spmv_mode<1>(c, c->Keff, c->dir, c->Ad, c->rhs, dqOut);
   if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], c->stream); c->nprof++; }
-  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq);
+  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->dq_part, &c->sc->dq));
   if (it % 30 == 0) {
     fb_launch(c->pdl, c->stream, k_update<true>, vg, VEC_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, c->sc, slotsV, itArg, rhoOut, dqSlots, nDq, nopeer);
     c->launches++;
@@ -679,10 +679,11 @@ void enqueue_iteration_kernels(fb_context *c, int it, bool fromCounter = false) 
     c->launches++;
     if (defer) { rhoSlots = slotsV; nRhoSlots = vg; }
   }
-  if (c->dist) fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]);
+  if (c->dist) FB_TRY(fb_dist_allreduce_scalar(c, &c->sc->rho_part, &c->sc->rho[it & 1]));
   fb_launch(c->pdl, c->stream, k_direction, vg, VEC_TB, n, c->res, c->invD, c->dir, c->sc, itArg, rhoSlots, nRhoSlots, nopeer, nullptr, nopush);
   c->launches++;
-  if (c->dist) fb_dist_halo_exchange(c, c->dir);
+  if (c->dist) FB_TRY(fb_dist_halo_exchange(c, c->dir));
+  return FB_OK;
 }
 
 // two kernels; `it` is only used to place the refresh (the kernels read the iteration from the device counter,
@@ -731,7 +732,10 @@ int finish_solve(fb_context *c) {
     return FB_ERR_CUDA;
   }
   if (c->dist && s.comm_error) {
-    fb_set_error("peer-memory exchange timed out (a rank stopped publishing)");
+    // CTAs that saw `done` raised in mid-kernel left without handing in their tickets: reset them before the next solve
+    c->comm_poisoned = 1;
+    fb_set_error(s.comm_error == 2 ? "peer-memory exchange overrun (a rank published a later value before this one was collected)"
+                                   : "peer-memory exchange timed out (a rank stopped publishing)");
     return FB_ERR_COMM;
   }
   return FB_OK;
@@ -743,6 +747,11 @@ int start_solve(fb_context *c, double eps, int maxIt) {
   memset(&pa, 0, sizeof(pa));
   const bool p2p = fb_dist_p2p(c) != 0;
   if (c->dist) fb_dist_next_solve(c);
+  if (c->comm_poisoned) {  // the previous solve ended in FB_ERR_COMM: last-block tickets may be half counted
+    FB_CUDA(cudaMemsetAsync(&c->sc->ticket_a, 0, 2 * sizeof(unsigned int), st));
+    FB_TRY(fb_dist_reset_tickets(c));
+    c->comm_poisoned = 0;
+  }
   // products from the block-upper triangle (fb_sym.cu): single-GPU three-kernel schedule only
   if (c->sym_want && (c->dist || c->batch || c->pers_grid > 0 || c->pcg_fused || c->pcg_graph)) c->sym_want = 0;
   if (c->sym_want && !c->sym) {
@@ -783,7 +792,7 @@ int ensure_period_graph(fb_context *c) {
   if (c->pcg_fused) {
     for (int k = 1; k <= 30; k++) kernels += enqueue_iteration_fused(c, k, false);
   } else {
-    for (int k = 1; k <= 30; k++) enqueue_iteration_kernels(c, k, true);
+    for (int k = 1; k <= 30; k++) (void)enqueue_iteration_kernels(c, k, true);  // no NCCL in a captured period (single GPU only)
     kernels = (int)(c->launches - before);
   }
   cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -900,7 +909,7 @@ int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
     } else {
       for (; it <= end; it++) {
         if (fused) enqueue_iteration_fused(c, it, true);
-        else enqueue_iteration_kernels(c, it);
+        else FB_TRY(enqueue_iteration_kernels(c, it));
       }
     }
     FB_CUDA(cudaMemcpyAsync(&c->sc_host[slot], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
@@ -933,23 +942,24 @@ int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec) {
     const bool useGraph = c->pcg_graph && !c->dist;
     if (useGraph) FB_TRY(ensure_period_graph(c));
     int it = 1;
-    auto run = [&](int count) {
+    auto run = [&](int count) -> int {
       const int end = it + count - 1;
       while (it <= end) {
         if (useGraph && c->graph_exec && (it - 1) % 30 == 0 && end - it + 1 >= 30) {
-          cudaGraphLaunch((cudaGraphExec_t)c->graph_exec, st);
+          FB_CUDA(cudaGraphLaunch((cudaGraphExec_t)c->graph_exec, st));
           c->launches += c->graph_kernels;
           it += 30;
         } else {
           if (fused) enqueue_iteration_fused(c, it, false);
-          else enqueue_iteration_kernels(c, it);
+          else FB_TRY(enqueue_iteration_kernels(c, it));
           it++;
         }
       }
+      return FB_OK;
     };
-    run(warm);
+    FB_TRY(run(warm));
     FB_CUDA(cudaEventRecord(c->ev[3], st));
-    run(repeats);
+    FB_TRY(run(repeats));
   }
   FB_CUDA(cudaEventRecord(c->ev[7], st));
   FB_CUDA(cudaStreamSynchronize(st));

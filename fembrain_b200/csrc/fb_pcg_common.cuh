@@ -130,18 +130,25 @@ __device__ __forceinline__ double cta_sum_slots(const double *__restrict__ slots
 // stores its value into slot [rank] of EVERY rank's block, fences at system scope, then stores the epoch into flag
 // [rank]; a consumer kernel spins (bounded) on its LOCAL flags until all carry the epoch, then adds the slots in rank
 // order — all ranks add the same bits in the same order, so alpha/beta/rho and the loop flag agree bit for bit.
-// Slots are single-buffered: a rank cannot overwrite a slot before every other rank has consumed it, because its next
-// write of that kind sits behind a wait on something each of them publishes only after consuming (fb_dist.cu).
+// INSIDE a solve a rank cannot overwrite a slot before every other rank has consumed it, because its next write of that
+// kind sits behind a wait on something each of them publishes only after consuming (fb_dist.cu).  ACROSS solves that
+// argument has one hole: the first publish of solve S+1 (k_cg_init, rho0) waits for nothing, so a rank that has left solve
+// S could overwrite its RHO slot while a lagging peer has not yet collected rho(final) of solve S.  Slots and flags are
+// therefore double-buffered by the parity of the solve counter: to touch parity p again a rank must have FINISHED solve
+// S+1, which needs every rank's publishes of S+1, which are stream-ordered after that rank's last collect of solve S.
+// With that, a flag can never legitimately run ahead of the epoch a consumer waits for: `flag > epochWait` is reported
+// as an overrun (comm_error = 2) instead of being taken as satisfied.
 #define FB_MAX_RANKS 16
 enum { FB_COMM_DQ = 0, FB_COMM_RHO = 1, FB_COMM_HALO = 2 };  // slot/flag families
-// block layout in 8-byte words: slots[family][FB_MAX_RANKS], then flags[family][FB_MAX_RANKS]
-#define FB_COMM_SLOT(fam, r) ((fam) * FB_MAX_RANKS + (r))
-#define FB_COMM_FLAG(fam, r) (3 * FB_MAX_RANKS + (fam) * FB_MAX_RANKS + (r))
-#define FB_COMM_WORDS (6 * FB_MAX_RANKS)
+// block layout in 8-byte words, per solve parity: slots[family][FB_MAX_RANKS], then flags[family][FB_MAX_RANKS]
+#define FB_COMM_SLOT(par, fam, r) ((par) * 6 * FB_MAX_RANKS + (fam) * FB_MAX_RANKS + (r))
+#define FB_COMM_FLAG(par, fam, r) ((par) * 6 * FB_MAX_RANKS + 3 * FB_MAX_RANKS + (fam) * FB_MAX_RANKS + (r))
+#define FB_COMM_WORDS (12 * FB_MAX_RANKS)
 #define FB_SPIN_LIMIT (1ll << 24)  // x ~100 ns: a lost peer turns into FB_ERR_COMM after ~2 s instead of a hung GPU
 
 struct FbPeerArgs {
   int enabled, rank, world;
+  int parity;                    // solve counter & 1: which half of the comm blocks this solve uses
   unsigned long long epoch;      // epoch of the value this kernel PUBLISHES (0 = none)
   unsigned long long epochWait;  // epoch of the value this kernel COLLECTS or waits for (0 = none)
   unsigned int haloMask;         // ranks whose halo flag the kernel waits for (SpMV)
@@ -163,9 +170,9 @@ struct FbPushArgs {
 
 // executed by ONE thread (the thread that holds the rank's total)
 __device__ __forceinline__ void peer_publish(const FbPeerArgs &pa, int family, double value) {
-  for (int p = 0; p < pa.world; p++) ((volatile double *)pa.comm[p])[FB_COMM_SLOT(family, pa.rank)] = value;
+  for (int p = 0; p < pa.world; p++) ((volatile double *)pa.comm[p])[FB_COMM_SLOT(pa.parity, family, pa.rank)] = value;
   __threadfence_system();
-  for (int p = 0; p < pa.world; p++) ((volatile unsigned long long *)pa.comm[p])[FB_COMM_FLAG(family, pa.rank)] = pa.epoch;
+  for (int p = 0; p < pa.world; p++) ((volatile unsigned long long *)pa.comm[p])[FB_COMM_FLAG(pa.parity, family, pa.rank)] = pa.epoch;
 }
 
 // executed by ALL threads of a CTA (TB >= 32); returns the rank-ordered sum in every thread; on timeout marks the solve
@@ -175,22 +182,26 @@ __device__ __forceinline__ double peer_collect(const FbPeerArgs &pa, int family,
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const volatile unsigned long long *flags = (const volatile unsigned long long *)pa.comm[pa.rank];
-    bool ok = true;
+    bool ok = true, overrun = false;
     if (lane < pa.world) {
       long long spins = 0;
-      while (flags[FB_COMM_FLAG(family, lane)] < pa.epochWait) {
+      unsigned long long f;
+      while ((f = flags[FB_COMM_FLAG(pa.parity, family, lane)]) < pa.epochWait) {
         __nanosleep(64);
         if (++spins > FB_SPIN_LIMIT) { ok = false; break; }
       }
+      overrun = f > pa.epochWait;  // the producer has already published a LATER value into this slot
     }
     ok = __all_sync(0xffffffffu, ok);
+    overrun = __any_sync(0xffffffffu, overrun);
     __threadfence_system();
-    const double v = (lane < pa.world) ? ((const volatile double *)pa.comm[pa.rank])[FB_COMM_SLOT(family, lane)] : 0.0;
+    const double v = (lane < pa.world) ? ((const volatile double *)pa.comm[pa.rank])[FB_COMM_SLOT(pa.parity, family, lane)] : 0.0;
     double tot = 0.0;
     for (int r = 0; r < pa.world; r++) tot += __shfl_sync(0xffffffffu, v, r);
     if (lane == 0) {
       s_total = tot;
       if (!ok) { sc->comm_error = 1; sc->done = 1; }
+      else if (overrun) { sc->comm_error = 2; sc->done = 1; }
     }
   }
   __syncthreads();
@@ -206,7 +217,7 @@ __device__ __forceinline__ void peer_wait_halo(const FbPeerArgs &pa, FbScalars *
     const volatile unsigned long long *flags = (const volatile unsigned long long *)pa.comm[pa.rank];
     if (lane < pa.world && ((pa.haloMask >> lane) & 1u)) {
       long long spins = 0;
-      while (flags[FB_COMM_FLAG(FB_COMM_HALO, lane)] < pa.epochWait) {
+      while (flags[FB_COMM_FLAG(pa.parity, FB_COMM_HALO, lane)] < pa.epochWait) {
         __nanosleep(64);
         if (++spins > FB_SPIN_LIMIT) { sc->comm_error = 1; sc->done = 1; break; }
       }

@@ -100,6 +100,8 @@ int fb_num_vertices(const fb_context *ctx);
 int fb_num_tets(const fb_context *ctx);
 int fb_num_dofs(const fb_context *ctx);              /* r = 3*num_vertices (ForceModel::Getr) */
 int fb_num_constrained_dofs(const fb_context *ctx);
+int fb_num_local_dofs(const fb_context *ctx);        /* DOFs of the LOCAL system the inspection hooks describe: = fb_num_dofs except on a
+                                                        partitioned context (owned + ghost vertices of this rank) */
 long long fb_nnz_stiffness(const fb_context *ctx);   /* scalar nnz of K (SparseMatrix::GetNumEntries) */
 long long fb_nnz_mass(const fb_context *ctx);
 long long fb_nnz_system(const fb_context *ctx);      /* scalar nnz of the constrained systemMatrix */
@@ -292,6 +294,16 @@ int fb_partition_peer_memory(const fb_context *ctx);
  * mesh): setters take the global vector and keep this rank's part; getters write this rank's OWNED entries and zeros
  * elsewhere, so the sum over ranks is the full vector.  fb_num_vertices/_tets/_dofs report the global mesh; the
  * inspection hooks (CSR, maps, rhs, ...) describe the rank's LOCAL system. */
+/* The LOCAL system of a partitioned context (what the inspection hooks describe): local vertices [local_begin, local_end) are
+ * the owned rows (contiguous), the others are ghosts; l2g[fb_num_local_dofs/3] maps a local vertex to the caller's vertex id. */
+int fb_partition_local_range(const fb_context *ctx, int *local_begin, int *local_end);
+int fb_partition_local_to_global(const fb_context *ctx, int *l2g);
+/* Owned-range variants for callers that keep their data distributed (no global-length vector, no host gather): f_owned,
+ * q, qvel, qaccel hold 3*(vertex_end - vertex_begin) doubles, the rows fb_partition_range reports, in the partition ordering
+ * (= the caller's numbering unless fb_partition_reordered).  On an ordinary context they are the whole vectors.  These are
+ * the calls a host program uses every frame (IntegratorBase::SetExternalForces / GetqState, integratorBase.cpp:84-122). */
+int fb_set_external_forces_owned(fb_context *ctx, const double *f_owned);
+int fb_get_state_owned(fb_context *ctx, double *q_owned, double *qvel_owned, double *qaccel_owned);
 /* Host-only view of the partition (runs without a GPU): what rank `rank` of `world` owns and exchanges.
  * counts[7] = {vertex_begin, vertex_end, local vertices, local tets, neighbours, total send vertices, total recv vertices};
  * every other output may be NULL; sizes come from a first call: l2g[counts[2]] (the local mesh's vertices in local order: ascending position in the partition ordering, as caller's vertex ids), local_tets[counts[3]], nbr_ranks/send_counts/recv_counts[counts[4]], send_global[counts[5]],

@@ -1,0 +1,152 @@
+"""Parity of a row-block partitioned context (N GPUs, one process each) against an ordinary single-GPU context of the
+whole mesh held by rank 0.  Used by tests/dist_check.py (small meshes, world 2 and 8) and by bench.py's N > 1 runs
+(`parity_check` block of the JSON line, on the bench mesh itself), so the check runs wherever the driver runs the path.
+
+What is compared (per-rank semantics of CGSolver.cpp:129-190):
+  * trajectory from rest at the shipped eps = 1e-6: PCG iteration counts per step (cross-rank sums associate differently,
+    so counts may differ by a few) and the state after the last step, <= 1e-4 relative;
+  * one step from EQUAL states: every rank's owned rows of the right-hand side bit-exact, every rank's owned rows of
+    Keff bit-exact (rank 0: value by value; other ranks: exact 64-bit checksum of the bit patterns per row range);
+  * one step from equal states with both solvers tightened to eps = 1e-12: displacement and velocity <= 1e-8 relative.
+All functions are collective: every rank must call them with its own context.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _rel(a, b):
+    den = float(np.abs(b).max()) if b.size else 0.0
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0)) if a.size else 0.0
+
+
+def gather_global(part, vec_local_full, r_global):
+    """Sum over ranks of (owned entries of a LOCAL full-length vector placed at the caller's DOF ids, zeros elsewhere)."""
+    lo, hi = part.local_range()
+    l2g = part.local_to_global()[lo:hi].astype(np.int64)
+    g = np.zeros(r_global)
+    own = np.asarray(vec_local_full).reshape(-1, 3)[lo:hi]
+    g.reshape(-1, 3)[l2g] = own
+    t = torch.from_numpy(g).cuda()
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def global_state(part, r_global):
+    """(q, qvel) of the whole mesh assembled from every rank's owned rows."""
+    q, qv, _ = part.get_state()  # global length: owned entries, zeros elsewhere
+    t = torch.from_numpy(np.stack([q, qv])).cuda()
+    dist.all_reduce(t)
+    s = t.cpu().numpy()
+    return s[0], s[1]
+
+
+def broadcast_state(part, ref, r_global):
+    """Put the partitioned context on the single-GPU context's state (rank 0 owns `ref`)."""
+    st = torch.zeros(2, r_global, dtype=torch.float64, device="cuda")
+    if ref is not None:
+        rq, rqv, _ = ref.get_state()
+        st.copy_(torch.from_numpy(np.stack([rq, rqv])))
+    dist.broadcast(st, 0)
+    s = st.cpu().numpy()
+    part.set_state(s[0], s[1], np.zeros(r_global))
+
+
+def _checksum(values):
+    return int(np.ascontiguousarray(values).view(np.uint64).sum(dtype=np.uint64))
+
+
+def partition_parity(part, ref, rank, world, r_global, traj_part=None, traj_steps=3, log=None):
+    """ref: the single-GPU Simulation on rank 0 (None elsewhere), same mesh, forces and cg settings as `part`, at rest.
+    traj_part = (iterations per step, global q after the last step) if the partitioned trajectory from rest has already
+    been run by the caller (bench.py's timed region); otherwise both sides run `traj_steps` steps here.
+    Returns the result dict on rank 0 (with "ok"), None on the other ranks; every rank learns `ok` via the return of
+    parity_ok()."""
+    log = log or (lambda *a: None)
+    res = {"world": world}
+    ok = True
+    # ---- (a) trajectory from rest, shipped tolerance -----------------------------------------------------------------
+    if traj_part is None:
+        part.reset_to_rest()
+        its_p = []
+        for _ in range(traj_steps):
+            part.do_timestep()
+            its_p.append(int(part.last_cg_iterations))
+        q_p, _ = global_state(part, r_global)
+    else:
+        its_p, q_p = list(traj_part[0]), traj_part[1]
+    if rank == 0:
+        ref.reset_to_rest()
+        its_r = []
+        for _ in range(len(its_p)):
+            ref.do_timestep()
+            its_r.append(int(ref.last_cg_iterations))
+        rq = ref.get_state()[0]
+        e = _rel(q_p, rq)
+        dit = max(abs(a - b) for a, b in zip(its_p, its_r)) if its_p else 0
+        res["trajectory"] = {"steps": len(its_p), "iterations_partitioned": its_p, "iterations_single_gpu": its_r,
+                             "max_iteration_difference": dit, "iterations_equal": its_p == its_r,
+                             "displacement_rel_err": e, "tolerance": 1e-4, "cg_eps": 1e-6}
+        ok &= (e <= 1e-4) and dit <= max(3, max(its_r) // 40)
+        log(f"[parity] trajectory: iterations {its_p} vs {its_r}, |dq| {e:.2e}")
+    # ---- (b) one step from equal states: owned rows of rhs and Keff bit-exact ---------------------------------------
+    broadcast_state(part, ref, r_global)
+    part.do_timestep()
+    rhs_g = gather_global(part, part.rhs_full(), r_global)   # x + 0.0 is exact: the sum is every rank's owned rows, bit for bit
+    lo, hi = part.local_range()
+    b, e_ = part.partition_range()
+    ia = part.K_row_pointers()
+    kv = part.K_values()[int(ia[3 * lo]):int(ia[3 * hi])] if hi > lo else np.zeros(0)
+    sums = torch.zeros(world, 3, dtype=torch.int64, device="cuda")   # per rank: vertex_begin, vertex_end, checksum (as int64 bits)
+    sums[rank, 0], sums[rank, 1] = b, e_
+    sums[rank, 2] = int(np.uint64(_checksum(kv)).astype(np.int64))
+    dist.all_reduce(sums)
+    reordered = int(part.reordered)
+    if rank == 0:
+        ref.do_timestep()
+        rrhs = ref.rhs_full()
+        rhs_equal = bool(np.array_equal(rhs_g, rrhs))
+        ria = ref.K_row_pointers()
+        rkv = ref.K_values()
+        res["equal_state_step"] = {"rhs_owned_rows_bit_exact_all_ranks": rhs_equal,
+                                   "iterations_partitioned": int(part.last_cg_iterations),
+                                   "iterations_single_gpu": int(ref.last_cg_iterations)}
+        ok &= rhs_equal
+        if not reordered:  # row blocks are ranges of the caller's numbering: the single-GPU rows of rank p are [begin, end)
+            mine = rkv[int(ria[3 * b]):int(ria[3 * e_])]
+            k0 = bool(np.array_equal(kv, mine))
+            h = sums.cpu().numpy()
+            chk = all(int(np.uint64(_checksum(rkv[int(ria[3 * int(h[p, 0])]):int(ria[3 * int(h[p, 1])])])).astype(np.int64)) == int(h[p, 2])
+                      for p in range(world))
+            res["equal_state_step"].update({"keff_owned_rows_bit_exact_rank0": k0, "keff_owned_rows_checksum_equal_all_ranks": bool(chk)})
+            ok &= k0 and chk
+        else:
+            res["equal_state_step"]["keff"] = "partition cut from a Cuthill-McKee ordering: rows are not a range of the single-GPU numbering; covered through the bit-exact rhs (T qvel + fint) and the tight solve"
+        dit = abs(int(part.last_cg_iterations) - int(ref.last_cg_iterations))
+        ok &= dit <= max(3, int(ref.last_cg_iterations) // 40)
+        log(f"[parity] equal-state step: rhs bit-exact {rhs_equal}, iterations {part.last_cg_iterations} vs {ref.last_cg_iterations}")
+    # ---- (c) tight solve from equal states ----------------------------------------------------------------------------
+    eps0, max0 = part.params.cg_epsilon, part.params.cg_max_iterations
+    broadcast_state(part, ref, r_global)
+    part.set_cg(1e-12, 20000)
+    part.do_timestep()
+    q_t, qv_t = global_state(part, r_global)
+    if rank == 0:
+        ref.set_cg(1e-12, 20000)
+        ref.do_timestep()
+        rq, rqv, _ = ref.get_state()
+        eq, ev = _rel(q_t, rq), _rel(qv_t, rqv)
+        res["tight_step"] = {"cg_eps": 1e-12, "displacement_rel_err": eq, "velocity_rel_err": ev, "tolerance": 1e-8,
+                             "iterations_partitioned": int(part.last_cg_iterations), "iterations_single_gpu": int(ref.last_cg_iterations)}
+        ok &= eq <= 1e-8 and ev <= 1e-8
+        ref.set_cg(eps0, max0)
+        log(f"[parity] tight step: |dq| {eq:.2e}, |dv| {ev:.2e}, iterations {part.last_cg_iterations} vs {ref.last_cg_iterations}")
+    part.set_cg(eps0, max0)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    res["ok"] = bool(int(flag[0]))
+    res["peer_memory"] = bool(part.peer_memory)
+    res["reordered"] = bool(reordered)
+    return res

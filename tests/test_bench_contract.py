@@ -9,14 +9,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nx", "8", "--steps", "2", "--warmup", "1",
-                          "--cpu-cg-iters", "10"], capture_output=True, text=True, timeout=300, check=True)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nx", "8", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, check=True)
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, out.stdout
     d = json.loads(lines[0])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
+    assert d["steps"] == 2 and d["warmup"] == 0 and len(d["step_seconds"]) == 2   # stock DoTimestep runs, from rest, no extrapolation
+    assert abs(d["ms_per_step"] * d["steps"] - 1e3 * sum(d["step_seconds"])) < 1e-6 * d["ms_per_step"] * d["steps"] + 1e-9
     assert d["impl"] == "reference" and d["metric"] == "fem_steps_per_s" and d["unit"] == "steps/s" and d["dtype"] == "f64"
     assert d["vs_baseline"] is None and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1

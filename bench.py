@@ -570,7 +570,7 @@ def run_ours(args):
             if rank == 0:
                 ref = make_sim(env, v, t, fixed, False)
                 ref.set_external_forces(f)
-            res = dist_parity.partition_parity(sim, ref, rank, world, r, traj_part=traj, log=log)
+            res = dist_parity.partition_parity(sim, ref, rank, world, r, traj_part=traj, log=log, tight_eps=1e-12 if nT < 2_000_000 else 1e-10)
             blocks_ok &= bool(res["ok"])
             if rank == 0:
                 res["mesh"] = f"the bench mesh itself (nx={nx}, {nT} tets); trajectory = the {args.warmup}+{args.steps} resident steps of this run"

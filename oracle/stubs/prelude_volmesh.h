@@ -16,5 +16,7 @@
 #include <sstream>
 #include <stdio.h>
 #define hifem_SGEffect_h       /* src/graphics/SGEffect.h (ShaderManager -> Loki, GL) */
+#define SELECTGL_H_           /* src/graphics/selectgl.h (GL/glew.h, GL/freeglut.h) */
+#include "graphics/selectgl.h"
 #include "graphics/SGEffect.h" /* resolves to oracle/stubs/graphics/SGEffect.h (stubs come first on the include path) */
 #endif

@@ -58,12 +58,13 @@ def _checksum(values):
     return int(np.ascontiguousarray(values).view(np.uint64).sum(dtype=np.uint64))
 
 
-def partition_parity(part, ref, rank, world, r_global, traj_part=None, traj_steps=3, log=None):
+def partition_parity(part, ref, rank, world, r_global, traj_part=None, traj_steps=3, log=None, tight_eps=1e-12):
     """ref: the single-GPU Simulation on rank 0 (None elsewhere), same mesh, forces and cg settings as `part`, at rest.
     traj_part = (iterations per step, global q after the last step) if the partitioned trajectory from rest has already
     been run by the caller (bench.py's timed region); otherwise both sides run `traj_steps` steps here.
     Returns the result dict on rank 0 (with "ok"), None on the other ranks; every rank learns `ok` via the return of
-    parity_ok()."""
+    parity_ok().  tight_eps: tolerance of the tightened solve (1e-12 on test meshes; at 10M tets the true-residual refresh every
+    30 iterations floors rho/rho0 near 1e-24, so the bench uses 1e-10)."""
     log = log or (lambda *a: None)
     res = {"world": world}
     ok = True
@@ -108,12 +109,20 @@ def partition_parity(part, ref, rank, world, r_global, traj_part=None, traj_step
         ref.do_timestep()
         rrhs = ref.rhs_full()
         rhs_equal = bool(np.array_equal(rhs_g, rrhs))
+        rhs_err = _rel(rhs_g, rrhs)
+        if reordered:
+            # rows of a Cuthill-McKee partition hold their columns in that ordering, so (hK + D) qvel is summed in another
+            # order than the single-GPU row sums it: equal to rounding, not bitwise (K, fint themselves are element-ordered sums)
+            rhs_ok = rhs_err <= 1e-12
+        else:
+            rhs_ok = rhs_equal
         ria = ref.K_row_pointers()
         rkv = ref.K_values()
-        res["equal_state_step"] = {"rhs_owned_rows_bit_exact_all_ranks": rhs_equal,
+        res["equal_state_step"] = {"rhs_owned_rows_bit_exact_all_ranks": rhs_equal, "rhs_rel_err": rhs_err,
+                                   "rhs_criterion": "relative 1e-12 (reordered partition: other column order in T qvel)" if reordered else "bit-exact",
                                    "iterations_partitioned": int(part.last_cg_iterations),
                                    "iterations_single_gpu": int(ref.last_cg_iterations)}
-        ok &= rhs_equal
+        ok &= rhs_ok
         if not reordered:  # row blocks are ranges of the caller's numbering: the single-GPU rows of rank p are [begin, end)
             mine = rkv[int(ria[3 * b]):int(ria[3 * e_])]
             k0 = bool(np.array_equal(kv, mine))
@@ -123,22 +132,23 @@ def partition_parity(part, ref, rank, world, r_global, traj_part=None, traj_step
             res["equal_state_step"].update({"keff_owned_rows_bit_exact_rank0": k0, "keff_owned_rows_checksum_equal_all_ranks": bool(chk)})
             ok &= k0 and chk
         else:
-            res["equal_state_step"]["keff"] = "partition cut from a Cuthill-McKee ordering: rows are not a range of the single-GPU numbering; covered through the bit-exact rhs (T qvel + fint) and the tight solve"
+            res["equal_state_step"]["keff"] = "partition cut from a Cuthill-McKee ordering: rows are not a range of the single-GPU numbering; covered through the rhs (T qvel + fint, 1e-12) and the tight solve"
         dit = abs(int(part.last_cg_iterations) - int(ref.last_cg_iterations))
         ok &= dit <= max(3, int(ref.last_cg_iterations) // 40)
         log(f"[parity] equal-state step: rhs bit-exact {rhs_equal}, iterations {part.last_cg_iterations} vs {ref.last_cg_iterations}")
     # ---- (c) tight solve from equal states ----------------------------------------------------------------------------
     eps0, max0 = part.params.cg_epsilon, part.params.cg_max_iterations
     broadcast_state(part, ref, r_global)
-    part.set_cg(1e-12, 20000)
-    part.do_timestep()
+    part.set_cg(tight_eps, 40000)
+    conv_p = part.step_raw() == 0   # every rank takes the same decision (same scalars), so nobody is left in a collective
     q_t, qv_t = global_state(part, r_global)
     if rank == 0:
-        ref.set_cg(1e-12, 20000)
-        ref.do_timestep()
+        ref.set_cg(tight_eps, 40000)
+        conv_r = ref.step_raw() == 0
         rq, rqv, _ = ref.get_state()
         eq, ev = _rel(q_t, rq), _rel(qv_t, rqv)
-        res["tight_step"] = {"cg_eps": 1e-12, "displacement_rel_err": eq, "velocity_rel_err": ev, "tolerance": 1e-8,
+        ok &= conv_p and conv_r
+        res["tight_step"] = {"cg_eps": tight_eps, "converged_partitioned": conv_p, "converged_single_gpu": conv_r, "displacement_rel_err": eq, "velocity_rel_err": ev, "tolerance": 1e-8,
                              "iterations_partitioned": int(part.last_cg_iterations), "iterations_single_gpu": int(ref.last_cg_iterations)}
         ok &= eq <= 1e-8 and ev <= 1e-8
         ref.set_cg(eps0, max0)

@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -282,8 +283,171 @@ class Oracle:
         return self._fn("solve_time")(self._h)
 
 
-# -- Deformable's vertex queries (force producers), restated with numpy.  PARITY UNPINNED: Deformable.cpp and
-#    CuttableMesh.cpp cannot be compiled here (TBB, Loki, GL); restated from source. -------------------------------------------
+# -- the reference's own `class Deformable`, compiled (oracle/deformable_harness.cpp) ------------------------------------------
+def _def_lib():
+    lib = _lib("ref")
+    if getattr(lib, "_fbdef_bound", False):
+        return lib
+    vp, ci, cd, cf = C.c_void_p, C.c_int, C.c_double, C.c_float
+    sig = {
+        "fbdef_create": (vp, [ci, vp, ci, vp, ci, vp]), "fbdef_destroy": (None, [vp]),
+        "fbdef_num_vertices": (ci, [vp]), "fbdef_num_cells": (ci, [vp]), "fbdef_num_edges": (ci, [vp]),
+        "fbdef_mesh": (None, [vp, vp, vp, vp]), "fbdef_node_neighbors": (ci, [vp, ci, ci, vp]),
+        "fbdef_set_gravity": (None, [vp, ci]), "fbdef_set_haptic_radius": (None, [vp, ci]), "fbdef_set_floor": (None, [vp, cf]),
+        "fbdef_floor_y": (cf, [vp]), "fbdef_set_haptic": (None, [vp, ci, vp, vp, ci]), "fbdef_timestep": (None, [vp]),
+        "fbdef_get_state": (None, [vp, vp, vp, vp]), "fbdef_set_state": (None, [vp, vp, vp]),
+        "fbdef_get_external_forces": (None, [vp, vp]), "fbdef_contacts": (ci, [vp]), "fbdef_set_contacts": (None, [vp, ci]),
+        "fbdef_positions": (None, [vp, vp]), "fbdef_aabb": (None, [vp, vp, vp]),
+        "fbdef_pick_vertices": (ci, [vp, vp, vp, ci, vp, vp]), "fbdef_pick_vertex": (ci, [vp, vp, vp, vp]),
+        "fbdef_sample_mesh": (ci, [ci, ci, ci, ci, cd, cd, vp, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib._fbdef_bound = True
+    return lib
+
+
+def _libc_fflush():
+    try:
+        C.CDLL(None).fflush(None)
+    except Exception:
+        pass
+
+
+def deformable_available() -> bool:
+    """True when oracle/_ref holds the compiled Deformable (built from /root/reference by oracle/Makefile)."""
+    if not available("ref"):
+        return False
+    try:
+        _def_lib()
+        return True
+    except AttributeError:
+        return False
+
+
+def sample_mesh(which, a=0, b=0, c=0, x=0.0, y=0.0):
+    """The reference's own VolMeshSamples generators (src/deformable/VolMeshSamples.cpp:15-253), compiled:
+    'one_tetra', 'two_tetra', 'truth_cube' (a, b, c = nx, ny, nz; x = cellsize), 'egg_shell' (a, b = hseg, vseg; x radius, y thickness)."""
+    lib = _def_lib()
+    code = {"one_tetra": 0, "two_tetra": 1, "truth_cube": 2, "egg_shell": 3}[which]
+    nV, nT = C.c_int(0), C.c_int(0)
+    if lib.fbdef_sample_mesh(code, a, b, c, x, y, C.byref(nV), C.byref(nT), None, None) != 0:
+        raise RuntimeError("sample mesh failed")
+    v, t = np.zeros((nV.value, 3)), np.zeros((nT.value, 4), np.int32)
+    lib.fbdef_sample_mesh(code, a, b, c, x, y, C.byref(nV), C.byref(nT), v.ctypes.data, t.ctypes.data)
+    return v, t
+
+
+class RefDeformable:
+    """The UNMODIFIED reference `Deformable` (Deformable.cpp, CuttableMesh / VolMesh under it) on a tet mesh: the compiled
+    checker for Deformable::timestep, applyHapticForces, the floor post-step, pickVertices / pickVertex and the
+    get_node_neighbors quirk.  Material, time step, damping and CG settings are the ones Deformable hard-codes."""
+
+    def __init__(self, verts, tets, fixed_verts=()):
+        self._lib = _def_lib()
+        v, t, fx = _f64(verts).reshape(-1, 3), _i32(tets).reshape(-1, 4), _i32(fixed_verts)
+        # CuttableMesh's setup runs the reference's mesh self-tests, which print to stdout (test_VolMesh.cpp): keep them off it
+        sys.stdout.flush()
+        saved, null = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null, 1)
+        try:
+            self._h = self._lib.fbdef_create(len(v), v.ctypes.data, len(t), t.ctypes.data, len(fx), fx.ctypes.data if len(fx) else None)
+            _libc_fflush()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(null)
+        if not self._h:
+            raise RuntimeError("reference VolMesh::setup failed")
+        self.nV, self.nT = self._lib.fbdef_num_vertices(self._h), self._lib.fbdef_num_cells(self._h)
+        self.r = 3 * self.nV
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fbdef_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mesh(self):
+        """(rest positions, cells, edges [nE,2] in VolMesh::m_vEdges order) of the CuttableMesh Deformable holds."""
+        nE = self._lib.fbdef_num_edges(self._h)
+        x, c, e = np.zeros((self.nV, 3)), np.zeros((self.nT, 4), np.int32), np.zeros((max(nE, 1), 2), np.int32)
+        self._lib.fbdef_mesh(self._h, x.ctypes.data, c.ctypes.data, e.ctypes.data)
+        return x, c, e[:nE]
+
+    def node_neighbors(self, v):
+        out = np.zeros(4096, np.int32)
+        n = self._lib.fbdef_node_neighbors(self._h, int(v), len(out), out.ctypes.data)
+        return out[:n].copy()
+
+    def set_gravity(self, on):
+        self._lib.fbdef_set_gravity(self._h, int(on))
+
+    def set_haptic_radius(self, rings):
+        self._lib.fbdef_set_haptic_radius(self._h, int(rings))
+
+    def set_floor(self, y):
+        self._lib.fbdef_set_floor(self._h, float(y))
+        return float(self._lib.fbdef_floor_y(self._h))
+
+    def set_haptic(self, indices, forces, in_progress=True):
+        idx, f = _i32(indices), _f64(forces).reshape(-1)
+        self._lib.fbdef_set_haptic(self._h, len(idx), idx.ctypes.data if len(idx) else None, f.ctypes.data if f.size else None, int(in_progress))
+
+    def timestep(self):
+        self._lib.fbdef_timestep(self._h)
+
+    def get_state(self):
+        q, qv, qa = np.zeros(self.r), np.zeros(self.r), np.zeros(self.r)
+        self._lib.fbdef_get_state(self._h, q.ctypes.data, qv.ctypes.data, qa.ctypes.data)
+        return q, qv, qa
+
+    def set_state(self, q, qvel):
+        q, qv = _f64(q).reshape(-1), _f64(qvel).reshape(-1)
+        self._lib.fbdef_set_state(self._h, q.ctypes.data, qv.ctypes.data)
+
+    def external_forces(self):
+        f = np.zeros(self.r)
+        self._lib.fbdef_get_external_forces(self._h, f.ctypes.data)
+        return f
+
+    @property
+    def contacts(self):
+        return self._lib.fbdef_contacts(self._h)
+
+    def set_contacts(self, n):
+        self._lib.fbdef_set_contacts(self._h, int(n))
+
+    def positions(self):
+        x = np.zeros((self.nV, 3))
+        self._lib.fbdef_positions(self._h, x.ctypes.data)
+        return x
+
+    def aabb(self):
+        lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self._lib.fbdef_aabb(self._h, lo.ctypes.data, hi.ctypes.data)
+        return lo, hi
+
+    def pick_vertices(self, lo, hi):
+        lo, hi = _f64(lo), _f64(hi)
+        idx, co = np.zeros(max(self.nV, 1), np.int32), np.zeros(3 * max(self.nV, 1))
+        n = self._lib.fbdef_pick_vertices(self._h, lo.ctypes.data, hi.ctypes.data, self.nV, idx.ctypes.data, co.ctypes.data)
+        return idx[:n].copy(), co[:3 * n].reshape(-1, 3).copy()
+
+    def pick_vertex(self, world_pos):
+        w, d, v = _f64(world_pos), C.c_double(0), np.zeros(3)
+        i = self._lib.fbdef_pick_vertex(self._h, w.ctypes.data, C.byref(d), v.ctypes.data)
+        return i, d.value, v
+
+
+# -- Deformable's vertex queries (force producers, SURVEY §8f N3), restated with numpy.  PINNED against the compiled
+#    Deformable::pickVertices / CuttableMesh::findClosestVertex (RefDeformable above; tests/test_oracle_deformable.py). ------
 def pick_vertices(rest_pos, u, box_lo, box_hi):
     """Deformable::pickVertices (src/deformable/Deformable.cpp:430-448) with Contains<double> (src/graphics/AABB.h:84-92, closed
     box) on pos = restpos + u (VolMesh::displace, src/deformable/VolMesh.cpp:1370-1385): ascending indices and coordinates."""

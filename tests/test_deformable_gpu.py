@@ -1,6 +1,11 @@
 """GPU parity of the caller around the step — Deformable::timestep (DEF/Deformable.cpp:318-420): gravity,
-haptic force ring spreading (both neighbour rules), floor-plane post-step — against the restatement in
-oracle/deformable_port.inc (unpinned against a compiled reference: Deformable.cpp does not build here)."""
+haptic force ring spreading (both neighbour rules), floor-plane post-step, vertex picks.
+
+Checkers: (1) frames of the reference's OWN compiled `Deformable` (oracle/deformable_harness.cpp; committed as
+tests/golden/deformable_*.npz by make_golden.py, and run live where oracle/_ref holds it); (2) the restatement in
+oracle/deformable_port.inc / pyoracle.pick_*, itself pinned bit-for-bit against (1) by tests/test_oracle_deformable.py."""
+import os
+
 import numpy as np
 import pytest
 
@@ -19,6 +24,61 @@ def unique_edges(tets, seed=0):
                 seen.add(k)
                 out.append((int(t[a]), int(t[b])))
     return np.array(out, np.int32)
+
+
+@pytest.mark.parametrize("name", ["cube6_low_index", "cube5_gravity_contact", "cube5_far_floor", "egg_shell_sample"])
+def test_deformable_timestep_matches_compiled_reference_frames(name):
+    """fb_deformable_timestep against frames produced by the reference's compiled Deformable::timestep: external forces
+    (gravity, haptic rings through the get_node_neighbors quirk on VolMesh's own edge array) bit-exact, contact counts
+    equal, state within the eps = 1e-6 solver tolerance; every frame restarts from the reference's state."""
+    import fembrain_b200 as fb
+    from tests import test_oracle_deformable as tod
+
+    v, t, fixed, hidx, hf, gravity, _, rings, steps = tod.scenario(name)
+    z = np.load(os.path.join(cases.GOLDEN, f"deformable_{name}.npz"))
+    sim = fb.Simulation(v, t, fixed)
+    sim.set_gravity(gravity)
+    sim.set_floor(True, float(z["floor_y"]))
+    sim.set_haptic_neighborhood(rings)
+    sim.set_haptic_forces(np.array(hidx, np.int32), np.array(hf, np.float64), True)
+    sim.set_edge_list(z["edges"], True)
+    zero = np.zeros(sim.r)
+    for k in range(steps):
+        sim.deformable_timestep()
+        assert np.array_equal(sim.get_external_forces(), z["ext"][k]), f"external forces, frame {k}"
+        assert sim.contact_count == int(z["contacts"][k]), f"contacts, frame {k}"
+        q, qv, qa = sim.get_state()
+        assert not qa.any()
+        assert cases.rel_err(q, z["q"][k]) <= 1e-4 and cases.rel_err(qv, z["qvel"][k]) <= 1e-4, f"state, frame {k}"
+        sim.set_state(z["q"][k], z["qvel"][k], zero)
+
+
+def test_picks_match_compiled_reference_live(ref_oracle):
+    """Deformable::pickVertices / pickVertex evaluated by the compiled reference itself on ITS deformed mesh vs the device
+    queries on the same displacement (skipped where oracle/_ref does not hold the compiled Deformable)."""
+    import fembrain_b200 as fb
+
+    if not ref_oracle.deformable_available():
+        pytest.skip("compiled Deformable not available")
+    v, t, fixed, load = cases.cube_case(6)
+    d = ref_oracle.RefDeformable(v, t, fixed)
+    d.set_haptic([load], [[1e4, 2e3, 0]], True)
+    d.timestep()
+    q, qv, _ = d.get_state()
+    pos = d.positions()
+    sim = fb.Simulation(v, t, fixed)
+    sim.set_state(q, qv, np.zeros_like(q))
+    for lo, hi in [((-0.25, 0.15, -0.25), (0.25, 0.65, 0.25)), ((-10, -10, -10), (10, 10, 10)), ((5, 5, 5), (6, 6, 6)),
+                   (tuple(pos[10]), tuple(pos[10])), (tuple(pos.min(axis=0)), tuple(pos.max(axis=0)))]:
+        idx, co, n = sim.pick_vertices(lo, hi)
+        ridx, rco = d.pick_vertices(lo, hi)
+        assert n == len(ridx) and np.array_equal(idx, ridx) and np.array_equal(co, rco)
+    rng = np.random.default_rng(11)
+    for w in list(rng.uniform(-1, 2, size=(8, 3))) + [pos[17], 0.5 * (pos[0] + pos[1])]:
+        i, dist, p = sim.pick_vertex(w)
+        ri, rd, rp = d.pick_vertex(w)
+        assert i == ri and dist == rd and np.array_equal(p, rp)
+    d.close()
 
 
 @pytest.mark.parametrize("quirk", [False, True])

@@ -40,7 +40,9 @@ class FbParams(C.Structure):
         ("internal_force_scaling", C.c_double),
         ("device", C.c_int),
         ("keep_raw_stiffness", C.c_int),
-        ("reserved", C.c_int * 6),
+        ("solver_variant", C.c_int),
+        ("warm_start", C.c_int),
+        ("reserved", C.c_int * 4),
     ]
 
 
@@ -88,6 +90,8 @@ def load_library():
         "fb_displacements_dev": (vp, [vp]),
         "fb_set_timestep": (ci, [vp, cd]), "fb_set_damping": (ci, [vp, cd, cd]),
         "fb_set_internal_force_scaling": (ci, [vp, cd]), "fb_set_cg": (ci, [vp, cd, ci]),
+        "fb_set_grid": (ci, [vp, ci, ci, ci]), "fb_set_solver": (ci, [vp, ci, ci]),
+        "fb_get_solver": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]), "fb_solver_name": (C.c_char_p, [ci]),
         "fb_step": (ci, [vp]),
         "fb_deformable_timestep": (ci, [vp]), "fb_deformable_set_gravity": (ci, [vp, ci]),
         "fb_deformable_set_floor": (ci, [vp, ci, cd]),
@@ -103,6 +107,7 @@ def load_library():
         "fb_batch_offsets": (ci, [vp, vp, vp]), "fb_batch_last_cg_iterations": (ci, [vp, vp, vp]),
         "fb_partition_ordering": (ci, [ci, ci, vp, ci, vp, C.POINTER(ci)]), "fb_partition_reordered": (ci, [vp]),
         "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]), "fb_trim_memory": (ci, []),
+        "fb_check_guards": (ci, [C.POINTER(ll), C.POINTER(ll)]),
         "fb_get_stiffness_csr": (ci, [vp, vp, vp]), "fb_get_mass_csr": (ci, [vp, vp, vp, vp]),
         "fb_get_system_csr": (ci, [vp, vp, vp, vp]), "fb_get_element_maps": (ci, [vp, vp, vp]),
         "fb_get_element_data": (ci, [vp, vp, vp]), "fb_get_super_maps": (ci, [vp, vp, vp]),
@@ -195,6 +200,16 @@ def partition_ordering(num_vertices, tets, world):
     if st != FB_OK:
         raise FemBrainError(st, "fb_partition_ordering", lib.fb_last_error_string().decode())
     return order[:num_vertices], bool(flag.value)
+
+
+def check_guards():
+    """(allocations checked, allocations with an overwritten guard band) — FEMBRAIN_B200_GUARD=1 processes only."""
+    lib = load_library()
+    a, b = C.c_longlong(0), C.c_longlong(0)
+    st = lib.fb_check_guards(C.byref(a), C.byref(b))
+    if st != FB_OK:
+        raise FemBrainError(st, "fb_check_guards", lib.fb_last_error_string().decode())
+    return a.value, b.value
 
 
 def trim_memory():
@@ -439,6 +454,21 @@ class Simulation:
 
     def set_cg(self, eps, max_iter):
         self._check(self._lib.fb_set_cg(self._h, eps, max_iter), "fb_set_cg")
+
+    def set_grid(self, nx, ny=None, nz=None):
+        """Declare the tensor grid of the mesh (CreateTruthCube numbering): what the multigrid variant coarsens."""
+        ny, nz = (nx if ny is None else ny), (nx if nz is None else nz)
+        self._check(self._lib.fb_set_grid(self._h, nx, ny, nz), "fb_set_grid")
+
+    def set_solver(self, variant, warm_start=False):
+        """variant: 0 / "jacobi" (the reference's solver), 1 / "block_jacobi", 2 / "mg" — labelled variants, see fembrain_b200.h."""
+        code = {"jacobi": 0, "block_jacobi": 1, "mg": 2}.get(variant, variant)
+        self._check(self._lib.fb_set_solver(self._h, int(code), int(bool(warm_start))), "fb_set_solver")
+
+    def solver(self):
+        v, w, lv = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self._lib.fb_get_solver(self._h, C.byref(v), C.byref(w), C.byref(lv)), "fb_get_solver")
+        return {"variant": v.value, "name": self._lib.fb_solver_name(v.value).decode(), "warm_start": bool(w.value), "levels": lv.value}
 
     def set_timestep(self, h):
         self._check(self._lib.fb_set_timestep(self._h, h), "fb_set_timestep")

@@ -25,6 +25,7 @@ UNITS = {
     "fb_fem.cu": ["-fmad=false"],
     "fb_assembly.cu": ["-fmad=false"],
     "fb_pcg.cu": [],
+    "fb_mg.cu": [],
     "fb_pcg_persistent.cu": [],
     "fb_dist.cu": [],
     "fb_batch.cu": [],

@@ -53,6 +53,8 @@ extern "C" void fb_default_params(fb_params *p) {
   p->internal_force_scaling = 1.0;
   p->device = 0;
   p->keep_raw_stiffness = 0;
+  p->solver_variant = FB_SOLVER_JACOBI_PCG;
+  p->warm_start = 0;
 }
 
 namespace {
@@ -100,6 +102,7 @@ int download(fb_context *c, void *dst, const void *src, size_t bytes) {
 void free_all(fb_context *c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  fb_mg_release(c);
   fb_pcg_release(c);
   fb_dist_destroy(c);
   fb_batch_destroy(c);
@@ -110,7 +113,7 @@ void free_all(fb_context *c) {
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,
                   c->contact_dev, c->ctaRows, c->pers_prof, c->ga_incp, c->ga_ctaV, c->ga_lists, c->ga_erec, c->ga_xu};
   for (void *p : ptrs)
-    if (p) cudaFree(p);
+    if (p) fb_dev_free(p);
   if (c->sc_host) cudaFreeHost(c->sc_host);
   if (c->fext_host) cudaFreeHost(c->fext_host);
   for (auto &e : c->ev)
@@ -119,7 +122,7 @@ void free_all(fb_context *c) {
     if (e) cudaEventDestroy(e);
   for (auto &e : c->evProf)
     if (e) cudaEventDestroy(e);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream && !c->stream_borrowed) cudaStreamDestroy(c->stream);
   free(c->cdofs_host);
   free(c->haptic_idx_host);
   free(c->haptic_f_host);
@@ -143,11 +146,12 @@ int fb_apply_constraints(fb_context *c, int nC, const int *cdofs_sorted) {
       return FB_ERR_INVALID_ARGUMENT;
     }
   }
-  if (c->cdofs) { cudaFree(c->cdofs); c->cdofs = nullptr; }
+  if (c->cdofs) { fb_dev_free(c->cdofs); c->cdofs = nullptr; }
   free(c->cdofs_host);
   c->cdofs_host = (int *)malloc(sizeof(int) * (size_t)(nC ? nC : 1));
   memcpy(c->cdofs_host, cdofs_sorted, sizeof(int) * (size_t)nC);
   c->nC = nC;
+  fb_mg_invalidate(c);   // coarse levels of a multigrid hierarchy carry the constraints too
   FB_TRY(fb_dev_alloc(c, &c->cdofs, (size_t)nC));
   FB_CUDA(cudaMemsetAsync(c->fixed, 0, (size_t)(c->r ? c->r : 1), c->stream));
   if (nC) {
@@ -224,6 +228,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   c->prm = p;
   c->nV = nV; c->nT = nT; c->r = 3 * nV;
   c->haptic_rings = 5;  // m_hapticForceNeighorhoodSize, DEF/Deformable.cpp ctor
+  c->uniform_material = (!E && !nu && !rho) ? 1 : 0;
   c->row_lo = 0; c->row_hi = nV;
   int st = FB_OK;
 #define CR(call) do { st = (call); if (st != FB_OK) { free_all(c); return st; } } while (0)
@@ -250,7 +255,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
     if (nV) { k_count_isolated<<<gridFor(nV, 256), 256, 0, c->stream>>>(nV, c->diag, flag); c->launches++; }
     CRC(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CRC(cudaStreamSynchronize(c->stream));
-    cudaFree(flag);
+    fb_dev_free(flag);
     if (h != 0x7fffffff) {
       fb_set_error("vertex %d belongs to no tetrahedron", h);
       free_all(c);
@@ -264,7 +269,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   if (rho) { CRC(cudaMalloc(&drho, sizeof(double) * (size_t)(nT ? nT : 1))); CR(upload(c, drho, rho, sizeof(double) * (size_t)nT)); }
   st = fb_launch_element_data(c, dE, dnu, drho);
   cudaStreamSynchronize(c->stream);
-  cudaFree(dE); cudaFree(dnu); cudaFree(drho);
+  fb_dev_free(dE); fb_dev_free(dnu); fb_dev_free(drho);
   if (st != FB_OK) { free_all(c); return st; }
   CR(fb_dev_alloc(c, &c->mblk, (size_t)c->nB));
   CR(fb_launch_mass(c));
@@ -320,6 +325,8 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   }
   CRC(cudaStreamSynchronize(c->stream));
   CRC(cudaGetLastError());
+  // the one variant that needs nothing but the matrix can be asked for at creation; FB_SOLVER_MG_PCG needs fb_set_grid first
+  if (p.solver_variant == FB_SOLVER_BLOCK_JACOBI_PCG) CR(fb_set_solver(c, p.solver_variant, p.warm_start));
 #undef CR
 #undef CRC
   *out = c;
@@ -379,6 +386,7 @@ int fb_do_step(fb_context *c) {
   FB_TRY(fb_launch_spmv_exact(c, c->T, c->qvel, c->tmp));
   FB_TRY(fb_launch_rhs(c));
   FB_CUDA(cudaEventRecord(c->ev[2], st));
+  if (fb_mg_active(c)) FB_TRY(fb_mg_prepare(c));   // variants: coarse operators / FP32 copies of this step's Keff (timed with the solve)
   FB_TRY(fb_pcg_solve(c, c->prm.cg_epsilon, c->prm.cg_max_iterations));
   FB_CUDA(cudaEventRecord(c->ev[3], st));
   const bool failed = c->last_iters < 0;
@@ -705,7 +713,7 @@ int fb_get_element_data(fb_context *c, double *minv16, double *k0) {
     if (st == FB_OK && minv16) st = download(c, minv16 + 16 * (size_t)el0, dm, sizeof(double) * 16 * (size_t)n);
     if (st == FB_OK && k0) st = download(c, k0 + 144 * (size_t)el0, dk, sizeof(double) * 144 * (size_t)n);
   }
-  cudaFree(dm); cudaFree(dk);
+  fb_dev_free(dm); fb_dev_free(dk);
   return st;
 }
 
@@ -856,6 +864,70 @@ int fb_bench_assembly(fb_context *c, int repeats, double *sec) {
   return FB_OK;
 }
 }  // extern "C"
+// ---- guard bands -------------------------------------------------------------------------------------------------
+#include <mutex>
+#include <unordered_map>
+namespace {
+constexpr size_t FB_GUARD = 256;
+struct GuardRec { unsigned char *base; size_t bytes; };
+std::mutex g_guard_mu;
+std::unordered_map<void *, GuardRec> g_guards;
+}  // namespace
+bool fb_guard_enabled() {
+  static const bool on = getenv("FEMBRAIN_B200_GUARD") && atoi(getenv("FEMBRAIN_B200_GUARD")) != 0;
+  return on;
+}
+cudaError_t fb_guard_alloc(void **p, size_t bytes, cudaStream_t st) {
+  unsigned char *base = nullptr;
+  const size_t padded = ((bytes + 255) / 256) * 256;   // the band after the buffer starts at the next 256-byte boundary
+  cudaError_t e = cudaMallocAsync((void **)&base, padded + 2 * FB_GUARD, st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(base, 0xA5, padded + 2 * FB_GUARD, st);
+  if (e != cudaSuccess) return e;
+  *p = base + FB_GUARD;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  g_guards[*p] = GuardRec{base, bytes};
+  return cudaSuccess;
+}
+void fb_dev_free(void *p) {
+  if (!p) return;
+  if (fb_guard_enabled()) {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    auto it = g_guards.find(p);
+    if (it != g_guards.end()) {
+      cudaFree(it->second.base);
+      g_guards.erase(it);
+      return;
+    }
+  }
+  cudaFree(p);
+}
+extern "C" int fb_check_guards(long long *checked, long long *corrupted) {
+  // bytes [bytes, padded) behind a buffer are slack the kernels may legitimately touch (e.g. whole 16-byte lines around a
+  // row tile); the bands proper must still hold the fill pattern
+  if (!checked || !corrupted) return FB_ERR_INVALID_ARGUMENT;
+  *checked = *corrupted = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return FB_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  unsigned char host[2 * FB_GUARD];
+  for (auto &kv : g_guards) {
+    const GuardRec &g = kv.second;
+    const size_t padded = ((g.bytes + 255) / 256) * 256;
+    if (cudaMemcpy(host, g.base, FB_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(host + FB_GUARD, g.base + FB_GUARD + padded, FB_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cudaGetLastError();   // an allocation that lives on another device of the process: skipped
+      continue;
+    }
+    bool bad = false;
+    for (size_t i = 0; i < 2 * FB_GUARD; i++) bad |= host[i] != 0xA5;
+    (*checked)++;
+    if (bad) {
+      (*corrupted)++;
+      fb_set_error("guard band of a %zu-byte device allocation was overwritten", g.bytes);
+    }
+  }
+  return FB_OK;
+}
 bool fb_use_pool() {
   static const bool on = !(getenv("FEMBRAIN_B200_POOL") && atoi(getenv("FEMBRAIN_B200_POOL")) == 0);
   return on;

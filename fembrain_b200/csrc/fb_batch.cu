@@ -357,7 +357,7 @@ void fb_batch_destroy(fb_context *c) {
   if (!b) return;
   void *ptrs[] = {b->wmeta, b->umeta, b->meshW, b->meshU, b->rho, b->rho0, b->iters, b->done, b->ticket, b->active, b->wnext, b->slotsA, b->slotsB};
   for (void *p : ptrs)
-    if (p) cudaFree(p);
+    if (p) fb_dev_free(p);
   delete b;
   c->batch = nullptr;
 }

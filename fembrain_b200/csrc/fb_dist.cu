@@ -388,11 +388,11 @@ static int setup_p2p(fb_context *c) {
   if (cudaMalloc(&vote, 2 * sizeof(int)) != cudaSuccess || cudaMalloc(&devH, sizeof(Handles) * (size_t)(d->world + 1)) != cudaSuccess ||
       cudaMalloc(&remoteScratch, sizeof(int) * (size_t)(nS + 1)) != cudaSuccess) {
     cudaGetLastError();
-    cudaFree(vote); cudaFree(devH); cudaFree(remoteScratch);
+    fb_dev_free(vote); fb_dev_free(devH); fb_dev_free(remoteScratch);
     fb_set_error("peer-memory setup: scratch allocation failed");
     return FB_ERR_OUT_OF_MEMORY;
   }
-  auto release = [&]() { cudaFree(vote); cudaFree(devH); cudaFree(remoteScratch); };
+  auto release = [&]() { fb_dev_free(vote); fb_dev_free(devH); fb_dev_free(remoteScratch); };
   {  // eligibility vote: all ranks take part, all ranks see the same answer
     int eligible = (d->world <= FB_MAX_RANKS && d->nNbr <= FB_MAX_NBR && c->use_rows3) ? 1 : 0, all = 0;
     cudaMemcpyAsync(vote, &eligible, sizeof(int), cudaMemcpyHostToDevice, st);
@@ -484,7 +484,7 @@ int fb_dist_refresh_rowmask(fb_context *c) {
   FB_CUDA(cudaMemcpyAsync(ownedDev, d->owned.data(), (size_t)c->nV, cudaMemcpyHostToDevice, c->stream));
   if (c->nV) { k_mask_ghost<<<(3 * c->nV + 255) / 256, 256, 0, c->stream>>>(c->nV, ownedDev, c->fixed, c->rowmask); c->launches++; }
   FB_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(ownedDev);
+  fb_dev_free(ownedDev);
   return FB_OK;
 }
 
@@ -524,19 +524,19 @@ int fb_dist_download_owned(fb_context *c, const double *localDev, double *g) {
 void fb_dist_destroy(fb_context *c) {
   FbDist *d = c->dist;
   if (!d) return;
-  if (d->sendIdx) cudaFree(d->sendIdx);
-  if (d->recvIdx) cudaFree(d->recvIdx);
-  if (d->sendBuf) cudaFree(d->sendBuf);
-  if (d->recvBuf) cudaFree(d->recvBuf);
+  if (d->sendIdx) fb_dev_free(d->sendIdx);
+  if (d->recvIdx) fb_dev_free(d->recvIdx);
+  if (d->sendBuf) fb_dev_free(d->sendBuf);
+  if (d->recvBuf) fb_dev_free(d->recvBuf);
   if (d->hostStage) cudaFreeHost(d->hostStage);
-  if (c->rowmask && c->rowmask != c->fixed) { cudaFree(c->rowmask); c->rowmask = nullptr; }
+  if (c->rowmask && c->rowmask != c->fixed) { fb_dev_free(c->rowmask); c->rowmask = nullptr; }
   for (int i = 0; i < d->nOpened; i++) cudaIpcCloseMemHandle(d->opened[i]);
-  if (d->comm) cudaFree(d->comm);
-  if (d->pushTicket) cudaFree(d->pushTicket);
-  if (d->remoteIdx) cudaFree(d->remoteIdx);
-  if (d->pushFlag) cudaFree(d->pushFlag);
-  if (d->pushPtr) cudaFree(d->pushPtr);
-  if (d->pushEnt) cudaFree(d->pushEnt);
+  if (d->comm) fb_dev_free(d->comm);
+  if (d->pushTicket) fb_dev_free(d->pushTicket);
+  if (d->remoteIdx) fb_dev_free(d->remoteIdx);
+  if (d->pushFlag) fb_dev_free(d->pushFlag);
+  if (d->pushPtr) fb_dev_free(d->pushPtr);
+  if (d->pushEnt) fb_dev_free(d->pushEnt);
   if (d->ncomm) ncclCommDestroy(d->ncomm);
   delete d;
   c->dist = nullptr;

@@ -51,6 +51,7 @@ struct FbDist;   // multi-GPU state (fb_dist.cu)
 struct FbBatch;  // a batch of independent meshes in one context (fb_batch.cu)
 struct FbSym;    // upper-triangle storage for the solver's products (fb_sym.cu)
 struct FbTma;    // row tiles for the bulk-copy staged products (fb_tma.cu)
+struct FbMg;     // labelled solver variants: block-Jacobi / multigrid preconditioned CG (fb_mg.cu)
 
 
 struct fb_context {
@@ -153,6 +154,10 @@ struct fb_context {
 
   int comm_poisoned;     // last solve returned FB_ERR_COMM: reset the last-block tickets before the next one
   FbDist *dist;
+  FbMg *mg;
+  int stream_borrowed;   // the stream belongs to another context (coarse levels of a multigrid hierarchy)
+  int uniform_material;  // created without per-element E / nu / density arrays
+  int have_solution;     // c->x holds the solution of a converged solve (warm start of the solver variants)
   FbBatch *batch;
   FbSym *sym;
   FbTma *tma;
@@ -189,6 +194,14 @@ int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, b
 int fb_pcg_bench_iteration(fb_context *c, int repeats, double *sec);
 int fb_spmv_plan(fb_context *c);  // call once after the block structure exists
 void fb_pcg_release(fb_context *c);
+int fb_pcg_launch_product_dq(fb_context *c, const double *d, double *q, int *nSlots);  // q = mask(Keff d), d.q partials in c->partials[0..nSlots)
+int fb_pcg_launch_residual(fb_context *c, const double *x, double *r);               // r = mask(rhs - Keff x)
+// ---- fb_mg.cu (labelled solver variants) ----------------------------------------------------------------------------------
+int fb_mg_active(const fb_context *c);   // 0, or the FB_SOLVER_* variant in use
+int fb_mg_prepare(fb_context *c);        // per step, after the assembly: coarse operators, FP32 copies, block inverses
+int fb_mg_pcg_solve(fb_context *c, double eps, int max_it);
+void fb_mg_invalidate(fb_context *c);    // constraints changed: the hierarchy is rebuilt at the next step
+void fb_mg_release(fb_context *c);
 // ---- fb_pcg_persistent.cu --------------------------------------------------------------------------
 int fb_pcg_plan_persistent(fb_context *c);
 int fb_pcg_launch_persistent(fb_context *c);
@@ -235,6 +248,12 @@ void fb_dist_push_args(fb_context *c, FbPushArgs *out, unsigned long long epoch)
 // (fb_create at 1M tets: 75-200 ms with cudaMalloc, profiles/r01_setup_time.txt).  fb_trim_memory() gives it back.
 // Buffers exported with CUDA IPC (peer-memory exchange) cannot live in a pool: fb_dev_alloc_plain.
 bool fb_use_pool();  // false with FEMBRAIN_B200_POOL=0: plain cudaMalloc for everything
+// Guard bands (FEMBRAIN_B200_GUARD=1; tests/test_guard_gpu.py): every pool allocation of a context is wrapped in two
+// 256-byte bands filled with 0xA5, and fb_check_guards() reports allocations whose bands were written to.  This is the
+// library's own out-of-bounds-write detector: compute-sanitizer is closed on the GPU pool this was developed on.
+bool fb_guard_enabled();
+cudaError_t fb_guard_alloc(void **p, size_t bytes, cudaStream_t st);
+void fb_dev_free(void *p);  // cudaFree, or the guarded allocation's base when p came from fb_guard_alloc
 template <typename T>
 static inline int fb_dev_alloc_plain(fb_context *c, T **p, size_t n) {
   size_t bytes = (n ? n : 1) * sizeof(T);
@@ -252,7 +271,7 @@ template <typename T>
 static inline int fb_dev_alloc(fb_context *c, T **p, size_t n) {
   size_t bytes = (n ? n : 1) * sizeof(T);
   if (!fb_use_pool()) return fb_dev_alloc_plain(c, p, n);
-  cudaError_t e = cudaMallocAsync((void **)p, bytes, c->stream);
+  cudaError_t e = fb_guard_enabled() ? fb_guard_alloc((void **)p, bytes, c->stream) : cudaMallocAsync((void **)p, bytes, c->stream);
   if (e != cudaSuccess) {
     cudaGetLastError();
     fb_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));

@@ -868,6 +868,17 @@ int fb_spmv_plan(fb_context *c) {
   return fb_pcg_plan_persistent(c);
 }
 
+// hooks for the solver variants (fb_mg.cu): the FP64 products of this file with their per-CTA sums left in c->partials
+int fb_pcg_launch_product_dq(fb_context *c, const double *d, double *q, int *nSlots) {
+  launch_spmv_mode<1>(c, c->Keff, d, q, c->rhs, nullptr);
+  *nSlots = c->grid_spmv[1];
+  return FB_OK;
+}
+int fb_pcg_launch_residual(fb_context *c, const double *x, double *r) {
+  launch_spmv_mode<2>(c, c->Keff, x, r, c->rhs, nullptr);
+  return FB_OK;
+}
+
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked) {
   (void)masked;
   if (c->nV == 0) return FB_OK;
@@ -884,6 +895,7 @@ void fb_pcg_release(fb_context *c) {
 // reference's return value: +iterations if converged, -iterations otherwise (CGSolver.cpp:189).
 int fb_pcg_solve(fb_context *c, double eps, int maxIt) {
   if (c->batch) return fb_batch_pcg_solve(c, eps, maxIt);
+  if (fb_mg_active(c)) return fb_mg_pcg_solve(c, eps, maxIt);   // labelled variants: same system, same stopping rule
   cudaStream_t st = c->stream;
   if (c->r == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
   c->nprof = 0;

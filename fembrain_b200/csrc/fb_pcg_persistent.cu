@@ -228,7 +228,7 @@ int fb_pcg_plan_persistent(fb_context *c) {
   if (grid > byRows) grid = byRows;
   if (grid > FB_MAX_PARTIALS) grid = FB_MAX_PARTIALS;
   if (grid < 1) grid = 1;
-  if (c->ctaRows) { cudaFree(c->ctaRows); c->ctaRows = nullptr; }
+  if (c->ctaRows) { fb_dev_free(c->ctaRows); c->ctaRows = nullptr; }
   FB_TRY(fb_dev_alloc(c, &c->ctaRows, (size_t)grid + 1));
   if (!c->pers_prof) {
     FB_TRY(fb_dev_alloc(c, &c->pers_prof, 2));

@@ -220,7 +220,7 @@ void fb_sym_release(fb_context *c) {
   if (!s) return;
   void *ptrs[] = {s->ubp, s->ubc, s->lbp, s->lmeta, s->U};
   for (void *p : ptrs)
-    if (p) cudaFree(p);
+    if (p) fb_dev_free(p);
   delete s;
   c->sym = nullptr;
 }

@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(TM_TB, 2) k_spmv_tma(int nTiles, const int4 *_
 void fb_tma_release(fb_context *c) {
   FbTma *t = c->tma;
   if (!t) return;
-  if (t->tiles) cudaFree(t->tiles);
-  if (t->err) cudaFree(t->err);
+  if (t->tiles) fb_dev_free(t->tiles);
+  if (t->err) fb_dev_free(t->err);
   delete t;
   c->tma = nullptr;
 }

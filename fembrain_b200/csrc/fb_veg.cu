@@ -394,8 +394,8 @@ int fb_export_positions_float4(fb_context *c, int count, const float *rest_xyzw,
   c->launches++;
   FB_CUDA(cudaMemcpyAsync(out_xyzw, dOut, sizeof(float4) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(dRest);
-  cudaFree(dOut);
+  fb_dev_free(dRest);
+  fb_dev_free(dOut);
   return FB_OK;
 }
 

@@ -57,8 +57,17 @@ typedef struct fb_params {
   double internal_force_scaling; /* 1.0  VEGA/integrator/integratorBase.cpp:46 */
   int device;                /* CUDA device ordinal, default 0 */
   int keep_raw_stiffness;    /* 0: K is consumed in registers; 1: also store raw K every step for fb_get_stiffness_values */
-  int reserved[6];
+  int solver_variant;        /* FB_SOLVER_JACOBI_PCG (0, default): the reference's solver.  See fb_set_solver */
+  int warm_start;            /* solver variants only: start PCG from the previous step's solution instead of 0 */
+  int reserved[4];
 } fb_params;
+
+/* Linear solver of the implicit step.  0 is the reference's algorithm and the parity path.  The others are LABELLED VARIANTS
+ * (not in the reference): the same system Keff dv = rhs, the same stopping rule (Jacobi-weighted residual
+ * sum r^2/diag <= eps^2 sum b^2/diag, CGSolver.cpp:147-150), a faster-converging preconditioner (fb_mg.cu). */
+#define FB_SOLVER_JACOBI_PCG 0        /* CGSolver::SolveLinearSystemWithJacobiPreconditioner, CGSolver.cpp:129-190 */
+#define FB_SOLVER_BLOCK_JACOBI_PCG 1  /* 3x3 block-diagonal preconditioner; any mesh */
+#define FB_SOLVER_MG_PCG 2            /* geometric multigrid V(1,1) preconditioner; meshes on a tensor grid (fb_set_grid) */
 
 typedef struct fb_context fb_context;
 
@@ -125,6 +134,15 @@ int fb_set_timestep(fb_context *ctx, double h);                        /* Integr
 int fb_set_damping(fb_context *ctx, double damping_mass, double damping_stiffness); /* SetDampingMassCoef / SetDampingStiffnessCoef */
 int fb_set_internal_force_scaling(fb_context *ctx, double s);          /* SetInternalForceScalingFactor */
 int fb_set_cg(fb_context *ctx, double epsilon, int max_iterations);
+/* Solver variants (single-mesh, single-GPU contexts).  fb_set_grid declares that the mesh's vertices are the nodes of an
+ * nx x ny x nz tensor grid numbered (i*ny + j)*nz + k, as VolMeshSamples::CreateTruthCube numbers them (any axis spacing; checked
+ * against the rest positions) — what FB_SOLVER_MG_PCG coarsens.  fb_set_solver selects the variant (FB_OK, or
+ * FB_ERR_NOT_SUPPORTED / FB_ERR_INVALID_ARGUMENT with the state unchanged); fb_last_cg_iterations / _residual_ratio then
+ * report the variant's iterations and its final weighted residual ratio.  fb_solve uses the selected solver too. */
+int fb_set_grid(fb_context *ctx, int nx, int ny, int nz);
+int fb_set_solver(fb_context *ctx, int variant, int warm_start);
+int fb_get_solver(const fb_context *ctx, int *variant, int *warm_start, int *levels);
+const char *fb_solver_name(int variant);
 
 /* ---- the step ---------------------------------------------------------------------------------
  * VolumeConservingIntegrator::DoTimestep (DEF/PS_VolumeConservingIntegrator.cpp:46-260), PCG branch,
@@ -208,6 +226,10 @@ size_t fb_device_bytes(const fb_context *ctx);           /* device memory held b
  * main.cpp:614-617, DEF/Deformable.cpp:127-220) does not pay for allocation again.  This gives unused pool memory
  * back to the driver. */
 int fb_trim_memory(void);
+/* Debug aid (environment FEMBRAIN_B200_GUARD=1 at process start): every device allocation of every context is wrapped in
+ * 256-byte guard bands; this call reports how many live allocations were checked and how many had a band overwritten (an
+ * out-of-bounds write by one of the library's kernels).  Always 0 / 0 when the guard mode is off. */
+int fb_check_guards(long long *checked, long long *corrupted);
 
 /* ---- inspection hooks for parity (outputs are host buffers sized by the fb_nnz_ / fb_num_ calls) -
  * CSR in the layout of SparseMatrix::GenerateCompressedRowMajorFormat (sparseMatrix.cpp:1151-1175). */

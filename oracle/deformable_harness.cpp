@@ -26,6 +26,12 @@
 
 #include <vector>
 
+/* the same wrapper is compiled twice: fbdef_* over the reference as it is (libfembrain_ref.so), fbdrop_* over the
+ * reference's Deformable.cpp compiled with the drop-in substitutions of stubs/prelude_dropin.h (libfembrain_dropin.so) */
+#ifndef FBDEF
+#define FBDEF(name) fbdef_##name
+#endif
+
 /* the two link-time leftovers of the GL tree (src/graphics/GLFuncs.cpp) and of the SQLite logger (DBLogger.cpp) */
 void DrawAABB(const PS::MATH::AABB &, const PS::MATH::vec3f &) {}
 void DrawAABB(const PS::MATH::vec3f &, const PS::MATH::vec3f &, const PS::MATH::vec3f &, float) {}
@@ -46,7 +52,7 @@ extern "C" {
 
 /* VolMesh::setup (src/deformable/VolMesh.cpp:139-163) + Deformable(const VolMesh&, const vector<int>&)
  * (src/deformable/Deformable.cpp:44-56 -> syncForceModel :127-220).  The collision object starts far below the mesh. */
-void *fbdef_create(int nV, const double *verts, int nT, const int *tets, int nFixed, const int *fixedVerts) {
+void *FBDEF(create)(int nV, const double *verts, int nT, const int *tets, int nFixed, const int *fixedVerts) {
   DefSim *s = new DefSim();
   s->mesh = new PS::MESH::VolMesh();
   std::vector<U32> el(tets, tets + 4 * (size_t)nT);
@@ -56,7 +62,13 @@ void *fbdef_create(int nV, const double *verts, int nT, const int *tets, int nFi
     return NULL;
   }
   std::vector<int> fv(fixedVerts, fixedVerts + nFixed);
-  s->def = new Deformable(*s->mesh, fv);
+  try {
+    s->def = new Deformable(*s->mesh, fv);
+  } catch (int) {  /* the drop-in build reports an unusable device this way (FEMBRAIN_B200_NO_EXIT) */
+    delete s->mesh;
+    delete s;
+    return NULL;
+  }
   s->def->setGravity(false);  /* Deformable::init (Deformable.cpp:84-123) leaves m_bApplyGravity uninitialised; main.cpp sets it */
   s->floor = new FloorNode();
   s->floor->transform()->translate(vec3f(0.0f, -1.0e30f, 0.0f));
@@ -65,7 +77,7 @@ void *fbdef_create(int nV, const double *verts, int nT, const int *tets, int nFi
   return s;
 }
 
-void fbdef_destroy(void *p) {
+void FBDEF(destroy)(void *p) {
   DefSim *s = (DefSim *)p;
   if (!s) return;
   delete s->def;
@@ -74,12 +86,12 @@ void fbdef_destroy(void *p) {
   delete s;
 }
 
-int fbdef_num_vertices(void *p) { return (int)((DefSim *)p)->def->m_lpVolMesh->countNodes(); }
-int fbdef_num_cells(void *p) { return (int)((DefSim *)p)->def->m_lpVolMesh->countCells(); }
-int fbdef_num_edges(void *p) { return (int)((DefSim *)p)->def->m_lpVolMesh->countEdges(); }
+int FBDEF(num_vertices)(void *p) { return (int)((DefSim *)p)->def->m_lpVolMesh->countNodes(); }
+int FBDEF(num_cells)(void *p) { return (int)((DefSim *)p)->def->m_lpVolMesh->countCells(); }
+int FBDEF(num_edges)(void *p) { return (int)((DefSim *)p)->def->m_lpVolMesh->countEdges(); }
 
 /* the mesh as Deformable holds it (its CuttableMesh copy): rest positions, cells, and the edge array in m_vEdges order */
-void fbdef_mesh(void *p, double *restpos, int *cells, int *edgesFromTo) {
+void FBDEF(mesh)(void *p, double *restpos, int *cells, int *edgesFromTo) {
   PS::CuttableMesh *m = ((DefSim *)p)->def->m_lpVolMesh;
   for (U32 i = 0; i < m->countNodes(); i++) {
     const vec3d r = m->const_nodeAt(i).restpos;
@@ -96,26 +108,26 @@ void fbdef_mesh(void *p, double *restpos, int *cells, int *edgesFromTo) {
 }
 
 /* VolMesh::get_node_neighbors (src/deformable/VolMesh.cpp:1346-1363), with its indexing quirk, as compiled */
-int fbdef_node_neighbors(void *p, int v, int capacity, int *out) {
+int FBDEF(node_neighbors)(void *p, int v, int capacity, int *out) {
   std::vector<U32> nb;
   U32 n = ((DefSim *)p)->def->m_lpVolMesh->get_node_neighbors((U32)v, nb);
   for (U32 i = 0; i < n && (int)i < capacity; i++) out[i] = (int)nb[i];
   return (int)n;
 }
 
-void fbdef_set_gravity(void *p, int on) { ((DefSim *)p)->def->setGravity(on != 0); }
-void fbdef_set_haptic_radius(void *p, int rings) { ((DefSim *)p)->def->setHapticForceRadius(rings); }
+void FBDEF(set_gravity)(void *p, int on) { ((DefSim *)p)->def->setGravity(on != 0); }
+void FBDEF(set_haptic_radius)(void *p, int rings) { ((DefSim *)p)->def->setHapticForceRadius(rings); }
 /* the collision object's transform: Deformable::timestep maps the origin through it and uses the y coordinate (a FLOAT) */
-void fbdef_set_floor(void *p, float y) {
+void FBDEF(set_floor)(void *p, float y) {
   DefSim *s = (DefSim *)p;
   s->floor->resetTransform();
   s->floor->transform()->translate(vec3f(0.0f, y, 0.0f));
   s->floor->transform()->syncMatrices();
 }
-float fbdef_floor_y(void *p) { return ((DefSim *)p)->floor->transform()->forward().map(vec3f(0, 0, 0)).y; }
+float FBDEF(floor_y)(void *p) { return ((DefSim *)p)->floor->transform()->forward().map(vec3f(0, 0, 0)).y; }
 
 /* hapticStart(index) / hapticSetCurrentForces / hapticEnd (src/deformable/Deformable.cpp:510-539, 712-717) */
-void fbdef_set_haptic(void *p, int n, const int *idx, const double *f3, int inProgress) {
+void FBDEF(set_haptic)(void *p, int n, const int *idx, const double *f3, int inProgress) {
   Deformable *d = ((DefSim *)p)->def;
   if (inProgress) d->hapticStart(n > 0 ? idx[0] : -1); else d->hapticEnd();
   std::vector<int> vi(idx, idx + n);
@@ -124,42 +136,42 @@ void fbdef_set_haptic(void *p, int n, const int *idx, const double *f3, int inPr
   d->hapticSetCurrentForces(vi, vf);
 }
 
-void fbdef_timestep(void *p) { ((DefSim *)p)->def->timestep(); }
+void FBDEF(timestep)(void *p) { ((DefSim *)p)->def->timestep(); }
 
-void fbdef_get_state(void *p, double *q, double *qvel, double *qacc) {
+void FBDEF(get_state)(void *p, double *q, double *qvel, double *qacc) {
   Deformable *d = ((DefSim *)p)->def;
   const size_t bytes = sizeof(double) * d->m_dof;
   if (q) memcpy(q, d->m_q, bytes);
   if (qvel) memcpy(qvel, d->m_qVel, bytes);
   if (qacc) memcpy(qacc, d->m_qAcc, bytes);
 }
-void fbdef_set_state(void *p, const double *q, const double *qvel) {
+void FBDEF(set_state)(void *p, const double *q, const double *qvel) {
   Deformable *d = ((DefSim *)p)->def;
   std::vector<double> zero(d->m_dof, 0.0);
   d->m_lpIntegrator->SetqState(q, qvel, &zero[0]);
 }
-void fbdef_get_external_forces(void *p, double *f) {
+void FBDEF(get_external_forces)(void *p, double *f) {
   Deformable *d = ((DefSim *)p)->def;
   memcpy(f, d->m_arrExtForces, sizeof(double) * d->m_dof);
 }
-int fbdef_contacts(void *p) { return (int)((DefSim *)p)->def->m_ctCollided; }
-void fbdef_set_contacts(void *p, int n) { ((DefSim *)p)->def->m_ctCollided = (U32)n; }
+int FBDEF(contacts)(void *p) { return (int)((DefSim *)p)->def->m_ctCollided; }
+void FBDEF(set_contacts)(void *p, int n) { ((DefSim *)p)->def->m_ctCollided = (U32)n; }
 /* node positions after VolMesh::displace (src/deformable/VolMesh.cpp:1370-1385) and the mesh AABB Deformable publishes */
-void fbdef_positions(void *p, double *pos) {
+void FBDEF(positions)(void *p, double *pos) {
   PS::CuttableMesh *m = ((DefSim *)p)->def->m_lpVolMesh;
   for (U32 i = 0; i < m->countNodes(); i++) {
     const vec3d x = m->const_nodeAt(i).pos;
     pos[3 * i] = x.x; pos[3 * i + 1] = x.y; pos[3 * i + 2] = x.z;
   }
 }
-void fbdef_aabb(void *p, float *lo3, float *hi3) {
+void FBDEF(aabb)(void *p, float *lo3, float *hi3) {
   const PS::MATH::AABB b = ((DefSim *)p)->def->aabb();
   lo3[0] = b.lower().x; lo3[1] = b.lower().y; lo3[2] = b.lower().z;
   hi3[0] = b.upper().x; hi3[1] = b.upper().y; hi3[2] = b.upper().z;
 }
 
 /* Deformable::pickVertices (src/deformable/Deformable.cpp:430-448) and ::pickVertex (:422-428) */
-int fbdef_pick_vertices(void *p, const double *lo, const double *hi, int capacity, int *indices, double *coords) {
+int FBDEF(pick_vertices)(void *p, const double *lo, const double *hi, int capacity, int *indices, double *coords) {
   std::vector<vec3d> c;
   std::vector<int> ix;
   int n = ((DefSim *)p)->def->pickVertices(vec3d(lo[0], lo[1], lo[2]), vec3d(hi[0], hi[1], hi[2]), c, ix);
@@ -169,7 +181,7 @@ int fbdef_pick_vertices(void *p, const double *lo, const double *hi, int capacit
   }
   return n;
 }
-int fbdef_pick_vertex(void *p, const double *w, double *dist, double *vertex) {
+int FBDEF(pick_vertex)(void *p, const double *w, double *dist, double *vertex) {
   DefSim *s = (DefSim *)p;
   vec3d v;
   double d = 0.0;
@@ -181,7 +193,7 @@ int fbdef_pick_vertex(void *p, const double *w, double *dist, double *vertex) {
 
 /* VolMeshSamples (src/deformable/VolMeshSamples.cpp:15-253): which = 0 one tetra, 1 two tetra, 2 truth cube (a,b,c = nx,ny,nz;
  * x = cellsize), 3 egg shell (a,b = hseg,vseg; x = radius, y = thickness).  First call with NULL outputs for the sizes. */
-int fbdef_sample_mesh(int which, int a, int b, int c, double x, double y, int *nV, int *nT, double *verts, int *cells) {
+int FBDEF(sample_mesh)(int which, int a, int b, int c, double x, double y, int *nV, int *nT, double *verts, int *cells) {
   PS::MESH::VolMesh *m = NULL;
   switch (which) {
     case 0: m = PS::MESH::VolMeshSamples::CreateOneTetra(); break;

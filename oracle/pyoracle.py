@@ -15,15 +15,16 @@ import sys
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBS = {"ref": os.path.join(_HERE, "_ref", "libfembrain_ref.so"), "port": os.path.join(_HERE, "libfembrain_port.so")}
+_LIBS = {"ref": os.path.join(_HERE, "_ref", "libfembrain_ref.so"), "port": os.path.join(_HERE, "libfembrain_port.so"),
+         "dropin": os.path.join(_HERE, "_ref", "libfembrain_dropin.so")}
 _PREFIX = {"ref": "fbref_", "port": "fbport_"}
 _loaded: dict = {}
 
 
 def build(kind: str, reference_root: str = "/root/reference") -> bool:
     """Build one checker with oracle/Makefile.  'ref' needs the reference tree (this container only)."""
-    if kind == "ref" and not os.path.isdir(reference_root):
-        return os.path.exists(_LIBS["ref"])
+    if kind in ("ref", "dropin") and not os.path.isdir(reference_root):
+        return os.path.exists(_LIBS[kind])
     subprocess.run(["make", "-C", _HERE, kind, f"REF={reference_root}", "-j8"], check=True, stdout=subprocess.DEVNULL)
     return os.path.exists(_LIBS[kind])
 
@@ -284,11 +285,21 @@ class Oracle:
 
 
 # -- the reference's own `class Deformable`, compiled (oracle/deformable_harness.cpp) ------------------------------------------
-def _def_lib():
-    lib = _lib("ref")
+def _def_lib(which="ref"):
+    """which = "ref": the compiled reference (fbdef_*); "dropin": the reference's Deformable.cpp compiled with the INTEGRATION.md
+    substitutions on top of libfembrain_b200.so (fbdrop_*, oracle/_ref/libfembrain_dropin.so; needs a GPU to create anything)."""
+    if which == "dropin":
+        if "dropin" not in _loaded:
+            if not os.path.exists(_LIBS["dropin"]):
+                raise FileNotFoundError(f"{_LIBS['dropin']} missing: run `make -C oracle dropin`")
+            _loaded["dropin"] = C.CDLL(_LIBS["dropin"])
+        lib = _loaded["dropin"]
+    else:
+        lib = _lib("ref")
     if getattr(lib, "_fbdef_bound", False):
         return lib
     vp, ci, cd, cf = C.c_void_p, C.c_int, C.c_double, C.c_float
+    pre = "fbdrop_" if which == "dropin" else "fbdef_"
     sig = {
         "fbdef_create": (vp, [ci, vp, ci, vp, ci, vp]), "fbdef_destroy": (None, [vp]),
         "fbdef_num_vertices": (ci, [vp]), "fbdef_num_cells": (ci, [vp]), "fbdef_num_edges": (ci, [vp]),
@@ -302,10 +313,15 @@ def _def_lib():
         "fbdef_sample_mesh": (ci, [ci, ci, ci, ci, cd, cd, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(lib, name)
+        fn = getattr(lib, pre + name[len("fbdef_"):])
         fn.restype, fn.argtypes = res, args
+        setattr(lib, name, fn)   # both libraries are driven through the fbdef_* names below
     lib._fbdef_bound = True
     return lib
+
+
+def dropin_available() -> bool:
+    return os.path.exists(_LIBS["dropin"])
 
 
 def _libc_fflush():
@@ -344,8 +360,10 @@ class RefDeformable:
     checker for Deformable::timestep, applyHapticForces, the floor post-step, pickVertices / pickVertex and the
     get_node_neighbors quirk.  Material, time step, damping and CG settings are the ones Deformable hard-codes."""
 
-    def __init__(self, verts, tets, fixed_verts=()):
-        self._lib = _def_lib()
+    def __init__(self, verts, tets, fixed_verts=(), lib="ref"):
+        """lib="dropin": the same reference class compiled with its integrator and force model replaced by the CUDA-backed
+        subclasses of include/fembrain_b200_vega_classes.hpp (oracle/stubs/prelude_dropin.h)."""
+        self._lib = _def_lib(lib)
         v, t, fx = _f64(verts).reshape(-1, 3), _i32(tets).reshape(-1, 4), _i32(fixed_verts)
         # CuttableMesh's setup runs the reference's mesh self-tests, which print to stdout (test_VolMesh.cpp): keep them off it
         sys.stdout.flush()
@@ -359,7 +377,7 @@ class RefDeformable:
             os.close(saved)
             os.close(null)
         if not self._h:
-            raise RuntimeError("reference VolMesh::setup failed")
+            raise RuntimeError("reference VolMesh::setup failed" if lib == "ref" else "drop-in Deformable could not be created (no usable GPU?)")
         self.nV, self.nT = self._lib.fbdef_num_vertices(self._h), self._lib.fbdef_num_cells(self._h)
         self.r = 3 * self.nV
 

@@ -173,3 +173,46 @@ def test_assembly_variants_identical_on_a_cube(port_oracle, env, monkeypatch):
         s.set_state(u, np.zeros_like(u))
         assert s.do_timestep() == 0
     assert np.array_equal(sim.K_values(), ora.K_values()) and np.array_equal(sim.rhs(), ora.rhs())
+
+
+def polar_edge_states(v, t):
+    """Displacements that drive chosen tets through the two special branches of the rotation extraction:
+    det(F) < 0 -> R = -R (corotationalLinearFEM.cpp:264-268) and det == 0 -> the Newton loop breaks with the warning
+    (polarDecomposition.cpp:63-67).  'inverted': vertex 3 of tet 0 mirrored through the plane of its other three vertices;
+    'flat': the same vertex moved INTO that plane, so the deformed tet has exactly zero volume (x-aligned coordinates make
+    the determinant exactly 0.0 in floating point)."""
+    out = {}
+    a, b, c, d = (v[t[0, k]] for k in range(4))
+    n = np.cross(b - a, c - a)
+    n /= np.linalg.norm(n)
+    h = float(np.dot(d - a, n))
+    u = np.zeros_like(v)
+    u[t[0, 3]] = -2.0 * h * n
+    out["inverted"] = u.reshape(-1).copy()
+    u[t[0, 3]] = -1.0 * h * n
+    out["flat"] = u.reshape(-1).copy()
+    # every vertex of the mesh squashed onto the plane y = 0: ALL tets flat (what the floor snap does to a layer of the mesh)
+    u = np.zeros_like(v)
+    u[:, 1] = -v[:, 1]
+    out["all_flat"] = u.reshape(-1).copy()
+    # the whole mesh mirrored (x -> -x): every tet inverted
+    u = np.zeros_like(v)
+    u[:, 0] = -2.0 * v[:, 0]
+    out["all_inverted"] = u.reshape(-1).copy()
+    return out
+
+
+@pytest.mark.parametrize("name", ["one_tetra", "two_tetra", "cube3"])
+def test_polar_edge_branches_bit_exact(port_oracle, name):
+    """Aimed at the det < 0 and det == 0 branches (a9): K and f stay bit-identical to the oracle, NaNs included where the
+    reference itself produces them (a zero determinant divides by zero in the next Newton step of a DIFFERENT element only
+    if that element is degenerate; here the loop breaks and R is whatever the iteration held)."""
+    v, t, fixed = CASES[name]()
+    sim, ora = _mk(port_oracle, v, t, fixed)
+    for label, u in polar_edge_states(v, t).items():
+        f, K = sim.force_and_matrix(u)
+        of, oK = ora.force_and_matrix(u)
+        assert np.array_equal(K, oK, equal_nan=True), f"{name}/{label}: K"
+        assert np.array_equal(f, of, equal_nan=True), f"{name}/{label}: f"
+        if label == "inverted":
+            assert np.isfinite(oK).all() and not np.array_equal(oK, ora.force_and_matrix(np.zeros_like(u))[1])

@@ -15,6 +15,8 @@ Every line also carries, measured in the same run:
   config5_50M   CreateTruthCube(204) = 50,192,562 tets on the same N GPUs (BASELINE.json configs[4])
   config4_batch 32 independent 196,608-tet meshes per GPU in one batch context per GPU (configs[3]; N = 8: the 256 meshes)
   config2_1M    (N = 1) the 998,250-tet cube of configs[1]
+  solver_variant (N = 1) the headline mesh again with the LABELLED multigrid-preconditioned CG variant (not the reference's
+                algorithm; same system, same stopping rule), side by side with the parity path's iterations and ms/step
   cpu_baseline  (N = 1) the unmodified reference's DoTimestep on the host, bounded sample
 `--replicas` restores round 1's N > 1 behaviour (every rank steps its own copy: weak scaling, no communication).
 
@@ -537,6 +539,60 @@ def batch_block(env, per_gpu, steps, warmup, nx=33):
                          "frac": b_s / m_s / 1e9 / peak if m_s > 0 else None, "samples": n_s, "traffic": ncu_table(f"batch{per_gpu}x{nx}", "spmv_bytes_per_launch")}}
 
 
+def variant_block(env, nx, steps, warmup, parity_iters, parity_ms, q_parity_end):
+    """The labelled solver variant on the headline mesh (single GPU): FB_SOLVER_MG_PCG — the same Keff and rhs, the same
+    stopping rule, a multigrid-preconditioned CG instead of the reference's Jacobi-PCG (fembrain_b200/csrc/fb_mg.cu).  Same
+    K steps from rest, resident and end to end; the final displacement is compared with the parity path's (both stop at
+    eps = 1e-6 of the same weighted residual, on different Krylov paths)."""
+    fb = env.fb
+    v, t, fixed, f = workload(nx)
+    nT, r = len(t), 3 * len(v)
+    t0 = time.perf_counter()
+    sim = fb.Simulation(v, t, fixed, device=env.local)
+    sim.set_grid(nx)
+    sim.set_solver("mg")
+    t_setup = time.perf_counter() - t0
+    st = Stepper(env, sim, f, False, t)
+    sim.reset_to_rest()
+    _, it_warm, _, _ = st.region(warmup, False)
+    sec, iters, t_asm, t_solve = st.region(steps, False)
+    q_end = st.owned_q()
+    sim.reset_to_rest()
+    st.region(warmup, True)
+    sec_e2e, iters_e2e, _, _ = st.region(steps, True)
+    info = sim.solver()
+    nb64 = sim.nnz_K // 9
+    # algorithmic bytes of ONE iteration (nu = 1): the FP64 product + update + direction on the finest level, and per level of
+    # the cycle two FP16 products (28 B per block + per vertex: row pointer 4, x 16, b 16, out 16, Binv 36 in the smoothing
+    # product), pre-smoothing (68 B/vertex), restriction / prolongation (48 B per fine vertex + 32 B per coarse vertex)
+    b_outer = 8.0 * 9 * nb64 + 4.0 * nb64 + 52.0 * (r / 3) + (61.0 + 21.0) * r
+    b_cycle = 0.0
+    lv, lb = info["level_vertices"], info["level_blocks"]
+    for k in range(len(lv) - 1):
+        b_cycle += 2 * (28.0 * lb[k] + 52.0 * lv[k]) + 36.0 * lv[k] + 68.0 * lv[k] + 48.0 * lv[k] + 32.0 * lv[k + 1]
+    b_iter = b_outer + b_cycle
+    peak, _ = measured_peak_gbs()
+    sim.close()
+    out = {
+        "solver": info["name"], "levels": info["levels"], "level_vertices": lv,
+        "value": steps / sec, "unit": UNIT, "ms_per_step": 1e3 * sec / steps, "steps": steps, "warmup": warmup,
+        "e2e": {"value": steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": st.h2d, "d2h_bytes_per_step": st.d2h,
+                "same_iterations_as_resident": iters_e2e == iters},
+        "cg_iterations_per_step": iters, "cg_iterations_warmup": it_warm,
+        "parity_path_iterations_per_step": parity_iters, "parity_path_ms_per_step": parity_ms,
+        "speedup_vs_parity_path": parity_ms / (1e3 * sec / steps),
+        "ms_per_iteration": 1e3 * t_solve / max(sum(iters), 1), "solve_share_of_step": t_solve / sec, "assembly_share_of_step": t_asm / sec,
+        "setup_seconds": t_setup,
+        "roofline_iteration": {"bound": "hbm", "algorithmic_bytes_per_iteration": b_iter, "achieved": b_iter * sum(iters) / t_solve / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": b_iter * sum(iters) / t_solve / 1e9 / peak,
+                               "note": "whole solve time (cycle set-up included) over iterations x modelled bytes; phases per iteration in profiles/r02_mg_iteration_phases.txt"},
+        "final_displacement_rel_diff_vs_parity_path": float(np.abs(q_end - q_parity_end).max() / np.abs(q_parity_end).max()),
+        "contract": "same Keff and rhs (bit-identical assembly), same stopping rule sum r^2/diag <= eps^2 sum b^2/diag with eps = 1e-6; "
+                    "tests/test_solver_variants_gpu.py: <= 1e-8 of the oracle after both converge to eps = 1e-12",
+    }
+    return out
+
+
 def run_ours(args):
     env = Env()
     world, rank = env.world, env.rank
@@ -578,6 +634,7 @@ def run_ours(args):
         finally:
             if ref is not None:
                 ref.close()
+    q_parity_end = sim.get_state_owned()[0] if world == 1 else None
     sim.close()
     env.fb.trim_memory()
 
@@ -596,6 +653,11 @@ def run_ours(args):
             line[name] = out
         env.fb.trim_memory()
         return ok
+
+    # ---- the labelled faster-converging solver variant on the headline mesh (single GPU) -----------------------------------
+    if world == 1 and not args.no_variant:
+        guarded("solver_variant", lambda: variant_block(env, nx, args.steps, args.warmup, main["cg_iterations_per_step"], main["ms_per_step"],
+                                                        q_parity_end))
 
     # ---- configs[4]: 50M tets on the same GPUs -------------------------------------------------------------------------
     if not args.no_50m:
@@ -693,6 +755,7 @@ def _main(saved_stdout):
     ap.add_argument("--steps-batch", type=int, default=3)
     ap.add_argument("--warmup-batch", type=int, default=1)
     ap.add_argument("--no-1m", action="store_true")
+    ap.add_argument("--no-variant", action="store_true", help="skip the solver_variant block (multigrid-preconditioned CG on the headline mesh)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-nx", type=int, default=40, help="cube resolution of the bounded cpu_baseline sample (40 = 355,914 tets)")
     ap.add_argument("--ref-budget-s", type=float, default=780.0, help="--impl reference: wall-clock budget for the whole run")
@@ -700,7 +763,7 @@ def _main(saved_stdout):
     ap.add_argument("--quick", action="store_true", help="headline mesh only (no 50M / batch / 1M / cpu blocks)")
     args = ap.parse_args()
     if args.quick:
-        args.no_50m = args.no_batch = args.no_1m = args.no_cpu_baseline = True
+        args.no_50m = args.no_batch = args.no_1m = args.no_cpu_baseline = args.no_variant = True
     if args.warmup < 3 and args.impl == "ours":
         print("note: timing rules ask for >= 3 warm-up steps", file=sys.stderr)
     args.emit = lambda line: emit(saved_stdout, line)

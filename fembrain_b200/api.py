@@ -92,6 +92,7 @@ def load_library():
         "fb_set_internal_force_scaling": (ci, [vp, cd]), "fb_set_cg": (ci, [vp, cd, ci]),
         "fb_set_grid": (ci, [vp, ci, ci, ci]), "fb_set_solver": (ci, [vp, ci, ci]),
         "fb_get_solver": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]), "fb_solver_name": (C.c_char_p, [ci]),
+        "fb_get_solver_levels": (ci, [vp, ci, vp, vp]),
         "fb_step": (ci, [vp]),
         "fb_deformable_timestep": (ci, [vp]), "fb_deformable_set_gravity": (ci, [vp, ci]),
         "fb_deformable_set_floor": (ci, [vp, ci, cd]),
@@ -468,7 +469,10 @@ class Simulation:
     def solver(self):
         v, w, lv = C.c_int(0), C.c_int(0), C.c_int(0)
         self._check(self._lib.fb_get_solver(self._h, C.byref(v), C.byref(w), C.byref(lv)), "fb_get_solver")
-        return {"variant": v.value, "name": self._lib.fb_solver_name(v.value).decode(), "warm_start": bool(w.value), "levels": lv.value}
+        nv, nb = np.zeros(max(lv.value, 1), np.int32), np.zeros(max(lv.value, 1), np.int64)
+        self._check(self._lib.fb_get_solver_levels(self._h, lv.value, _ptr(nv), _ptr(nb)), "fb_get_solver_levels")
+        return {"variant": v.value, "name": self._lib.fb_solver_name(v.value).decode(), "warm_start": bool(w.value), "levels": lv.value,
+                "level_vertices": [int(x) for x in nv[:lv.value]], "level_blocks": [int(x) for x in nb[:lv.value]]}
 
     def set_timestep(self, h):
         self._check(self._lib.fb_set_timestep(self._h, h), "fb_set_timestep")

@@ -16,8 +16,11 @@
 //       transfer   trilinear interpolation P (3x3 identity blocks) and restriction P^T, constrained DOFs masked on both sides;
 //       smoother   damped 3x3-block Jacobi, omega = 1.4 / lambda_max(B^-1 A) (power iteration, refreshed every 32 solves);
 //       coarsest   explicit dense inverse (<= 81 unknowns), rebuilt every step;
-//       precision  the whole cycle runs in FP32 on an FP32 copy of each level's Keff (4.4 instead of 8.4 bytes per
-//                  nonzero streamed); the outer CG — A d, the dot products, x, r, d — stays FP64 on the FP64 Keff.
+//       precision  the whole cycle runs in FP32 arithmetic on a reduced-precision copy of each level's Keff: FP16 values
+//                  (default; scaled by a power of two per level so that the largest diagonal entry sits near 2^13) or FP32
+//                  (FEMBRAIN_B200_MG_PREC=fp32), 3x3 blocks padded to 3x4 so that one lane loads one block with three
+//                  8-byte (16-byte) loads and one float4 of x — 28 (52) instead of 76 bytes per block streamed;
+//                  the outer CG — A d, the dot products, x, r, d — stays FP64 on the FP64 Keff.
 //   The cycle is a fixed symmetric positive definite linear operator (same pre/post smoother, R = P^T), so plain PCG applies.
 //   Iteration counts are mesh independent (CPU prototype on the reference's matrices: 34 at 16^3, 24^3 and 32^3 nodes
 //   where Jacobi-PCG needs 558 / 691 / 728).
@@ -31,12 +34,30 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "fb_internal.h"
 #include "fb_pcg_common.cuh"
 
 namespace {
 
+// developer aid (FEMBRAIN_B200_MG_TIMING=1): CUDA events between the phases of ONE iteration per solve, printed to stderr
+struct MgTiming {
+  bool on, armed;
+  cudaEvent_t ev[16];
+  int n;
+  const char *name[16];
+};
+MgTiming g_tm = {false, false, {}, 0, {}};
+void tm_mark(cudaStream_t st, const char *what) {
+  if (!g_tm.armed || g_tm.n >= 16) return;
+  if (!g_tm.ev[g_tm.n]) cudaEventCreate(&g_tm.ev[g_tm.n]);
+  cudaEventRecord(g_tm.ev[g_tm.n], st);
+  g_tm.name[g_tm.n++] = what;
+}
+
 constexpr int MG_TB = 256;
+constexpr int VS = 4;   // floats per vertex in the FP32 level vectors: (x, y, z, 0) so that a lane fetches a vertex with one float4 load
 constexpr int MG_MAX_LEVELS = 12;
 constexpr int MG_MAX_DENSE = 96;   // unknowns of the coarsest level's dense inverse
 constexpr int MG_SLOTS = FB_MAX_PARTIALS;
@@ -44,7 +65,9 @@ constexpr int MG_SLOTS = FB_MAX_PARTIALS;
 struct MgLevel {
   fb_context *ctx;
   int n[3], nV, r;
-  float *A32, *Binv, *b, *x, *xn, *res, *pv;
+  void *AB;                  // [nB][3][4] blocks of Keff, __half or float (padded rows), scaled by scale[0]
+  float *scale;              // device [2]: power-of-two scale of AB and its inverse; [2] = bits of the running min of 1/diag
+  float *Binv, *b, *x, *xn, *res, *pv;
   double *u;                 // levels > 0: displacement injected from the finest level
   int nc[3];                 // node counts of the next coarser level (0 = this is the coarsest)
   int *cidx[3];              // device [nc]: fine index of every coarse node, per axis
@@ -66,6 +89,8 @@ struct FbMg {
   float *denseInv;           // [n*n] fp32 copy of the inverse
   int nDense;
   double *slotsM, *slotsZ;   // per-CTA partial sums: weighted residual, r.z
+  int nu;                    // smoothing sweeps before and after the coarse correction
+  int half;                  // 1: FP16 storage of the levels' matrices (default), 0: FP32
   int solves;                // since the last lambda_max estimate
   int prepared;
   long long vcycles;
@@ -73,9 +98,55 @@ struct FbMg {
 
 namespace {
 
-// ---- FP32 copies of a level's operator --------------------------------------------------------------------------------
-__global__ void k_mg_convert(size_t n, const double *__restrict__ a, float *__restrict__ o) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) o[i] = (float)a[i];
+// ---- reduced-precision copy of a level's operator ----------------------------------------------------------------------
+// scale[0] = 2^e with max diag * 2^e in [2^13, 2^14) (FP16 storage; 1 for FP32), scale[1] = 2^-e; the minimum of 1/diag over
+// the unconstrained DOFs is taken with an integer atomicMin on the bits of the positive floats (order independent)
+__global__ void __launch_bounds__(MG_TB) k_mg_scale_min(size_t n, const double *__restrict__ invD, unsigned int *bits) {
+  float m = __int_as_float(0x7f800000);
+  for (size_t i = (size_t)blockIdx.x * MG_TB + threadIdx.x; i < n; i += (size_t)gridDim.x * MG_TB) {
+    const float w = (float)invD[i];
+    if (w > 0.f) m = fminf(m, w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(bits, __float_as_uint(m));
+}
+__global__ void k_mg_scale_final(float *scale, int half) {
+  unsigned int *bits = reinterpret_cast<unsigned int *>(scale + 2);
+  const float minInv = __uint_as_float(*bits);
+  float s = 1.f;
+  if (half && minInv > 0.f && minInv < __int_as_float(0x7f800000)) {
+    int e;
+    frexpf(1.f / minInv, &e);        // max diag = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 14 - e);         // max diag * s in [2^13, 2^14)
+  }
+  scale[0] = s;
+  scale[1] = 1.f / s;
+  *bits = 0x7f800000u;
+}
+
+template <typename T> __device__ __forceinline__ T mg_store(float v);
+template <> __device__ __forceinline__ float mg_store<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half mg_store<__half>(float v) { return __float2half_rn(v); }
+
+// Row v with nb blocks owns 12 nb entries at 12 bp[v]: THREE PLANES of nb x 4 entries, plane k = row k of every block
+// (entry (j, k, l) at 12 bp[v] + k * 4 nb + 4 j + l, l = 3 is padding).  The 16 lanes of a row then read 16 x 8 (16) contiguous
+// bytes per load instruction — one or two L1 wavefronts instead of the four of a block-major layout.  One thread per block.
+template <typename T>
+__global__ void __launch_bounds__(MG_TB) k_mg_pack(int nB, const int *__restrict__ bp, const int *__restrict__ brow, const double *__restrict__ A,
+                                                   const float *__restrict__ scale, T *__restrict__ AB) {
+  const float s = scale[0];
+  for (size_t b = (size_t)blockIdx.x * MG_TB + threadIdx.x; b < (size_t)nB; b += (size_t)gridDim.x * MG_TB) {
+    const int v = brow[b], rs = bp[v], nb = bp[v + 1] - rs, j = (int)b - rs;
+    const double *a = A + 9 * (size_t)rs + 3 * j;
+    T *o = AB + 12 * (size_t)rs + 4 * j;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+      for (int l = 0; l < 3; l++) o[(size_t)k * 4 * nb + l] = mg_store<T>((float)(a[(size_t)k * 3 * nb + l] * (double)s));
+      o[(size_t)k * 4 * nb + 3] = mg_store<T>(0.f);
+    }
+  }
 }
 
 // inverse of the 3x3 diagonal block of every vertex, constrained DOFs decoupled (their rows and columns of the inverse are 0)
@@ -108,64 +179,125 @@ __global__ void k_mg_block_inverse(int nV, const int *__restrict__ bp, const int
     for (int l = 0; l < 3; l++) Binv[9 * (size_t)v + 3 * k + l] = (fx[k] || fx[l]) ? 0.0f : (float)inv[k][l];
 }
 
-// ---- the FP32 product: 16 lanes per block row, three unrolled passes (rows of the tet stencil hold <= 16 blocks) --------
+// one 3x3 block = one 8-byte (__half) or 16-byte (float) word from each of the three planes of its block row
+template <typename T> struct MgRaw;
+template <> struct MgRaw<__half> { typedef uint2 type; };
+template <> struct MgRaw<float> { typedef float4 type; };
+__device__ __forceinline__ void mg_unpack(const uint2 &w, float &a0, float &a1, float &a2) {
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+  a0 = lo.x; a1 = lo.y; a2 = hi.x;
+}
+__device__ __forceinline__ void mg_unpack(const float4 &w, float &a0, float &a1, float &a2) { a0 = w.x; a1 = w.y; a2 = w.z; }
+
+// ---- the product of the cycle: 16 lanes per block row, ONE LANE PER 3x3 BLOCK, two block rows per trip, software pipelined --
+// A lane fetches its block (three 8/16-byte words), the block's column and that vertex of x (one float4).  A trip's loads form
+// a chain of three dependent round trips (row pointer -> column -> x); un-pipelined, that chain — not DRAM, not the L1
+// wavefront rate — set the pace: 270-300 us per product at 10M tets for 0.73 GB (FP16), as slow as the 2 GB FP64 product
+// (profiles/r02_mg_iteration_phases.txt).  Here the row pointers are fetched two trips ahead and columns + blocks one trip
+// ahead, so a trip waits for one round trip (the x gather) only.
 // MODE 0: out = mask(b - A x)
 // MODE 1: out = x + omega * Binv (b - A x)      [DOT: also sum b . out into slots]
 // MODE 2: out = Binv (A x)                       (power iteration)
-template <int MODE, bool DOT>
+template <typename T, int MODE, bool DOT>
 __global__ void __launch_bounds__(MG_TB, 4) k_mg_spmv(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
-                                                     const float *__restrict__ A, const float *__restrict__ x,
-                                                     const float *__restrict__ b, const float *__restrict__ Binv,
-                                                     const unsigned char *__restrict__ mask, float omega, float *__restrict__ out,
-                                                     double *slots, const FbScalars *sc) {
+                                                     const T *__restrict__ AB, const float *__restrict__ scale,
+                                                     const float *__restrict__ x, const float *__restrict__ b,
+                                                     const float *__restrict__ Binv, const unsigned char *__restrict__ mask, float omega,
+                                                     float *__restrict__ out, double *slots, const FbScalars *sc) {
+  typedef typename MgRaw<T>::type Raw;
   pdl_wait();
   pdl_trigger();
   if (sc && sc->done) return;
+  const float inv = __ldg(scale + 1);
   const int lane = threadIdx.x & 15;
   const unsigned gmask = 0xffffu << (threadIdx.x & 16);
   const int group = blockIdx.x * (MG_TB / 16) + threadIdx.x / 16;
-  const int nGroups = gridDim.x * (MG_TB / 16);
+  const int stride = 2 * gridDim.x * (MG_TB / 16);
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  const Raw *AR = reinterpret_cast<const Raw *>(AB);
   double part = 0.0;
-  // TWO block rows per trip: a 4-byte load moves half of what the FP64 product's loads move, so twice as many have to be in
-  // flight per lane to keep the same number of bytes in flight per SM (one row per trip ran at 4.1 TB/s, profiles/r02_mg_*)
-  for (int v0 = 2 * group; v0 < nV; v0 += 2 * nGroups) {
-    int rs[2], n3[2];
-    float acc[2][3];
+  // pipeline registers: [0] = this trip, [1] = next trip, per row h of the pair
+  int rs[2][2], nb[2][2], col[2];
+  Raw raw[2][3];
+  auto load_ptrs = [&](int v0, int slot) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int v = v0 + h;
-      rs[h] = 0; n3[h] = 0;
-      if (v < nV) { rs[h] = __ldg(bp + v); n3[h] = 3 * (__ldg(bp + v + 1) - rs[h]); }
-      acc[h][0] = acc[h][1] = acc[h][2] = 0.f;
+      rs[slot][h] = 0; nb[slot][h] = 0;
+      if (v < nV) { rs[slot][h] = __ldg(bp + v); nb[slot][h] = __ldg(bp + v + 1) - rs[slot][h]; }
     }
-    const int nmax = max(n3[0], n3[1]);
-    for (int base = 0; base < nmax; base += 48) {
-      float val[2][3][3];
-      int col[2][3];
+  };
+  auto load_blocks = [&](int slot) {   // first 16 blocks of both rows of the pair in `slot`
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const float *a0 = A + 9 * (size_t)rs[h];
+    for (int h = 0; h < 2; h++) {
+      col[h] = -1;
+      if (lane < nb[slot][h]) {
+        col[h] = __ldg(bc + rs[slot][h] + lane);
+        const Raw *p = AR + 3 * (size_t)rs[slot][h] + lane;
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
-          const int t = base + lane + 16 * p;
-          const bool ok = t < n3[h];
-          col[h][p] = ok ? __ldg(bc + rs[h] + t / 3) : -1;
-          val[h][p][0] = ok ? __ldcs(a0 + t) : 0.f;
-          val[h][p][1] = ok ? __ldcs(a0 + n3[h] + t) : 0.f;
-          val[h][p][2] = ok ? __ldcs(a0 + 2 * (size_t)n3[h] + t) : 0.f;
+        for (int k = 0; k < 3; k++) raw[h][k] = __ldcs(p + (size_t)k * nb[slot][h]);
+      }
+    }
+  };
+  int v0 = 2 * group;
+  load_ptrs(v0, 0);
+  load_ptrs(v0 + stride, 1);
+  load_blocks(0);
+  for (; v0 < nV; v0 += stride) {
+    // this trip's operands are in flight or have arrived; start the gather of x, which depends on col only
+    float4 xv[2];
+    float a[2][3][3];
+    int nbc[2], rsc[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      rsc[h] = rs[0][h]; nbc[h] = nb[0][h];
+      xv[h] = (col[h] >= 0) ? __ldg(x4 + col[h]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        a[h][k][0] = a[h][k][1] = a[h][k][2] = 0.f;
+        if (col[h] >= 0) mg_unpack(raw[h][k], a[h][k][0], a[h][k][1], a[h][k][2]);
+      }
+    }
+    // the finishing lanes' own operands (independent of everything above)
+    const int hh = lane >> 3, kk = lane & 7;
+    const int vf = v0 + hh;
+    const bool fin = kk < 3 && vf < nV;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bi0 = 0.f, bi1 = 0.f, bi2 = 0.f, xr = 0.f;
+    unsigned char mk = 0;
+    if (fin) {
+      if (MODE != 2) bv = *reinterpret_cast<const float4 *>(b + VS * (size_t)vf);
+      if (MODE == 0) mk = mask[3 * (size_t)vf + kk];
+      if (MODE != 0) {
+        const float *bi = Binv + 9 * (size_t)vf + 3 * kk;
+        bi0 = bi[0]; bi1 = bi[1]; bi2 = bi[2];
+      }
+      if (MODE == 1) xr = x[VS * (size_t)vf + kk];
+    }
+    // next trip: columns + blocks (its row pointers arrived a trip ago); the trip after: row pointers
+    rs[0][0] = rs[1][0]; rs[0][1] = rs[1][1]; nb[0][0] = nb[1][0]; nb[0][1] = nb[1][1];
+    load_blocks(0);
+    load_ptrs(v0 + 2 * stride, 1);
+    float acc[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) acc[h][k] = fmaf(a[h][k][0], xv[h].x, fmaf(a[h][k][1], xv[h].y, a[h][k][2] * xv[h].z));
+    // rows with more than 16 blocks (never on the tet stencil of a tensor grid): the rest, un-pipelined
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+      for (int j = 16 + lane; j < nbc[h]; j += 16) {
+        const int c2 = __ldg(bc + rsc[h] + j);
+        const float4 x2 = __ldg(x4 + c2);
+        const Raw *p = AR + 3 * (size_t)rsc[h] + j;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          float a0, a1, a2;
+          mg_unpack(__ldcs(p + (size_t)k * nbc[h]), a0, a1, a2);
+          acc[h][k] = fmaf(a0, x2.x, fmaf(a1, x2.y, fmaf(a2, x2.z, acc[h][k])));
         }
       }
-#pragma unroll
-      for (int h = 0; h < 2; h++)
-#pragma unroll
-        for (int p = 0; p < 3; p++) {
-          const int t = base + lane + 16 * p;
-          const float xv = (col[h][p] >= 0) ? __ldg(x + 3 * (size_t)col[h][p] + (t % 3)) : 0.f;
-          acc[h][0] = fmaf(val[h][p][0], xv, acc[h][0]);
-          acc[h][1] = fmaf(val[h][p][1], xv, acc[h][1]);
-          acc[h][2] = fmaf(val[h][p][2], xv, acc[h][2]);
-        }
-    }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
@@ -175,26 +307,22 @@ __global__ void __launch_bounds__(MG_TB, 4) k_mg_spmv(int nV, const int *__restr
         acc[h][2] += __shfl_xor_sync(gmask, acc[h][2], o, 16);
       }
     // lanes 0-2 finish row v0, lanes 8-10 row v0 + 1
-    const int h = lane >> 3, k = lane & 7;
-    const int v = v0 + h;
-    if (k < 3 && v < nV) {
-      const float a0v = h ? acc[1][0] : acc[0][0], a1v = h ? acc[1][1] : acc[0][1], a2v = h ? acc[1][2] : acc[0][2];
-      const size_t row = 3 * (size_t)v + k;
+    if (fin) {
+      const float a0v = inv * (hh ? acc[1][0] : acc[0][0]), a1v = inv * (hh ? acc[1][1] : acc[0][1]), a2v = inv * (hh ? acc[1][2] : acc[0][2]);
+      const size_t row = VS * (size_t)vf + kk;
       if (MODE == 0) {
-        const float ax = k == 0 ? a0v : (k == 1 ? a1v : a2v);
-        out[row] = mask[row] ? 0.f : (b[row] - ax);
+        const float ax = kk == 0 ? a0v : (kk == 1 ? a1v : a2v);
+        const float bk = kk == 0 ? bv.x : (kk == 1 ? bv.y : bv.z);
+        out[row] = mk ? 0.f : (bk - ax);
       } else {
-        float r0, r1, r2;
-        if (MODE == 1) {
-          r0 = b[3 * (size_t)v] - a0v; r1 = b[3 * (size_t)v + 1] - a1v; r2 = b[3 * (size_t)v + 2] - a2v;
-        } else {
-          r0 = a0v; r1 = a1v; r2 = a2v;
-        }
-        const float *bi = Binv + 9 * (size_t)v + 3 * k;
-        const float corr = fmaf(bi[0], r0, fmaf(bi[1], r1, bi[2] * r2));   // zero rows / columns at constrained DOFs
-        const float val = (MODE == 1) ? fmaf(omega, corr, x[row]) : corr;
+        const float r0 = (MODE == 1) ? bv.x - a0v : a0v, r1 = (MODE == 1) ? bv.y - a1v : a1v, r2 = (MODE == 1) ? bv.z - a2v : a2v;
+        const float corr = fmaf(bi0, r0, fmaf(bi1, r1, bi2 * r2));   // zero rows / columns at constrained DOFs
+        const float val = (MODE == 1) ? fmaf(omega, corr, xr) : corr;
         out[row] = val;
-        if (DOT) part = fma((double)b[row], (double)val, part);
+        if (DOT) {
+          const float bk = kk == 0 ? bv.x : (kk == 1 ? bv.y : bv.z);
+          part = fma((double)bk, (double)val, part);
+        }
       }
     }
   }
@@ -213,9 +341,9 @@ __global__ void __launch_bounds__(MG_TB) k_mg_presmooth(int nV, const float *__r
     const size_t v = i / 3;
     const int k = (int)(i - 3 * v);
     const float *bi = Binv + 9 * v + 3 * k;
-    const float val = omega * fmaf(bi[0], b[3 * v], fmaf(bi[1], b[3 * v + 1], bi[2] * b[3 * v + 2]));
-    x[i] = val;
-    if (DOT) part = fma((double)b[i], (double)val, part);
+    const float val = omega * fmaf(bi[0], b[VS * v], fmaf(bi[1], b[VS * v + 1], bi[2] * b[VS * v + 2]));
+    x[VS * v + k] = val;
+    if (DOT) part = fma((double)b[VS * v + k], (double)val, part);
   }
   if (DOT) block_reduce_to_slot<MG_TB>(part, slots);
 }
@@ -250,12 +378,12 @@ __global__ void __launch_bounds__(MG_TB) k_mg_restrict(GridMaps g, const float *
         for (int kk = lo[2]; kk <= hi[2]; kk++) {
           const float wk = (g.fa[2][kk] == K) ? 1.f - g.fw[2][kk] : g.fw[2][kk];
           const size_t f = ((size_t)i * g.nf[1] + j) * g.nf[2] + kk;
-          s = fmaf(wi * wj * wk, rf[3 * f + k], s);
+          s = fmaf(wi * wj * wk, rf[VS * f + k], s);
         }
       }
     }
-    bc[t] = maskC[t] ? 0.f : s;
-    if (xc_zero) xc_zero[t] = 0.f;
+    bc[VS * V + k] = maskC[t] ? 0.f : s;
+    (void)xc_zero;
   }
 }
 
@@ -282,11 +410,11 @@ __global__ void __launch_bounds__(MG_TB) k_mg_prolong_add(GridMaps g, const floa
           const float wk = dk ? w[2] : 1.f - w[2];
           if (wk == 0.f) continue;
           const size_t V = ((size_t)(a[0] + di) * g.nc[1] + (a[1] + dj)) * g.nc[2] + (a[2] + dk);
-          s = fmaf(wi * wj * wk, xc[3 * V + k], s);
+          s = fmaf(wi * wj * wk, xc[VS * V + k], s);
         }
       }
     }
-    xf[t] += s;
+    xf[VS * v + k] += s;
   }
 }
 
@@ -347,12 +475,12 @@ __global__ void __launch_bounds__(128) k_mg_dense_apply(int n, const float *__re
                                                         float *__restrict__ x, const FbScalars *sc) {
   if (sc && sc->done) return;
   __shared__ float sb[MG_MAX_DENSE];
-  for (int j = threadIdx.x; j < n; j += blockDim.x) sb[j] = b[j];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sb[j] = b[j + j / 3];   // DOF 3v + k lives at VS v + k
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float s = 0.f;
     for (int j = 0; j < n; j++) s = fmaf(inv[(size_t)i * n + j], sb[j], s);
-    x[i] = s;
+    x[i + i / 3] = s;
   }
 }
 
@@ -365,9 +493,9 @@ __global__ void __launch_bounds__(MG_TB) k_mg_norm2(size_t n, const float *__res
 __global__ void k_mg_scale_copy(size_t n, float s, const float *__restrict__ a, float *__restrict__ o) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) o[i] = s * a[i];
 }
-__global__ void k_mg_fill_pattern(size_t n, const unsigned char *__restrict__ mask, float *__restrict__ o) {
+__global__ void k_mg_fill_pattern(size_t n, const unsigned char *__restrict__ mask, float *__restrict__ o) {   // n = 3 nV DOFs
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    o[i] = mask[i] ? 0.f : 1.0f + 0.37f * (float)((i * 2654435761ull) % 1000ull) * 1e-3f;
+    o[i + i / 3] = mask[i] ? 0.f : 1.0f + 0.37f * (float)((i * 2654435761ull) % 1000ull) * 1e-3f;
 }
 
 // ---- outer PCG, FP64 ----------------------------------------------------------------------------------------------------
@@ -386,7 +514,7 @@ __global__ void __launch_bounds__(MG_TB) k_mgcg_init(int n, const double *__rest
     double ri;
     if (warm) ri = r[i];
     else { ri = bi; r[i] = bi; x[i] = 0.0; }
-    r32[i] = (float)ri;
+    r32[i + i / 3] = (float)ri;
     p0 = fma(bi * bi, wi, p0);
     p1 = fma(ri * ri, wi, p1);
   }
@@ -402,7 +530,7 @@ __global__ void __launch_bounds__(MG_TB) k_mgcg_begin(int n, const float *__rest
   const double m0 = cta_sum_slots<MG_TB>(slotsM0, nSlotsV);
   const double m = cta_sum_slots<MG_TB>(slotsM, nSlotsV);
   const double rz = cta_sum_slots<MG_TB>(slotsZ, nSlotsZ);
-  for (size_t i = (size_t)blockIdx.x * MG_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * MG_TB) d[i] = (double)z[i];
+  for (size_t i = (size_t)blockIdx.x * MG_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * MG_TB) d[i] = (double)z[i + i / 3];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->rho0 = m0;
     sc->rq = m;
@@ -431,7 +559,7 @@ __global__ void __launch_bounds__(MG_TB) k_mgcg_update(int n, const double *__re
     x[i] = fma(alpha, d[i], x[i]);
     const double ri = fma(-alpha, q[i], r[i]);
     r[i] = ri;
-    r32[i] = (float)ri;
+    r32[i + i / 3] = (float)ri;
     part = fma(ri * ri, invD[i], part);
   }
   block_reduce_to_slot<MG_TB>(part, slotsM);
@@ -460,7 +588,7 @@ __global__ void __launch_bounds__(MG_TB) k_mgcg_direction(int n, const float *__
   const double rzNew = cta_sum_slots<MG_TB>(slotsZ, nSlotsZ);
   const double beta = rzNew / sc->rho[(it - 1) & 1];
   for (size_t i = (size_t)blockIdx.x * MG_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * MG_TB)
-    d[i] = fma(beta, d[i], (double)z[i]);
+    d[i] = fma(beta, d[i], (double)z[i + i / 3]);
   if (blockIdx.x == 0 && threadIdx.x == 0) sc->rho[it & 1] = rzNew;   // read next by k_mgcg_update(it + 1): other slot than the one read here
 }
 
@@ -515,7 +643,7 @@ void grid_mesh(const std::vector<double> ax[3], std::vector<double> &verts, std:
 }
 
 void free_level(fb_context *owner, MgLevel &L, int li) {
-  void *ptrs[] = {L.A32, L.Binv, L.b, L.x, L.xn, L.res, L.pv, L.u, L.twin, L.cidx[0], L.cidx[1], L.cidx[2], L.fa[0], L.fa[1], L.fa[2],
+  void *ptrs[] = {L.AB, L.scale, L.Binv, L.b, L.x, L.xn, L.res, L.pv, L.u, L.twin, L.cidx[0], L.cidx[1], L.cidx[2], L.fa[0], L.fa[1], L.fa[2],
                   L.fw[0], L.fw[1], L.fw[2]};
   for (void *p : ptrs)
     if (p) fb_dev_free(p);
@@ -524,18 +652,28 @@ void free_level(fb_context *owner, MgLevel &L, int li) {
   memset(&L, 0, sizeof(L));
 }
 
-int alloc_level_vectors(fb_context *c, MgLevel &L) {
+int alloc_level_vectors(fb_context *c, MgLevel &L, bool half) {
   fb_context *lc = L.ctx;
   L.nV = lc->nV; L.r = lc->r;
-  FB_TRY(fb_dev_alloc(c, &L.A32, (size_t)lc->nnzK + 4));
+  {
+    unsigned char *ab = nullptr;   // 12 entries per block, 2 (FP16) or 4 (FP32) bytes each
+    FB_TRY(fb_dev_alloc(c, &ab, (size_t)lc->nB * 12 * (half ? 2 : 4) + 64));
+    L.AB = ab;
+    FB_TRY(fb_dev_alloc(c, &L.scale, 4));
+    const float init[4] = {1.f, 1.f, 0.f, 0.f};
+    FB_CUDA(cudaMemcpyAsync(L.scale, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    const unsigned int inf = 0x7f800000u;
+    FB_CUDA(cudaMemcpyAsync(L.scale + 2, &inf, sizeof(inf), cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+  }
   FB_TRY(fb_dev_alloc(c, &L.Binv, 9 * (size_t)lc->nV));
   float **vecs[] = {&L.b, &L.x, &L.xn, &L.res, &L.pv};
   for (float **v : vecs) {
-    FB_TRY(fb_dev_alloc(c, v, (size_t)lc->r + 4));
-    FB_CUDA(cudaMemsetAsync(*v, 0, sizeof(float) * ((size_t)lc->r + 4), c->stream));
+    FB_TRY(fb_dev_alloc(c, v, (size_t)VS * lc->nV + 4));   // (x, y, z, 0) per vertex; the fourth entries stay zero for ever
+    FB_CUDA(cudaMemsetAsync(*v, 0, sizeof(float) * ((size_t)VS * lc->nV + 4), c->stream));
   }
   int perSM = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_mg_spmv<1, true>, MG_TB, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_mg_spmv<__half, 1, true>, MG_TB, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
   size_t want = ((size_t)lc->nV + 2 * (MG_TB / 16) - 1) / (2 * (MG_TB / 16));   // two block rows per 16-lane group and trip
   size_t cap = (size_t)c->sm_count * perSM;
   if (cap > MG_SLOTS) cap = MG_SLOTS;
@@ -544,6 +682,11 @@ int alloc_level_vectors(fb_context *c, MgLevel &L) {
   L.lmax = 0.f;
   return FB_OK;
 }
+
+// the cycle's product on one level, storage type chosen at run time
+template <int MODE, bool DOT>
+void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, const float *x, const float *b, float omega, float *out,
+                    double *slots, const FbScalars *sc);
 
 // lambda_max(Binv A) of one level by power iteration (host reads the norms: only at setup and every 32 solves)
 int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
@@ -555,9 +698,9 @@ int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
   double lam = L.lmax;
   std::vector<double> h((size_t)L.grid_vec);
   for (int k = 0; k < its; k++) {
-    k_mg_spmv<2, false><<<L.grid_spmv, MG_TB, 0, st>>>(L.nV, lc->bp, lc->bc, L.A32, L.pv, nullptr, L.Binv, lc->rowmask, 0.f, L.res, nullptr, nullptr);
-    k_mg_norm2<<<L.grid_vec, MG_TB, 0, st>>>((size_t)L.r, L.res, mg->slotsM);
-    k_mg_norm2<<<L.grid_vec, MG_TB, 0, st>>>((size_t)L.r, L.pv, mg->slotsZ);
+    launch_mg_spmv<2, false>(c, mg, L, false, L.pv, nullptr, 0.f, L.res, nullptr, nullptr);
+    k_mg_norm2<<<L.grid_vec, MG_TB, 0, st>>>((size_t)VS * L.nV, L.res, mg->slotsM);
+    k_mg_norm2<<<L.grid_vec, MG_TB, 0, st>>>((size_t)VS * L.nV, L.pv, mg->slotsZ);
     double ny = 0.0, nx = 0.0;
     FB_CUDA(cudaMemcpyAsync(h.data(), mg->slotsM, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
@@ -568,15 +711,27 @@ int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
     c->launches += 3;
     if (!(nx > 0.0) || !(ny > 0.0) || !std::isfinite(ny)) break;
     lam = std::sqrt(ny / nx);
-    k_mg_scale_copy<<<L.grid_vec, MG_TB, 0, st>>>((size_t)L.r, (float)(1.0 / std::sqrt(ny)), L.res, L.pv);
+    k_mg_scale_copy<<<L.grid_vec, MG_TB, 0, st>>>((size_t)VS * L.nV, (float)(1.0 / std::sqrt(ny)), L.res, L.pv);
     c->launches++;
   }
   L.lmax = (float)((lam > 0.0 && std::isfinite(lam)) ? lam : 3.0);
   return FB_OK;
 }
 
-// z = V(b) on level li, result in L.xn (li = 0: with the dot b.z into slotsZ)
-void vcycle(fb_context *c, FbMg *mg, int li) {
+template <int MODE, bool DOT>
+void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, const float *x, const float *b, float omega, float *out,
+                    double *slots, const FbScalars *sc) {
+  const fb_context *lc = L.ctx;
+  if (mg->half)
+    fb_launch(pdl, c->stream, k_mg_spmv<__half, MODE, DOT>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, (const __half *)L.AB, (const float *)L.scale, x, b,
+              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
+  else
+    fb_launch(pdl, c->stream, k_mg_spmv<float, MODE, DOT>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, (const float *)L.AB, (const float *)L.scale, x, b,
+              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
+}
+
+// z = V(b) on level li; returns the vector holding the result (li = 0: with the dot b.z into slotsZ)
+float *vcycle(fb_context *c, FbMg *mg, int li) {
   cudaStream_t st = c->stream;
   MgLevel &L = mg->L[li];
   fb_context *lc = L.ctx;
@@ -584,32 +739,47 @@ void vcycle(fb_context *c, FbMg *mg, int li) {
   if (li == mg->nLevels - 1) {   // coarsest: dense inverse
     k_mg_dense_apply<<<1, 128, 0, st>>>(L.r, mg->denseInv, L.b, L.xn, sc);
     c->launches++;
-    return;
+    return L.xn;
   }
   MgLevel &C = mg->L[li + 1];
   const float omega = 1.4f / L.lmax;
   const GridMaps g = maps_of(L);
+  const int nu = mg->nu;
+  // pre-smoothing from the zero guess: the first sweep needs no product
   fb_launch(true, st, k_mg_presmooth<false>, L.grid_vec, MG_TB, L.nV, L.Binv, L.b, omega, L.x, (double *)nullptr, sc);
-  fb_launch(true, st, k_mg_spmv<0, false>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, L.A32, L.x, L.b, L.Binv, lc->rowmask, omega, L.res,
-            (double *)nullptr, sc);
+  c->launches++;
+  float *cur = L.x, *alt = L.xn;
+  for (int s = 1; s < nu; s++) {
+    launch_mg_spmv<1, false>(c, mg, L, true, cur, L.b, omega, alt, nullptr, sc);
+    c->launches++;
+    std::swap(cur, alt);
+  }
+  launch_mg_spmv<0, false>(c, mg, L, true, cur, L.b, omega, L.res, nullptr, sc);
+  if (li == 0) tm_mark(st, "presmooth + residual (level 0)");
   k_mg_restrict<<<C.grid_vec, MG_TB, 0, st>>>(g, L.res, C.ctx->rowmask, C.b, (float *)nullptr, sc);
-  c->launches += 3;
-  vcycle(c, mg, li + 1);
-  k_mg_prolong_add<<<L.grid_vec, MG_TB, 0, st>>>(g, C.xn, lc->rowmask, L.x, sc);
-  if (li == 0)
-    fb_launch(true, st, k_mg_spmv<1, true>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, L.A32, L.x, L.b, L.Binv, lc->rowmask, omega, L.xn,
-              mg->slotsZ, sc);
-  else
-    fb_launch(true, st, k_mg_spmv<1, false>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, L.A32, L.x, L.b, L.Binv, lc->rowmask, omega, L.xn,
-              (double *)nullptr, sc);
   c->launches += 2;
+  if (li == 0) tm_mark(st, "restrict (level 0 -> 1)");
+  float *coarse = vcycle(c, mg, li + 1);
+  if (li == 0) tm_mark(st, "levels >= 1");
+  k_mg_prolong_add<<<L.grid_vec, MG_TB, 0, st>>>(g, coarse, lc->rowmask, cur, sc);
+  c->launches++;
+  if (li == 0) tm_mark(st, "prolong (level 1 -> 0)");
+  for (int s = 0; s < nu; s++) {   // the same sweeps after the correction: the cycle stays symmetric
+    const bool last = s == nu - 1;
+    if (li == 0 && last) launch_mg_spmv<1, true>(c, mg, L, true, cur, L.b, omega, alt, mg->slotsZ, sc);
+    else launch_mg_spmv<1, false>(c, mg, L, true, cur, L.b, omega, alt, nullptr, sc);
+    c->launches++;
+    std::swap(cur, alt);
+  }
+  return cur;
 }
 
-// z = preconditioner(r32) on the finest level: result in L[0].xn, r.z partials in slotsZ (nSlotsZ returned)
-int apply_preconditioner(fb_context *c, FbMg *mg) {
+// z = preconditioner(r32) on the finest level: result in *z, r.z partials in slotsZ (nSlotsZ returned)
+int apply_preconditioner(fb_context *c, FbMg *mg, float **z) {
   MgLevel &L = mg->L[0];
+  *z = L.xn;
   if (mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1) {
-    vcycle(c, mg, 0);
+    *z = vcycle(c, mg, 0);
     mg->vcycles++;
     return L.grid_spmv;
   }
@@ -638,6 +808,9 @@ static int mg_ensure(fb_context *c) {
   FbMg *mg = new FbMg();
   memset(mg, 0, sizeof(*mg));
   c->mg = mg;
+  mg->half = !(getenv("FEMBRAIN_B200_MG_PREC") && !strcmp(getenv("FEMBRAIN_B200_MG_PREC"), "fp32"));
+  mg->nu = 1;
+  if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = atoi(getenv("FEMBRAIN_B200_MG_NU"));
   FB_TRY(fb_dev_alloc(c, &mg->slotsM, 2 * (size_t)MG_SLOTS));
   FB_TRY(fb_dev_alloc(c, &mg->slotsZ, (size_t)MG_SLOTS));
   return FB_OK;
@@ -655,7 +828,7 @@ static int mg_build(fb_context *c) {
   MgLevel &L0 = mg->L[0];
   memset(&L0, 0, sizeof(L0));
   L0.ctx = c;
-  FB_TRY(alloc_level_vectors(c, L0));
+  FB_TRY(alloc_level_vectors(c, L0, mg->half != 0));
   mg->nLevels = 1;
   if (mg->variant != FB_SOLVER_MG_PCG) return FB_OK;
   const int *n0 = mg->grid;
@@ -746,7 +919,7 @@ static int mg_build(fb_context *c) {
     C.ctx = lc;
     for (int d = 0; d < 3; d++) C.n[d] = L.nc[d];
     mg->nLevels = li + 2;
-    FB_TRY(alloc_level_vectors(c, C));
+    FB_TRY(alloc_level_vectors(c, C, mg->half != 0));
     FB_TRY(fb_dev_alloc(c, &C.u, (size_t)lc->r));
     FB_TRY(mg_upload(c, &C.twin, twinF));   // straight from the FINEST level: injection needs no intermediate vectors
     c->bytes += lc->bytes;
@@ -785,9 +958,14 @@ int fb_mg_prepare(fb_context *c) {
       FB_TRY(fb_launch_assembly(lc, L.u, nullptr, true));
       c->launches += lc->launches - before;
     }
-    k_mg_convert<<<grid_for_n(c, (size_t)lc->nnzK, 4), MG_TB, 0, st>>>((size_t)lc->nnzK, lc->Keff, L.A32);
+    if (mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1) {   // (the one-level variant applies Binv only)
+      k_mg_scale_min<<<L.grid_vec, MG_TB, 0, st>>>((size_t)lc->r, lc->invD, reinterpret_cast<unsigned int *>(L.scale + 2));
+      k_mg_scale_final<<<1, 1, 0, st>>>(L.scale, mg->half);
+      if (mg->half) k_mg_pack<__half><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (__half *)L.AB);
+      else k_mg_pack<float><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (float *)L.AB);
+    }
     k_mg_block_inverse<<<(L.nV + 127) / 128, 128, 0, st>>>(L.nV, lc->bp, lc->diag, lc->Keff, lc->rowmask, L.Binv);
-    c->launches += 2;
+    c->launches += 4;
   }
   if (mg->nLevels > 1) {
     MgLevel &Lc = mg->L[mg->nLevels - 1];
@@ -833,10 +1011,12 @@ int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
   }
   k_mgcg_init<<<gv, MG_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, L.b, warm, slotsM0, slotsM, c->sc);
   c->launches++;
-  int nZ = apply_preconditioner(c, mg);
-  k_mgcg_begin<<<gv, MG_TB, 0, st>>>(n, L.xn, c->dir, c->sc, slotsM0, slotsM, mg->slotsZ, gv, nZ, eps, maxIt);
+  float *z = nullptr;
+  int nZ = apply_preconditioner(c, mg, &z);
+  k_mgcg_begin<<<gv, MG_TB, 0, st>>>(n, z, c->dir, c->sc, slotsM0, slotsM, mg->slotsZ, gv, nZ, eps, maxIt);
   c->launches++;
   const int CH = 6;
+  g_tm.on = getenv("FEMBRAIN_B200_MG_TIMING") && atoi(getenv("FEMBRAIN_B200_MG_TIMING")) != 0;
   static const bool trace = getenv("FEMBRAIN_B200_MG_TRACE") && atoi(getenv("FEMBRAIN_B200_MG_TRACE")) != 0;
   int it = 1, slot = 0, pending = 0;
   bool finished = false;
@@ -846,15 +1026,31 @@ int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
       const bool sample = c->profiling && (it % 4 == 1) && c->nprof < 64;
       if (sample) cudaEventRecord(c->evProf[2 * c->nprof], st);
       int nDq = 0;
+      g_tm.armed = g_tm.on && it == 3;
+      g_tm.n = 0;
+      tm_mark(st, "start");
       FB_TRY(fb_pcg_launch_product_dq(c, c->dir, c->Ad, &nDq));    // q = A d, d.q partials in c->partials
+      tm_mark(st, "FP64 product A d");
       if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], st); c->nprof++; }
       fb_launch(true, st, k_mgcg_update, gv, MG_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, L.b, (const FbScalars *)c->sc, it,
                 (const double *)c->partials, nDq, slotsM);
       fb_launch(true, st, k_mgcg_check, 1, MG_TB, c->sc, it, (const double *)slotsM, gv);
       c->launches += 2;
-      nZ = apply_preconditioner(c, mg);
-      fb_launch(true, st, k_mgcg_direction, gv, MG_TB, n, (const float *)L.xn, c->dir, c->sc, it, (const double *)mg->slotsZ, nZ);
+      tm_mark(st, "update + check");
+      nZ = apply_preconditioner(c, mg, &z);
+      tm_mark(st, "postsmooth (level 0)");
+      fb_launch(true, st, k_mgcg_direction, gv, MG_TB, n, (const float *)z, c->dir, c->sc, it, (const double *)mg->slotsZ, nZ);
       c->launches++;
+      tm_mark(st, "direction");
+      if (g_tm.armed) {
+        cudaStreamSynchronize(st);
+        for (int k = 1; k < g_tm.n; k++) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, g_tm.ev[k - 1], g_tm.ev[k]);
+          fprintf(stderr, "[mg timing] %-36s %8.1f us\n", g_tm.name[k], 1e3 * ms);
+        }
+        g_tm.armed = false;
+      }
     }
     FB_CUDA(cudaMemcpyAsync(&c->sc_host[slot], c->sc, sizeof(FbScalars), cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaEventRecord(c->evChunk[slot], st));
@@ -928,6 +1124,16 @@ int fb_get_solver(const fb_context *c, int *variant, int *warm_start, int *level
   if (variant) *variant = c->mg ? c->mg->variant : FB_SOLVER_JACOBI_PCG;
   if (warm_start) *warm_start = c->mg ? c->mg->warm : 0;
   if (levels) *levels = c->mg ? c->mg->nLevels : 0;
+  return FB_OK;
+}
+
+int fb_get_solver_levels(const fb_context *c, int capacity, int *num_vertices, long long *num_blocks) {
+  if (!c) return FB_ERR_INVALID_ARGUMENT;
+  const int n = c->mg ? c->mg->nLevels : 0;
+  for (int i = 0; i < n && i < capacity; i++) {
+    if (num_vertices) num_vertices[i] = c->mg->L[i].ctx->nV;
+    if (num_blocks) num_blocks[i] = c->mg->L[i].ctx->nB;
+  }
   return FB_OK;
 }
 

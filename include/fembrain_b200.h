@@ -143,6 +143,8 @@ int fb_set_grid(fb_context *ctx, int nx, int ny, int nz);
 int fb_set_solver(fb_context *ctx, int variant, int warm_start);
 int fb_get_solver(const fb_context *ctx, int *variant, int *warm_start, int *levels);
 const char *fb_solver_name(int variant);
+/* vertices and 3x3 blocks of every level of the variant's hierarchy, finest first (fb_get_solver gives the level count) */
+int fb_get_solver_levels(const fb_context *ctx, int capacity, int *num_vertices, long long *num_blocks);
 
 /* ---- the step ---------------------------------------------------------------------------------
  * VolumeConservingIntegrator::DoTimestep (DEF/PS_VolumeConservingIntegrator.cpp:46-260), PCG branch,

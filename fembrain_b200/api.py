@@ -78,6 +78,7 @@ def load_library():
         "fb_create_with_materials": (ci, [pp, ci, vp, ci, vp, ci, vp, vp, vp, vp, prm]),
         "fb_create_with_constrained_dofs": (ci, [pp, ci, vp, ci, vp, ci, vp, prm]),
         "fb_destroy": (None, [vp]),
+        "fb_sync_force_model": (ci, [vp, ci, vp, ci, vp, ci, vp]),
         "fb_set_fixed_vertices": (ci, [vp, ci, vp]),
         "fb_num_vertices": (ci, [vp]), "fb_num_tets": (ci, [vp]), "fb_num_dofs": (ci, [vp]),
         "fb_num_constrained_dofs": (ci, [vp]), "fb_num_local_dofs": (ci, [vp]),
@@ -107,7 +108,7 @@ def load_library():
         "fb_create_batch": (ci, [pp, ci, vp, vp, vp, vp, vp, vp, prm]), "fb_batch_count": (ci, [vp]),
         "fb_batch_offsets": (ci, [vp, vp, vp]), "fb_batch_last_cg_iterations": (ci, [vp, vp, vp]),
         "fb_partition_ordering": (ci, [ci, ci, vp, ci, vp, C.POINTER(ci)]), "fb_partition_reordered": (ci, [vp]),
-        "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]), "fb_trim_memory": (ci, []),
+        "fb_kernel_launches": (ll, [vp]), "fb_device_bytes": (C.c_size_t, [vp]), "fb_trim_memory": (ci, []), "fb_experiments_built": (ci, []),
         "fb_check_guards": (ci, [C.POINTER(ll), C.POINTER(ll)]),
         "fb_get_stiffness_csr": (ci, [vp, vp, vp]), "fb_get_mass_csr": (ci, [vp, vp, vp, vp]),
         "fb_get_system_csr": (ci, [vp, vp, vp, vp]), "fb_get_element_maps": (ci, [vp, vp, vp]),
@@ -201,6 +202,11 @@ def partition_ordering(num_vertices, tets, world):
     if st != FB_OK:
         raise FemBrainError(st, "fb_partition_ordering", lib.fb_last_error_string().decode())
     return order[:num_vertices], bool(flag.value)
+
+
+def experiments_built() -> bool:
+    """True when libfembrain_b200.so carries the shelved experiments of csrc/experiments/ (build --experiments)."""
+    return bool(load_library().fb_experiments_built())
 
 
 def check_guards():
@@ -448,6 +454,13 @@ class Simulation:
 
     def reset_to_rest(self):
         self._check(self._lib.fb_reset_to_rest(self._h), "fb_reset_to_rest")
+
+    def sync_force_model(self, verts, tets, fixed_verts=()):
+        """Deformable::syncForceModel after a topology change: full re-setup in place, same handle, state at rest."""
+        v, t, fx = _f64(verts).reshape(-1, 3), _i32(tets).reshape(-1, 4), _i32(fixed_verts)
+        self._check(self._lib.fb_sync_force_model(self._h, len(v), _ptr(v), len(t), _ptr(t), len(fx), _ptr(fx)), "fb_sync_force_model")
+        self.nV, self.nT = len(v), len(t)
+        self.r = self._lib.fb_num_dofs(self._h)
 
     def set_fixed_vertices(self, fixed):
         fx = _i32(fixed)

@@ -26,14 +26,16 @@ UNITS = {
     "fb_assembly.cu": ["-fmad=false"],
     "fb_pcg.cu": [],
     "fb_mg.cu": [],
-    "fb_pcg_persistent.cu": [],
     "fb_dist.cu": [],
     "fb_batch.cu": [],
-    "fb_sym.cu": [],
-    "fb_tma.cu": [],
     "fb_veg.cu": ["-fmad=false"],
     "fb_deformable.cu": ["-fmad=false"],
 }
+# measured-and-shelved experiments (csrc/experiments/): built only with --experiments / FEMBRAIN_B200_BUILD_EXPERIMENTS=1;
+# the default library carries fb_experiments_off.cu instead (stubs that answer "not available")
+EXPERIMENT_UNITS = {os.path.join("experiments", "fb_sym.cu"): [], os.path.join("experiments", "fb_pcg_persistent.cu"): [],
+                    os.path.join("experiments", "fb_tma.cu"): [], os.path.join("experiments", "fb_experiments_on.cu"): []}
+DEFAULT_ONLY_UNITS = {"fb_experiments_off.cu": []}
 HEADERS = ["fb_internal.h", "fb_element_math.h", "fb_pcg_common.cuh", os.path.join("..", "..", "include", "fembrain_b200.h")]
 
 
@@ -51,15 +53,27 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, experiments: bool | None = None) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    if experiments is None:
+        experiments = os.environ.get("FEMBRAIN_B200_BUILD_EXPERIMENTS") == "1"
+    units = dict(UNITS)
+    units.update(EXPERIMENT_UNITS if experiments else DEFAULT_ONLY_UNITS)
+    stamp = os.path.join(OBJ, "experiments.on" if experiments else "experiments.off")
+    other = os.path.join(OBJ, "experiments.off" if experiments else "experiments.on")
+    if os.path.exists(other):   # the flavour changed: relink
+        os.remove(other)
+        force_link = True
+    else:
+        force_link = not os.path.exists(stamp)
+    open(stamp, "w").close()
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
     logs = []
-    for unit, extra in UNITS.items():
+    for unit, extra in units.items():
         src = os.path.join(CSRC, unit)
-        obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+        obj = os.path.join(OBJ, os.path.basename(unit).replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", src, "-o", obj]
@@ -68,7 +82,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             if res.returncode != 0:
                 sys.stderr.write(logs[-1])
                 raise RuntimeError(f"nvcc failed on {unit}")
-    if force or _stale(LIB, objs):
+    if force or force_link or _stale(LIB, objs):
         cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lnccl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
@@ -84,4 +98,4 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments=True if "--experiments" in sys.argv else None))

@@ -21,8 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "fb_internal.h"
-#include "fb_pcg_common.cuh"
+#include "../fb_internal.h"
+#include "../fb_pcg_common.cuh"
 
 namespace cg = cooperative_groups;
 

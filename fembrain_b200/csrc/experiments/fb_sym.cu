@@ -27,8 +27,8 @@
 // block to a per-row list and sum them in fixed order, or stage the stream with TMA into shared memory).
 #include <cub/cub.cuh>
 
-#include "fb_internal.h"
-#include "fb_pcg_common.cuh"
+#include "../fb_internal.h"
+#include "../fb_pcg_common.cuh"
 
 struct FbSym {
   int nBu, nBl;    // upper (incl. diagonal) and lower blocks

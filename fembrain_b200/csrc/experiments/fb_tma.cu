@@ -15,8 +15,8 @@
 #include <algorithm>
 #include <vector>
 
-#include "fb_internal.h"
-#include "fb_pcg_common.cuh"
+#include "../fb_internal.h"
+#include "../fb_pcg_common.cuh"
 
 struct FbTma {
   int nTiles;

@@ -111,7 +111,7 @@ void free_all(fb_context *c) {
   void *ptrs[] = {c->x0, c->tets, c->edata, c->bp, c->bc, c->brow, c->diag, c->seg, c->src, c->colIdx, c->mblk,
                   c->fixed, c->cdofs, c->T, c->Keff, c->Kraw, c->scrK, c->scrF, c->q, c->qvel, c->qaccel, c->fext,
                   c->fint, c->qres, c->rhs, c->x, c->res, c->dir, c->Ad, c->invD, c->tmp, c->sc, c->partials,
-                  c->contact_dev, c->ctaRows, c->pers_prof, c->ga_incp, c->ga_ctaV, c->ga_lists, c->ga_erec, c->ga_xu};
+                  c->contact_dev, c->haptic_idx_dev, c->haptic_f_dev, c->edges_dev, c->edge_degree_dev, c->haptic_stamp, c->haptic_listA, c->haptic_listB, c->ctaRows, c->pers_prof, c->ga_incp, c->ga_ctaV, c->ga_lists, c->ga_erec, c->ga_xu};
   for (void *p : ptrs)
     if (p) fb_dev_free(p);
   if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -428,6 +428,35 @@ int fb_create_with_constrained_dofs(fb_context **out, int nV, const double *x0, 
 }
 
 void fb_destroy(fb_context *c) { free_all(c); }
+
+// Deformable::syncForceModel after a topology change (cutCompleted -> syncForceModel, main.cpp:614-617,
+// DEF/Deformable.cpp:127-220): the reference deletes TetMesh, CorotationalLinearFEM, force model, mass matrix and integrator
+// and rebuilds them all from the edited VolMesh on the same Deformable object; state restarts at rest (a new integrator).
+// Same here on the same context handle: parameters, timestep / damping / CG settings and the Deformable-level options are
+// kept, the mesh-sized buffers come back from the memory pool.  The solver variant falls back to the reference's solver
+// unless it is the mesh-independent one (a cut mesh is no tensor grid any more).
+int fb_sync_force_model(fb_context *c, int nV, const double *x0, int nT, const int *tets, int nFixed, const int *fixedVerts) {
+  CHECK_CTX(c);
+  if (c->dist || c->batch) { fb_set_error("fb_sync_force_model: recreate partitioned / batch contexts"); return FB_ERR_NOT_SUPPORTED; }
+  std::vector<int> dofs;
+  FB_TRY(fixed_vertices_to_dofs(nV, nFixed, fixedVerts, dofs));
+  fb_params prm = c->prm;
+  const int variant = fb_mg_active(c);
+  prm.solver_variant = FB_SOLVER_JACOBI_PCG;
+  fb_context *n = nullptr;
+  FB_TRY(fb_create_local(&n, nV, x0, nT, tets, (int)dofs.size(), dofs.data(), nullptr, nullptr, nullptr, &prm));
+  // Deformable-level options survive the re-setup (they are members of Deformable, not of the integrator)
+  n->gravity = c->gravity; n->floor_enabled = c->floor_enabled; n->floor_y = c->floor_y; n->haptic_rings = c->haptic_rings;
+  n->profiling = 0;
+  n->launches += c->launches;
+  // swap the guts so that the caller's handle stays valid, then release the old mesh's buffers (back to the pool)
+  fb_context tmp = *c;
+  *c = *n;
+  *n = tmp;
+  free_all(n);
+  if (variant == FB_SOLVER_BLOCK_JACOBI_PCG) FB_TRY(fb_set_solver(c, variant, 0));
+  return FB_OK;
+}
 
 int fb_set_fixed_vertices(fb_context *c, int nFixed, const int *fv) {
   CHECK_CTX(c);

@@ -2,8 +2,12 @@
 // (reference src/deformable/Deformable.cpp:318-420) — external-force build (gravity :331-338, haptic forces with
 // ring spreading applyHapticForces :634-706) before DoTimestep, floor-plane post-step (:350-402) after it.
 //
-// The force build is O(picked vertices x rings) set arithmetic on the host, exactly as in the reference; the
-// post-step is one kernel over the vertices.  Neighbour rings: the reference walks VolMesh::get_node_neighbors
+// The force build runs on the device (k_force_base, k_haptic_spread): nothing of size r is built on or copied from the
+// host per frame (41 MB at 10M tets).  The rings of applyHapticForces are breadth-first levels from each haptic vertex;
+// one CTA walks the haptic vertices IN ORDER, so that every entry of the force vector receives its additions in the
+// reference's order (direct forces by index, then per haptic vertex ring by ring) and the result is bit-identical to the
+// reference's std::set arithmetic; inside one ring the new vertices are distinct, so their additions run in parallel.
+// The post-step is one kernel over the vertices.  Neighbour rings: the reference walks VolMesh::get_node_neighbors
 // (DEF/VolMesh.cpp:1346-1363), which indexes the GLOBAL edge array with a loop counter that runs over the node's
 // incident-edge COUNT (const_edgeAt(i) instead of const_edgeAt(edges[i])) — so its "neighbours" of v are those
 // among the first deg(v) edges of the mesh that touch v.  Two modes are offered and the choice is explicit:
@@ -16,7 +20,6 @@
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
-#include <set>
 #include <vector>
 
 #include "fb_internal.h"
@@ -111,21 +114,83 @@ __global__ void __launch_bounds__(256) k_pick_closest(int nV, const double *__re
   if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
 }
 
-// neighbours of vtx under the chosen rule
-void node_neighbors(const fb_context *c, int vtx, std::vector<int> &out) {
-  out.clear();
-  if (c->haptic_quirk && c->edges_host) {
-    // VolMesh::get_node_neighbors: for (i = 0; i < incident_edges(vtx).size(); i++) { e = const_edgeAt(i); ... }
-    const int deg = c->edge_degree_host[vtx];
-    for (int i = 0; i < deg && i < c->nEdges; i++) {
-      const int from = c->edges_host[2 * i], to = c->edges_host[2 * i + 1];
-      if (from == vtx) out.push_back(to);
-      else if (to == vtx) out.push_back(from);
-    }
-    return;
+// SetExternalForcesToZero + memset + gravity (DEF/Deformable.cpp:325-338): 0, or 0 + (-10000) on the y components
+__global__ void k_force_base(size_t r, int gravity, double *__restrict__ f) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < r; i += (size_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (gravity && (i % 3 == 1)) v += -10000.0;
+    f[i] = v;
   }
-  for (int p = c->adj_host_bp[vtx]; p < c->adj_host_bp[vtx + 1]; p++)
-    if (c->adj_host_bc[p] != vtx) out.push_back(c->adj_host_bc[p]);
+}
+
+struct HapticArgs {
+  int nH, rings, nV;
+  const int *idx;          // [nH] haptic vertices
+  const double *force;     // [3 nH]
+  const int *bp, *bc;      // true adjacency: the block structure of K (vertices sharing a tet), self excluded
+  int quirk, nEdges;       // reference rule: VolMesh::get_node_neighbors on the host's edge array
+  const int *edges, *deg;
+  unsigned int *stamp;     // [nV] visit stamps, never cleared: stampBase + haptic index + 1 marks "affected by this haptic vertex"
+  unsigned int stampBase;
+  int *listA, *listB;      // [nV] frontier lists
+};
+
+// applyHapticForces (DEF/Deformable.cpp:634-706).  ONE CTA.
+__global__ void __launch_bounds__(1024) k_haptic_spread(HapticArgs a, double *__restrict__ f) {
+  __shared__ int nLast, nFresh;
+  // direct forces, in index order (a vertex may be listed twice)                                   (:641-647)
+  if (threadIdx.x < 3)
+    for (int i = 0; i < a.nH; i++) f[3 * (size_t)a.idx[i] + threadIdx.x] += a.force[3 * (size_t)i + threadIdx.x];
+  __syncthreads();
+  if (a.rings <= 1) return;
+  for (int iv = 0; iv < a.nH; iv++) {
+    const unsigned int cur = a.stampBase + (unsigned int)iv + 1u;
+    const double fx = a.force[3 * (size_t)iv], fy = a.force[3 * (size_t)iv + 1], fz = a.force[3 * (size_t)iv + 2];
+    int *last = a.listA, *fresh = a.listB;
+    if (threadIdx.x == 0) {
+      a.stamp[a.idx[iv]] = cur;   // affectedVertices = lastLayerVertices = { the haptic vertex }
+      last[0] = a.idx[iv];
+      nLast = 1;
+    }
+    __syncthreads();
+    for (int j = 1; j < a.rings; j++) {
+      // linear kernel (:657-658): 1.0 * (size - j) / static_cast<double>(size)
+      const double mag = 1.0 * (a.rings - j) / static_cast<double>(a.rings);
+      if (threadIdx.x == 0) nFresh = 0;
+      __syncthreads();
+      const int nl = nLast;
+      // every neighbour of the last ring that is not yet affected joins the new ring once (atomicMax = test-and-set)
+      for (int e = threadIdx.x; e < nl; e += blockDim.x) {
+        const int v = last[e];
+        if (a.quirk) {
+          // VolMesh::get_node_neighbors (DEF/VolMesh.cpp:1346-1363): for (i = 0; i < incident_edges(v).size(); i++) e = const_edgeAt(i)
+          const int d = min(a.deg[v], a.nEdges);
+          for (int i = 0; i < d; i++) {
+            const int from = a.edges[2 * i], to = a.edges[2 * i + 1];
+            const int nb = (from == v) ? to : ((to == v) ? from : -1);
+            if (nb >= 0 && atomicMax(&a.stamp[nb], cur) < cur) fresh[atomicAdd(&nFresh, 1)] = nb;
+          }
+        } else {
+          for (int p = a.bp[v]; p < a.bp[v + 1]; p++) {
+            const int nb = a.bc[p];
+            if (nb != v && atomicMax(&a.stamp[nb], cur) < cur) fresh[atomicAdd(&nFresh, 1)] = nb;
+          }
+        }
+      }
+      __syncthreads();
+      const int nf = nFresh;
+      for (int e = threadIdx.x; e < nf; e += blockDim.x) {   // distinct vertices: one addition each (:687-690)
+        const size_t v = (size_t)fresh[e];
+        f[3 * v] += mag * fx;
+        f[3 * v + 1] += mag * fy;
+        f[3 * v + 2] += mag * fz;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) nLast = nf;
+      int *t = last; last = fresh; fresh = t;
+      __syncthreads();
+    }
+  }
 }
 
 }  // namespace
@@ -155,6 +220,17 @@ int fb_deformable_set_haptic_forces(fb_context *c, int count, const int *idx, co
   memcpy(c->haptic_f_host, forces, sizeof(double) * 3 * (size_t)count);
   c->nHaptic = count;
   c->haptic_in_progress = inProgress != 0;
+  // device copies for the force-build kernel
+  if (cudaSetDevice(c->device) != cudaSuccess) { cudaGetLastError(); return FB_ERR_CUDA; }
+  if (c->haptic_idx_dev) { fb_dev_free(c->haptic_idx_dev); c->haptic_idx_dev = nullptr; }
+  if (c->haptic_f_dev) { fb_dev_free(c->haptic_f_dev); c->haptic_f_dev = nullptr; }
+  FB_TRY(fb_dev_alloc(c, &c->haptic_idx_dev, (size_t)count));
+  FB_TRY(fb_dev_alloc(c, &c->haptic_f_dev, 3 * (size_t)count));
+  if (count) {
+    FB_CUDA(cudaMemcpyAsync(c->haptic_idx_dev, idx, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaMemcpyAsync(c->haptic_f_dev, forces, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+  }
   return FB_OK;
 }
 int fb_deformable_set_haptic_neighborhood(fb_context *c, int rings) {
@@ -180,6 +256,16 @@ int fb_deformable_set_edge_list(fb_context *c, int numEdges, const int *fromTo, 
       c->edge_degree_host[fromTo[2 * i]]++;
       c->edge_degree_host[fromTo[2 * i + 1]]++;
     }
+  }
+  if (cudaSetDevice(c->device) != cudaSuccess) { cudaGetLastError(); return FB_ERR_CUDA; }
+  if (c->edges_dev) { fb_dev_free(c->edges_dev); c->edges_dev = nullptr; }
+  if (c->edge_degree_dev) { fb_dev_free(c->edge_degree_dev); c->edge_degree_dev = nullptr; }
+  if (numEdges > 0) {
+    FB_TRY(fb_dev_alloc(c, &c->edges_dev, 2 * (size_t)numEdges));
+    FB_TRY(fb_dev_alloc(c, &c->edge_degree_dev, (size_t)c->nV));
+    FB_CUDA(cudaMemcpyAsync(c->edges_dev, c->edges_host, sizeof(int) * 2 * (size_t)numEdges, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaMemcpyAsync(c->edge_degree_dev, c->edge_degree_host, sizeof(int) * (size_t)c->nV, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
   }
   return FB_OK;
 }
@@ -269,54 +355,40 @@ int fb_deformable_timestep(fb_context *c) {
   CHECK_CTX(c);
   if (c->dist) { fb_set_error("fb_deformable_timestep on a partitioned context: build the force vector on the host and call fb_step"); return FB_ERR_NOT_SUPPORTED; }
   const size_t r = (size_t)c->r;
-  if (!c->fext_host) FB_CUDA(cudaMallocHost(&c->fext_host, sizeof(double) * (r ? r : 1)));
-  double *f = c->fext_host;
-  // SetExternalForcesToZero + memset(m_arrExtForces)                                    (:325-328)
-  memset(f, 0, sizeof(double) * r);
-  // gravity: applyGravity = m_bApplyGravity && m_ctCollided == 0; ext[3i+1] += -10000   (:331-338)
-  if (c->gravity && c->contact_count == 0)
-    for (size_t i = 1; i < r; i += 3) f[i] += -10000.0;
-  // applyHapticForces                                                                    (:634-706)
-  if (c->nHaptic > 0 && c->haptic_in_progress) {
-    for (int i = 0; i < c->nHaptic; i++)
-      for (int d = 0; d < 3; d++) f[3 * (size_t)c->haptic_idx_host[i] + d] += c->haptic_f_host[3 * (size_t)i + d];
-    const int R = c->haptic_rings;
-    if (R > 1) {
-      if (!(c->haptic_quirk && c->edges_host) && !c->adj_host_bp) {
-        std::vector<int> bp, bc;
-        FB_TRY(fb_fetch_structure(c, bp, bc));
-        c->adj_host_bp = (int *)malloc(sizeof(int) * bp.size());
-        c->adj_host_bc = (int *)malloc(sizeof(int) * (bc.size() ? bc.size() : 1));
-        memcpy(c->adj_host_bp, bp.data(), sizeof(int) * bp.size());
-        memcpy(c->adj_host_bc, bc.data(), sizeof(int) * bc.size());
-      }
-      std::vector<int> nbors;
-      for (int iv = 0; iv < c->nHaptic; iv++) {
-        std::set<int> affected, last;
-        affected.insert(c->haptic_idx_host[iv]);
-        last.insert(c->haptic_idx_host[iv]);
-        const double *ef = c->haptic_f_host + 3 * (size_t)iv;
-        for (int j = 1; j < R; j++) {
-          const double mag = 1.0 * (R - j) / static_cast<double>(R);  // linear kernel (:657-658)
-          std::set<int> fresh;
-          for (std::set<int>::iterator itv = last.begin(); itv != last.end(); ++itv) {
-            node_neighbors(c, *itv, nbors);
-            for (size_t k = 0; k < nbors.size(); k++)
-              if (affected.find(nbors[k]) == affected.end()) fresh.insert(nbors[k]);
-          }
-          last.clear();
-          for (std::set<int>::iterator itn = fresh.begin(); itn != fresh.end(); ++itn) {
-            f[3 * (size_t)*itn] += mag * ef[0];
-            f[3 * (size_t)*itn + 1] += mag * ef[1];
-            f[3 * (size_t)*itn + 2] += mag * ef[2];
-            last.insert(*itn);
-            affected.insert(*itn);
-          }
-        }
-      }
-    }
+  cudaStream_t st = c->stream;
+  // SetExternalForcesToZero + memset(m_arrExtForces) + gravity (applyGravity = m_bApplyGravity && m_ctCollided == 0)   (:325-338)
+  if (r) {
+    int grid = (int)((r + 255) / 256);
+    if (grid > 8 * c->sm_count) grid = 8 * c->sm_count;
+    k_force_base<<<grid, 256, 0, st>>>(r, (c->gravity && c->contact_count == 0) ? 1 : 0, c->fext);
+    c->launches++;
   }
-  if (r) FB_CUDA(cudaMemcpyAsync(c->fext, f, sizeof(double) * r, cudaMemcpyHostToDevice, c->stream));
+  // applyHapticForces                                                                                                    (:634-706)
+  if (c->nHaptic > 0 && c->haptic_in_progress) {
+    if (!c->haptic_stamp) {
+      FB_TRY(fb_dev_alloc(c, &c->haptic_stamp, (size_t)c->nV));
+      FB_TRY(fb_dev_alloc(c, &c->haptic_listA, (size_t)c->nV));
+      FB_TRY(fb_dev_alloc(c, &c->haptic_listB, (size_t)c->nV));
+      FB_CUDA(cudaMemsetAsync(c->haptic_stamp, 0, sizeof(unsigned int) * (size_t)(c->nV ? c->nV : 1), st));
+      c->haptic_stamp_base = 0;
+    }
+    if (c->haptic_stamp_base > 0xffffffffu - (unsigned int)c->nHaptic - 2u) {   // stamps would wrap: start over
+      FB_CUDA(cudaMemsetAsync(c->haptic_stamp, 0, sizeof(unsigned int) * (size_t)(c->nV ? c->nV : 1), st));
+      c->haptic_stamp_base = 0;
+    }
+    HapticArgs a;
+    a.nH = c->nHaptic; a.rings = c->haptic_rings; a.nV = c->nV;
+    a.idx = c->haptic_idx_dev; a.force = c->haptic_f_dev;
+    a.bp = c->bp; a.bc = c->bc;
+    a.quirk = (c->haptic_quirk && c->edges_dev) ? 1 : 0;
+    a.nEdges = c->nEdges; a.edges = c->edges_dev; a.deg = c->edge_degree_dev;
+    a.stamp = c->haptic_stamp; a.stampBase = c->haptic_stamp_base;
+    a.listA = c->haptic_listA; a.listB = c->haptic_listB;
+    k_haptic_spread<<<1, 1024, 0, st>>>(a, c->fext);
+    c->launches++;
+    c->haptic_stamp_base += (unsigned int)c->nHaptic + 1u;
+  }
+  FB_CUDA(cudaGetLastError());
   FB_TRY(fb_do_step(c));
   if (c->floor_enabled) {
     FB_CUDA(cudaMemsetAsync(c->contact_dev, 0, sizeof(int), c->stream));

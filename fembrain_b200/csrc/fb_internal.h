@@ -121,7 +121,11 @@ struct fb_context {
   int nHaptic;
   int *haptic_idx_host;
   double *haptic_f_host;
-  int *adj_host_bp, *adj_host_bc;  // host copy of vertex adjacency for ring spreading
+  int *adj_host_bp, *adj_host_bc;  // (unused since the ring spreading moved to the device; kept zero)
+  int *haptic_idx_dev, *edges_dev, *edge_degree_dev;   // device copies for k_haptic_spread
+  double *haptic_f_dev;
+  unsigned int *haptic_stamp, haptic_stamp_base;        // visit stamps of the ring walk, never cleared between frames
+  int *haptic_listA, *haptic_listB;
   int nEdges, *edges_host;         // optional reference edge array (VolMesh::m_vEdges order), 2 ints per edge
   int *edge_degree_host;           // incident-edge count per vertex of that array
   int haptic_quirk;                // replicate VolMesh::get_node_neighbors (DEF/VolMesh.cpp:1346-1363) exactly
@@ -202,20 +206,21 @@ int fb_mg_prepare(fb_context *c);        // per step, after the assembly: coarse
 int fb_mg_pcg_solve(fb_context *c, double eps, int max_it);
 void fb_mg_invalidate(fb_context *c);    // constraints changed: the hierarchy is rebuilt at the next step
 void fb_mg_release(fb_context *c);
-// ---- fb_pcg_persistent.cu --------------------------------------------------------------------------
+// (fb_experiments_built() of the public header: 1 when csrc/experiments/ was compiled in (fb_experiments_on.cu), 0 for the default library)
+// ---- experiments/fb_pcg_persistent.cu (stubs in fb_experiments_off.cu by default) ------------------
 int fb_pcg_plan_persistent(fb_context *c);
 int fb_pcg_launch_persistent(fb_context *c);
 // ---- fb_batch.cu -----------------------------------------------------------------------------------
 int fb_batch_pcg_solve(fb_context *c, double eps, int max_it);  // every mesh of the batch, own scalars and stopping rule each
 void fb_batch_destroy(fb_context *c);
-// ---- fb_sym.cu -------------------------------------------------------------------------------------
+// ---- experiments/fb_sym.cu -------------------------------------------------------------------------------------
 int fb_sym_plan(fb_context *c);   // FB_OK with c->sym == nullptr: not applicable, keep the full-matrix kernels
 int fb_sym_pack(fb_context *c);   // U <- upper(Keff), start of every solve
 void fb_sym_launch(fb_context *c, int mode, const double *x, double *y, const double *b, double *slots);
 int fb_sym_grid(const fb_context *c, int mode);
 size_t fb_sym_bytes_per_product(const fb_context *c);
 void fb_sym_release(fb_context *c);
-// ---- fb_tma.cu -------------------------------------------------------------------------------------
+// ---- experiments/fb_tma.cu -------------------------------------------------------------------------------------
 int fb_tma_plan(fb_context *c);   // FB_OK with c->tma == nullptr: not applicable, keep the default kernels
 void fb_tma_launch(fb_context *c, int mode, const double *x, double *y, const double *b, double *slots);
 int fb_tma_grid(const fb_context *c);

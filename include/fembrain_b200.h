@@ -98,6 +98,13 @@ int fb_create_with_constrained_dofs(fb_context **out, int num_vertices, const do
                                     int num_tets, const int *tets, int num_constrained_dofs,
                                     const int *constrained_dofs, const fb_params *params);
 void fb_destroy(fb_context *ctx);
+/* Deformable::syncForceModel on an existing model after its mesh changed (cutting: cutCompleted -> syncForceModel, main.cpp:614-617;
+ * DEF/Deformable.cpp:127-220 deletes and rebuilds TetMesh, CorotationalLinearFEM, force model, mass matrix and integrator).
+ * Full re-setup IN PLACE: the handle stays valid, parameters / timestep / damping / CG settings / gravity / floor / haptic radius
+ * are kept, state restarts at rest, haptic forces and the edge list are dropped (they index the old mesh).  ~10 ms at 1M tets
+ * from the memory pool (the reference's constructors: 18.8 s).  Uniform material (params); single-mesh contexts only. */
+int fb_sync_force_model(fb_context *ctx, int num_vertices, const double *rest_positions, int num_tets, const int *tets,
+                        int num_fixed_vertices, const int *fixed_vertices);
 
 /* Deformable::setFixedVertices + the integrator rebuild it needs.  (IntegratorBaseSparse::setConstrainedDOF,
  * integratorBaseSparse.cpp:73-87, updates the list but not systemMatrix — a reference bug; here the
@@ -228,6 +235,9 @@ size_t fb_device_bytes(const fb_context *ctx);           /* device memory held b
  * main.cpp:614-617, DEF/Deformable.cpp:127-220) does not pay for allocation again.  This gives unused pool memory
  * back to the driver. */
 int fb_trim_memory(void);
+/* 1 when the library was built with the shelved SpMV / PCG experiments of csrc/experiments/ (python -m fembrain_b200.build
+ * --experiments; selected at run time with FEMBRAIN_B200_SPMV=sym|tma, FEMBRAIN_B200_PCG=persistent), 0 for the default build */
+int fb_experiments_built(void);
 /* Debug aid (environment FEMBRAIN_B200_GUARD=1 at process start): every device allocation of every context is wrapped in
  * 256-byte guard bands; this call reports how many live allocations were checked and how many had a band overwritten (an
  * out-of-bounds write by one of the library's kernels).  Always 0 / 0 when the guard mode is off. */

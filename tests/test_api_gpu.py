@@ -201,3 +201,39 @@ def test_state_api_roundtrip_and_zero_force_rest():
     sim.reset_to_rest()
     sim.do_timestep()  # at rest with no load: f_int is rounding noise (K_el P - RK x0), so is the motion
     assert np.abs(sim.get_state()[0]).max() < 1e-12
+
+
+def test_sync_force_model_rebuilds_in_place(port_oracle):
+    """fb_sync_force_model = Deformable::syncForceModel after a cut (DEF/Deformable.cpp:127-220): same handle, new mesh, state at
+    rest, Deformable-level options kept; everything the new mesh's oracle says must hold bit for bit."""
+    import time
+
+    import fembrain_b200 as fb
+
+    v, t, fixed, load = cases.cube_case(8)
+    sim = fb.Simulation(v, t, fixed)
+    sim.set_gravity(True)
+    sim.set_floor(True, -3.0)
+    sim.set_external_forces(cases.point_load(sim.r, load))
+    sim.do_timestep()
+    # the "cut": another mesh altogether (fewer cells, other fixed set)
+    v2, t2, fixed2, load2 = cases.cube_case(6, 5, 7)
+    t0 = time.perf_counter()
+    sim.sync_force_model(v2, t2, fixed2)
+    dt = time.perf_counter() - t0
+    assert sim.r == 3 * len(v2) and dt < 5.0
+    q, qv, qa = sim.get_state()
+    assert not q.any() and not qv.any() and not qa.any()           # a new integrator starts at rest
+    ora = port_oracle.Oracle(v2, t2, fixed2, kind="port")
+    ia, ja, _ = sim.K_csr()
+    oia, oja, _ = ora.K_csr(values=False)
+    assert np.array_equal(ia, oia) and np.array_equal(ja, oja)
+    f = cases.point_load(sim.r, load2)
+    for s in (sim, ora):
+        s.set_external_forces(f)
+        assert s.do_timestep() == 0
+    assert np.array_equal(sim.K_values(), ora.K_values()) and np.array_equal(sim.rhs(), ora.rhs())
+    # options of the Deformable survived: gravity shows up in the next deformable frame's force vector
+    sim.deformable_timestep()
+    fe = sim.get_external_forces()
+    assert np.all(fe[1::3] == -10000.0)

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CHILD = r'''
-import json, sys
+import json, os, sys
 import numpy as np
 sys.path.insert(0, %r)
 import fembrain_b200 as fb
@@ -28,6 +28,12 @@ for name, mesh in (("cube7", cases.cube_case(7)[:3]), ("slab", cases.cube_case(5
                    ("beam3", cases.golden_mesh("beam3"))):
     v, t, fixed = mesh
     sim = fb.Simulation(v, t, fixed)
+    if os.environ.get("FB_GUARD_TEST_MG") == "1":   # the labelled solver variants and their level hierarchy
+        if name in ("cube7", "slab"):
+            sim.set_grid(*((7, 7, 7) if name == "cube7" else (5, 3, 9)))
+            sim.set_solver("mg")
+        else:
+            sim.set_solver("block_jacobi")
     load = int(np.argmax(v[:, 1] * 1000 + v[:, 0]))
     sim.set_external_forces(cases.point_load(sim.r, load))
     for _ in range(2):
@@ -55,13 +61,13 @@ print("GUARD_REPORT " + json.dumps(report))
 ''' % ROOT
 
 
-@pytest.mark.parametrize("variant", ["default", "twophase", "tma"])
+@pytest.mark.parametrize("variant", ["default", "twophase", "mg"])
 def test_no_kernel_writes_outside_its_buffers(variant):
     env = dict(os.environ, FEMBRAIN_B200_GUARD="1")
     if variant == "twophase":
         env["FEMBRAIN_B200_ASSEMBLY"] = "twophase"
-    if variant == "tma":
-        env["FEMBRAIN_B200_SPMV"] = "tma"
+    if variant == "mg":
+        env["FB_GUARD_TEST_MG"] = "1"
     out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("GUARD_REPORT ")][-1]

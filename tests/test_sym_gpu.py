@@ -6,7 +6,13 @@ import pytest
 
 from tests import cases
 
-pytestmark = pytest.mark.gpu
+def _built():
+    from fembrain_b200 import api
+
+    return api.experiments_built()
+
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not _built(), reason="shelved experiment (csrc/experiments/fb_sym.cu): build with `python -m fembrain_b200.build --experiments`")]
 
 
 def _pair(monkeypatch, v, t, fixed, **kw):

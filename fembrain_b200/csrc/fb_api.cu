@@ -717,7 +717,8 @@ int fb_get_super_maps(fb_context *c, int *superRows, int *superIdx) {
   return system_structure(c, nullptr, nullptr, nullptr, superRows, superIdx);
 }
 int fb_get_constrained_dofs(fb_context *c, int *dofs) {
-  if (!c || !dofs) return FB_ERR_INVALID_ARGUMENT;
+  if (!c || (!dofs && c->nC > 0)) return FB_ERR_INVALID_ARGUMENT;   // an empty list needs no buffer (a rank without fixed vertices)
+  if (c->nC == 0) return FB_OK;
   memcpy(dofs, c->cdofs_host, sizeof(int) * (size_t)c->nC);
   return FB_OK;
 }

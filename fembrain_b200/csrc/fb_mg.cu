@@ -90,6 +90,10 @@ struct FbMg {
   int nDense;
   double *slotsM, *slotsZ;   // per-CTA partial sums: weighted residual, r.z
   int nu;                    // smoothing sweeps before and after the coarse correction
+  int useGraph, capturing, subFailed, subKernels;   // levels >= 1 replayed as one CUDA graph
+  void *subGraph;            // cudaGraphExec_t
+  float *subResult;
+  int preDone;               // the finest level's first smoothing sweep was fused into k_mgcg_update for this cycle
   int half;                  // 1: FP16 storage of the levels' matrices (default), 0: FP32
   int solves;                // since the last lambda_max estimate
   int prepared;
@@ -355,14 +359,15 @@ struct GridMaps {
   const float *fw[3];
 };
 
-// b_c = P^T res_f : one thread per coarse DOF gathers the fine nodes between its neighbouring coarse nodes (fixed order)
+// b_c = P^T res_f : one thread per coarse VERTEX gathers the fine vertices between its neighbouring coarse nodes (fixed order),
+// one float4 load per fine vertex
 __global__ void __launch_bounds__(MG_TB) k_mg_restrict(GridMaps g, const float *__restrict__ rf, const unsigned char *__restrict__ maskC,
                                                        float *__restrict__ bc, float *__restrict__ xc_zero, const FbScalars *sc) {
   if (sc && sc->done) return;
+  (void)xc_zero;
   const size_t nC = (size_t)g.nc[0] * g.nc[1] * g.nc[2];
-  for (size_t t = (size_t)blockIdx.x * MG_TB + threadIdx.x; t < 3 * nC; t += (size_t)gridDim.x * MG_TB) {
-    const size_t V = t / 3;
-    const int k = (int)(t - 3 * V);
+  const float4 *rf4 = reinterpret_cast<const float4 *>(rf);
+  for (size_t V = (size_t)blockIdx.x * MG_TB + threadIdx.x; V < nC; V += (size_t)gridDim.x * MG_TB) {
     const int K = (int)(V % g.nc[2]), J = (int)((V / g.nc[2]) % g.nc[1]), I = (int)(V / ((size_t)g.nc[2] * g.nc[1]));
     const int C[3] = {I, J, K};
     int lo[3], hi[3];
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(MG_TB) k_mg_restrict(GridMaps g, const float *
       lo[d] = C[d] > 0 ? g.cidx[d][C[d] - 1] + 1 : g.cidx[d][C[d]];
       hi[d] = C[d] + 1 < g.nc[d] ? g.cidx[d][C[d] + 1] - 1 : g.cidx[d][C[d]];
     }
-    float s = 0.f;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
     for (int i = lo[0]; i <= hi[0]; i++) {
       const float wi = (g.fa[0][i] == I) ? 1.f - g.fw[0][i] : g.fw[0][i];
       for (int j = lo[1]; j <= hi[1]; j++) {
@@ -378,28 +383,30 @@ __global__ void __launch_bounds__(MG_TB) k_mg_restrict(GridMaps g, const float *
         for (int kk = lo[2]; kk <= hi[2]; kk++) {
           const float wk = (g.fa[2][kk] == K) ? 1.f - g.fw[2][kk] : g.fw[2][kk];
           const size_t f = ((size_t)i * g.nf[1] + j) * g.nf[2] + kk;
-          s = fmaf(wi * wj * wk, rf[VS * f + k], s);
+          const float w = wi * wj * wk;
+          const float4 r = __ldg(rf4 + f);
+          sx = fmaf(w, r.x, sx); sy = fmaf(w, r.y, sy); sz = fmaf(w, r.z, sz);
         }
       }
     }
-    bc[VS * V + k] = maskC[t] ? 0.f : s;
-    (void)xc_zero;
+    float4 o;
+    o.x = maskC[3 * V] ? 0.f : sx; o.y = maskC[3 * V + 1] ? 0.f : sy; o.z = maskC[3 * V + 2] ? 0.f : sz; o.w = 0.f;
+    reinterpret_cast<float4 *>(bc)[V] = o;
   }
 }
 
-// x_f += P x_c : one thread per fine DOF, trilinear weights; constrained fine DOFs stay untouched (zero)
+// x_f += P x_c : one thread per fine VERTEX, trilinear weights, float4 loads; constrained fine DOFs stay untouched (zero)
 __global__ void __launch_bounds__(MG_TB) k_mg_prolong_add(GridMaps g, const float *__restrict__ xc, const unsigned char *__restrict__ maskF,
                                                           float *__restrict__ xf, const FbScalars *sc) {
   if (sc && sc->done) return;
   const size_t nF = (size_t)g.nf[0] * g.nf[1] * g.nf[2];
-  for (size_t t = (size_t)blockIdx.x * MG_TB + threadIdx.x; t < 3 * nF; t += (size_t)gridDim.x * MG_TB) {
-    if (maskF[t]) continue;
-    const size_t v = t / 3;
-    const int k = (int)(t - 3 * v);
+  const float4 *xc4 = reinterpret_cast<const float4 *>(xc);
+  float4 *xf4 = reinterpret_cast<float4 *>(xf);
+  for (size_t v = (size_t)blockIdx.x * MG_TB + threadIdx.x; v < nF; v += (size_t)gridDim.x * MG_TB) {
     const int kk = (int)(v % g.nf[2]), j = (int)((v / g.nf[2]) % g.nf[1]), i = (int)(v / ((size_t)g.nf[2] * g.nf[1]));
     const int a[3] = {g.fa[0][i], g.fa[1][j], g.fa[2][kk]};
     const float w[3] = {g.fw[0][i], g.fw[1][j], g.fw[2][kk]};
-    float s = 0.f;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
     for (int di = 0; di < 2; di++) {
       const float wi = di ? w[0] : 1.f - w[0];
       if (wi == 0.f) continue;
@@ -410,11 +417,17 @@ __global__ void __launch_bounds__(MG_TB) k_mg_prolong_add(GridMaps g, const floa
           const float wk = dk ? w[2] : 1.f - w[2];
           if (wk == 0.f) continue;
           const size_t V = ((size_t)(a[0] + di) * g.nc[1] + (a[1] + dj)) * g.nc[2] + (a[2] + dk);
-          s = fmaf(wi * wj * wk, xc[VS * V + k], s);
+          const float ww = wi * wj * wk;
+          const float4 c = __ldg(xc4 + V);
+          sx = fmaf(ww, c.x, sx); sy = fmaf(ww, c.y, sy); sz = fmaf(ww, c.z, sz);
         }
       }
     }
-    xf[VS * v + k] += s;
+    float4 x = xf4[v];
+    if (!maskF[3 * v]) x.x += sx;
+    if (!maskF[3 * v + 1]) x.y += sy;
+    if (!maskF[3 * v + 2]) x.z += sz;
+    xf4[v] = x;
   }
 }
 
@@ -544,23 +557,40 @@ __global__ void __launch_bounds__(MG_TB) k_mgcg_begin(int n, const float *__rest
   }
 }
 
-// alpha = r.z / d.q; x += alpha d; r -= alpha q; r32 = r; m partial
-__global__ void __launch_bounds__(MG_TB) k_mgcg_update(int n, const double *__restrict__ d, const double *__restrict__ q,
+// alpha = r.z / d.q; x += alpha d; r -= alpha q; m partial; r32 = r and — when Binv is given — the cycle's first smoothing
+// sweep from the zero guess, x1 = omega Binv r32, in the same pass (one thread per vertex: it holds all three components)
+__global__ void __launch_bounds__(MG_TB) k_mgcg_update(int nV, const double *__restrict__ d, const double *__restrict__ q,
                                                        const double *__restrict__ invD, double *__restrict__ x, double *__restrict__ r,
                                                        float *__restrict__ r32, const FbScalars *sc, int it, const double *dqSlots,
-                                                       int nDq, double *slotsM) {
+                                                       int nDq, double *slotsM, const float *__restrict__ Binv, float omega,
+                                                       float *__restrict__ x1) {
   pdl_wait();
   pdl_trigger();
   if (sc->done) return;
   const double dq = cta_sum_slots<MG_TB>(dqSlots, nDq);
   const double alpha = sc->rho[(it - 1) & 1] / dq;
   double part = 0.0;
-  for (size_t i = (size_t)blockIdx.x * MG_TB + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * MG_TB) {
-    x[i] = fma(alpha, d[i], x[i]);
-    const double ri = fma(-alpha, q[i], r[i]);
-    r[i] = ri;
-    r32[i + i / 3] = (float)ri;
-    part = fma(ri * ri, invD[i], part);
+  for (size_t v = (size_t)blockIdx.x * MG_TB + threadIdx.x; v < (size_t)nV; v += (size_t)gridDim.x * MG_TB) {
+    float rv[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const size_t i = 3 * v + k;
+      x[i] = fma(alpha, d[i], x[i]);
+      const double ri = fma(-alpha, q[i], r[i]);
+      r[i] = ri;
+      rv[k] = (float)ri;
+      part = fma(ri * ri, invD[i], part);
+    }
+    reinterpret_cast<float4 *>(r32)[v] = make_float4(rv[0], rv[1], rv[2], 0.f);
+    if (Binv) {
+      const float *bi = Binv + 9 * v;
+      float4 o;
+      o.x = omega * fmaf(bi[0], rv[0], fmaf(bi[1], rv[1], bi[2] * rv[2]));
+      o.y = omega * fmaf(bi[3], rv[0], fmaf(bi[4], rv[1], bi[5] * rv[2]));
+      o.z = omega * fmaf(bi[6], rv[0], fmaf(bi[7], rv[1], bi[8] * rv[2]));
+      o.w = 0.f;
+      reinterpret_cast<float4 *>(x1)[v] = o;
+    }
   }
   block_reduce_to_slot<MG_TB>(part, slotsM);
 }
@@ -688,6 +718,8 @@ template <int MODE, bool DOT>
 void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, const float *x, const float *b, float omega, float *out,
                     double *slots, const FbScalars *sc);
 
+void drop_subcycle_graph(FbMg *mg);
+
 // lambda_max(Binv A) of one level by power iteration (host reads the norms: only at setup and every 32 solves)
 int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
   cudaStream_t st = c->stream;
@@ -715,6 +747,7 @@ int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
     c->launches++;
   }
   L.lmax = (float)((lam > 0.0 && std::isfinite(lam)) ? lam : 3.0);
+  drop_subcycle_graph(mg);   // omega is a constant of the captured kernels
   return FB_OK;
 }
 
@@ -728,6 +761,41 @@ void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, c
   else
     fb_launch(pdl, c->stream, k_mg_spmv<float, MODE, DOT>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, (const float *)L.AB, (const float *)L.scale, x, b,
               (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
+}
+
+float *vcycle(fb_context *c, FbMg *mg, int li);
+
+// The sub-cycle of levels >= 1 is ~30 kernels of a few microseconds each: launch latency, not work (185 us of a 1.08 ms
+// iteration at 10M tets, profiles/r02_mg_iteration_phases.txt).  Captured once per hierarchy / lambda_max estimate into a CUDA
+// graph (pointers and omegas are constants of the capture) and replayed with one launch per cycle.
+float *subcycle_graph(fb_context *c, FbMg *mg) {
+  cudaStream_t st = c->stream;
+  if (mg->subFailed) return nullptr;
+  if (!mg->subGraph) {
+    const long long before = c->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); mg->subFailed = 1; return nullptr; }
+    mg->capturing = 1;
+    mg->subResult = vcycle(c, mg, 1);
+    mg->capturing = 0;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    mg->subKernels = (int)(c->launches - before);
+    c->launches = before;
+    if (e != cudaSuccess || !graph) { cudaGetLastError(); mg->subFailed = 1; return nullptr; }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); mg->subFailed = 1; return nullptr; }
+    mg->subGraph = exec;
+  }
+  if (cudaGraphLaunch((cudaGraphExec_t)mg->subGraph, st) != cudaSuccess) { cudaGetLastError(); mg->subFailed = 1; return nullptr; }
+  c->launches += mg->subKernels;
+  return mg->subResult;
+}
+
+void drop_subcycle_graph(FbMg *mg) {
+  if (mg->subGraph) { cudaGraphExecDestroy((cudaGraphExec_t)mg->subGraph); mg->subGraph = nullptr; }
+  mg->subFailed = 0;
 }
 
 // z = V(b) on level li; returns the vector holding the result (li = 0: with the dot b.z into slotsZ)
@@ -745,29 +813,35 @@ float *vcycle(fb_context *c, FbMg *mg, int li) {
   const float omega = 1.4f / L.lmax;
   const GridMaps g = maps_of(L);
   const int nu = mg->nu;
-  // pre-smoothing from the zero guess: the first sweep needs no product
-  fb_launch(true, st, k_mg_presmooth<false>, L.grid_vec, MG_TB, L.nV, L.Binv, L.b, omega, L.x, (double *)nullptr, sc);
-  c->launches++;
+  const bool pdl = !mg->capturing;   // inside a captured sub-cycle the graph's own edges order the kernels
+  // pre-smoothing from the zero guess: the first sweep needs no product (on the finest level the CG update kernel has
+  // already written it together with r32, except before the first iteration)
+  if (!(li == 0 && mg->preDone)) {
+    fb_launch(pdl, st, k_mg_presmooth<false>, L.grid_vec, MG_TB, L.nV, L.Binv, L.b, omega, L.x, (double *)nullptr, sc);
+    c->launches++;
+  }
   float *cur = L.x, *alt = L.xn;
   for (int s = 1; s < nu; s++) {
-    launch_mg_spmv<1, false>(c, mg, L, true, cur, L.b, omega, alt, nullptr, sc);
+    launch_mg_spmv<1, false>(c, mg, L, pdl, cur, L.b, omega, alt, nullptr, sc);
     c->launches++;
     std::swap(cur, alt);
   }
-  launch_mg_spmv<0, false>(c, mg, L, true, cur, L.b, omega, L.res, nullptr, sc);
+  launch_mg_spmv<0, false>(c, mg, L, pdl, cur, L.b, omega, L.res, nullptr, sc);
   if (li == 0) tm_mark(st, "presmooth + residual (level 0)");
   k_mg_restrict<<<C.grid_vec, MG_TB, 0, st>>>(g, L.res, C.ctx->rowmask, C.b, (float *)nullptr, sc);
   c->launches += 2;
   if (li == 0) tm_mark(st, "restrict (level 0 -> 1)");
-  float *coarse = vcycle(c, mg, li + 1);
+  float *coarse = nullptr;
+  if (li == 0 && mg->useGraph && !mg->capturing) coarse = subcycle_graph(c, mg);   // levels >= 1 as ONE graph launch (~30 small kernels)
+  if (!coarse) coarse = vcycle(c, mg, li + 1);
   if (li == 0) tm_mark(st, "levels >= 1");
   k_mg_prolong_add<<<L.grid_vec, MG_TB, 0, st>>>(g, coarse, lc->rowmask, cur, sc);
   c->launches++;
   if (li == 0) tm_mark(st, "prolong (level 1 -> 0)");
   for (int s = 0; s < nu; s++) {   // the same sweeps after the correction: the cycle stays symmetric
     const bool last = s == nu - 1;
-    if (li == 0 && last) launch_mg_spmv<1, true>(c, mg, L, true, cur, L.b, omega, alt, mg->slotsZ, sc);
-    else launch_mg_spmv<1, false>(c, mg, L, true, cur, L.b, omega, alt, nullptr, sc);
+    if (li == 0 && last) launch_mg_spmv<1, true>(c, mg, L, pdl, cur, L.b, omega, alt, mg->slotsZ, sc);
+    else launch_mg_spmv<1, false>(c, mg, L, pdl, cur, L.b, omega, alt, nullptr, sc);
     c->launches++;
     std::swap(cur, alt);
   }
@@ -794,6 +868,7 @@ int apply_preconditioner(fb_context *c, FbMg *mg, float **z) {
 void fb_mg_release(fb_context *c) {
   FbMg *mg = c->mg;
   if (!mg) return;
+  drop_subcycle_graph(mg);
   for (int li = mg->nLevels - 1; li >= 0; li--) free_level(c, mg->L[li], li);
   if (mg->dense) fb_dev_free(mg->dense);
   if (mg->denseInv) fb_dev_free(mg->denseInv);
@@ -809,6 +884,7 @@ static int mg_ensure(fb_context *c) {
   memset(mg, 0, sizeof(*mg));
   c->mg = mg;
   mg->half = !(getenv("FEMBRAIN_B200_MG_PREC") && !strcmp(getenv("FEMBRAIN_B200_MG_PREC"), "fp32"));
+  mg->useGraph = !(getenv("FEMBRAIN_B200_MG_GRAPH") && atoi(getenv("FEMBRAIN_B200_MG_GRAPH")) == 0);
   mg->nu = 1;
   if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = atoi(getenv("FEMBRAIN_B200_MG_NU"));
   FB_TRY(fb_dev_alloc(c, &mg->slotsM, 2 * (size_t)MG_SLOTS));
@@ -819,6 +895,7 @@ static int mg_ensure(fb_context *c) {
 // builds (or rebuilds) the level hierarchy for the current variant; level 0 always exists for variants != 0
 static int mg_build(fb_context *c) {
   FbMg *mg = c->mg;
+  drop_subcycle_graph(mg);
   for (int li = mg->nLevels - 1; li >= 0; li--) free_level(c, mg->L[li], li);
   mg->nLevels = 0;
   mg->prepared = 0;
@@ -986,6 +1063,7 @@ int fb_mg_prepare(fb_context *c) {
 void fb_mg_invalidate(fb_context *c) {
   FbMg *mg = c->mg;
   if (!mg) return;
+  drop_subcycle_graph(mg);
   for (int li = mg->nLevels - 1; li >= 0; li--) free_level(c, mg->L[li], li);
   mg->nLevels = 0;
   mg->prepared = 0;
@@ -1012,7 +1090,10 @@ int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
   k_mgcg_init<<<gv, MG_TB, 0, st>>>(n, c->rhs, c->invD, c->x, c->res, L.b, warm, slotsM0, slotsM, c->sc);
   c->launches++;
   float *z = nullptr;
+  mg->preDone = 0;
   int nZ = apply_preconditioner(c, mg, &z);
+  const bool cyc = mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1;
+  const float omega0 = cyc ? 1.4f / L.lmax : 0.f;
   k_mgcg_begin<<<gv, MG_TB, 0, st>>>(n, z, c->dir, c->sc, slotsM0, slotsM, mg->slotsZ, gv, nZ, eps, maxIt);
   c->launches++;
   const int CH = 6;
@@ -1032,8 +1113,9 @@ int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
       FB_TRY(fb_pcg_launch_product_dq(c, c->dir, c->Ad, &nDq));    // q = A d, d.q partials in c->partials
       tm_mark(st, "FP64 product A d");
       if (sample) { cudaEventRecord(c->evProf[2 * c->nprof + 1], st); c->nprof++; }
-      fb_launch(true, st, k_mgcg_update, gv, MG_TB, n, c->dir, c->Ad, c->invD, c->x, c->res, L.b, (const FbScalars *)c->sc, it,
-                (const double *)c->partials, nDq, slotsM);
+      fb_launch(true, st, k_mgcg_update, gv, MG_TB, L.nV, c->dir, c->Ad, c->invD, c->x, c->res, L.b, (const FbScalars *)c->sc, it,
+                (const double *)c->partials, nDq, slotsM, (const float *)(cyc ? L.Binv : nullptr), omega0, L.x);
+      mg->preDone = cyc ? 1 : 0;
       fb_launch(true, st, k_mgcg_check, 1, MG_TB, c->sc, it, (const double *)slotsM, gv);
       c->launches += 2;
       tm_mark(st, "update + check");

@@ -331,6 +331,27 @@ def _libc_fflush():
         pass
 
 
+def apply_fem_displacements(rest_xyzw, displacements):
+    """GPUPoly::applyFemDisplacements (src/implicit/OclPolygonizer.cpp:1543-1584) with the reference's own OpenCL kernel
+    ApplyVertexDeformations (data/opencl/Polygonizer.cl:1417-1427) compiled from its text for the CPU
+    (oracle/cl_kernel_harness.cpp): float4 out = rest + float4(displacement, 0)."""
+    lib = _lib("ref")
+    fn = lib.fbcl_apply_fem_displacements
+    fn.restype, fn.argtypes = None, [C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    rest = np.ascontiguousarray(rest_xyzw, dtype=np.float32).reshape(-1, 4)
+    d = _f64(displacements).reshape(-1)
+    n = len(rest)
+    assert d.size >= 3 * n
+    out = np.full((n + 64, 4), np.float32(-7.0))   # work items past ctVertices must not write
+    fn(n, rest.ctypes.data, d.ctypes.data, out.ctypes.data)
+    assert np.all(out[n:] == np.float32(-7.0))
+    return out[:n].copy()
+
+
+def cl_kernel_available() -> bool:
+    return available("ref") and hasattr(_lib("ref"), "fbcl_apply_fem_displacements")
+
+
 def deformable_available() -> bool:
     """True when oracle/_ref holds the compiled Deformable (built from /root/reference by oracle/Makefile)."""
     if not available("ref"):

@@ -119,6 +119,26 @@ def test_export_positions_float4_matches_apply_vertex_deformations():
     out2 = sim.export_positions_float4(None, count=17)
     exp = np.concatenate([v[:17].astype(np.float32), np.ones((17, 1), np.float32)], axis=1) + disp[:17]
     assert np.array_equal(out2, exp)
+    # ... and against the reference's OWN kernel text + host repack, compiled for the CPU (oracle/cl_kernel_harness.cpp)
+    from oracle import pyoracle
+
+    if pyoracle.cl_kernel_available():
+        assert np.array_equal(out, pyoracle.apply_fem_displacements(rest, q.reshape(-1)))
+        assert np.array_equal(out2, pyoracle.apply_fem_displacements(np.concatenate([v[:17].astype(np.float32), np.ones((17, 1), np.float32)], axis=1), q.reshape(-1)))
+
+
+def test_numpy_hand_off_restatement_matches_the_reference_kernel(ref_oracle):
+    """CPU pin of the N1 checker: rest + float32(displacement) in numpy == ApplyVertexDeformations + the host repack of
+    GPUPoly::applyFemDisplacements, on values that exercise float rounding (large rest coordinates, tiny displacements)."""
+    if not ref_oracle.cl_kernel_available():
+        pytest.skip("oracle/_ref was built without the OpenCL kernel harness")
+    rng = np.random.default_rng(9)
+    n = 1000
+    rest = np.concatenate([(rng.standard_normal((n, 3)) * 1e3).astype(np.float32), np.ones((n, 1), np.float32)], axis=1)
+    q = rng.standard_normal(3 * n) * 1e-4
+    out = ref_oracle.apply_fem_displacements(rest, q)
+    disp = np.concatenate([q.reshape(-1, 3).astype(np.float32), np.zeros((n, 1), np.float32)], axis=1)
+    assert np.array_equal(out, rest + disp)
 
 
 def _write_tetgen(base, v, t, comment=True):

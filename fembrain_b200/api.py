@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfembrain_b200.so")
+LIB_PATH = os.environ.get("FEMBRAIN_B200_LIB") or os.path.join(_HERE, "libfembrain_b200.so")   # (override: A/B timing of two builds)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fembrain_b200.h")
 
 FB_OK = 0

@@ -76,6 +76,12 @@ struct MgLevel {
   int *twin;                 // device [nV of the coarser level]: fine vertex coinciding with each coarse vertex
   float lmax;
   int grid_spmv, grid_vec;
+  // structured storage of the level's matrix (tensor-grid levels: every row's blocks sit at a subset of ONE set of <= 16 grid
+  // offsets): AE[slot][vertex][3][4] __half, empty slots zero; see k_mg_spmv_ell
+  __half *AE;
+  int nSlots, grid_ell;
+  int slotOff[16];           // vertex-index offset of every slot
+  signed char slotOf[27];    // (di+1)*9 + (dj+1)*3 + (dk+1) -> slot, -1 = not in the stencil
 };
 
 }  // namespace
@@ -90,6 +96,8 @@ struct FbMg {
   int nDense;
   double *slotsM, *slotsZ;   // per-CTA partial sums: weighted residual, r.z
   int nu;                    // smoothing sweeps before and after the coarse correction
+  int useEll;                // structured slot-major storage + k_mg_spmv_ell on tensor-grid levels (FP16 storage only)
+  signed char *slotOfDev;    // device copies of every level's slotOf table, 27 bytes per level
   int useGraph, capturing, subFailed, subKernels;   // levels >= 1 replayed as one CUDA graph
   void *subGraph;            // cudaGraphExec_t
   float *subResult;
@@ -331,6 +339,124 @@ __global__ void __launch_bounds__(MG_TB, 4) k_mg_spmv(int nV, const int *__restr
     }
   }
   if (DOT) block_reduce_to_slot<MG_TB>(part, slots);
+}
+
+// ---- structured product for tensor-grid levels -----------------------------------------------------------------------
+// On a tensor grid the tet stencil is the same set of grid offsets (di, dj, dk) for every vertex (15 of the 27 for the
+// TruthCube split; boundary vertices use a subset).  Storing the blocks slot-major, AE[slot][vertex], turns the product into
+// a streaming kernel: ONE THREAD PER ROW, matrix loads coalesced across the threads of a warp (24 contiguous bytes per
+// thread and slot), x staged through shared memory as nine runs of consecutive vertices (one per (di, dj)), no shuffles.
+// That removes the scattered float4 gathers whose L1 wavefronts bounded k_mg_spmv (77 % of the LSU data pipe at 4.5 TB/s,
+// profiles/r02_mg_spmv16_ncu_details.txt).
+struct EllArgs {
+  int nV, nSlots, nz, nynz;
+  int slotOff[16];        // di * ny*nz + dj * nz + dk
+  signed char slotSeg[16];   // (di+1)*3 + (dj+1): which of the nine staged runs
+  signed char slotDk[16];
+};
+
+constexpr int ELL_T = 128;   // rows (threads) per tile
+
+__global__ void __launch_bounds__(MG_TB) k_mg_pack_ell(int nB, int nV, int ny, int nz, const int *__restrict__ bp, const int *__restrict__ brow,
+                                                       const int *__restrict__ bc, const double *__restrict__ A, const float *__restrict__ scale,
+                                                       const signed char *__restrict__ slotOf27, __half *__restrict__ AE) {
+  const float s = scale[0];
+  for (size_t b = (size_t)blockIdx.x * MG_TB + threadIdx.x; b < (size_t)nB; b += (size_t)gridDim.x * MG_TB) {
+    const int v = brow[b], c = bc[b], rs = bp[v], nb = bp[v + 1] - rs, j = (int)b - rs;
+    const int vk = v % nz, vj = (v / nz) % ny, vi = v / (nz * ny);
+    const int ck = c % nz, cj = (c / nz) % ny, ci = c / (nz * ny);
+    const int slot = slotOf27[(ci - vi + 1) * 9 + (cj - vj + 1) * 3 + (ck - vk + 1)];
+    const double *a = A + 9 * (size_t)rs + 3 * j;
+    __half *o = AE + 12 * ((size_t)slot * nV + v);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+      for (int l = 0; l < 3; l++) o[4 * k + l] = __float2half_rn((float)(a[(size_t)k * 3 * nb + l] * (double)s));
+      o[4 * k + 3] = __float2half_rn(0.f);
+    }
+  }
+}
+
+// MODE 0: out = mask(b - A x);  MODE 1: out = x + omega Binv (b - A x) [DOT: sum b . out];  MODE 2: out = Binv (A x)
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(ELL_T, 8) k_mg_spmv_ell(EllArgs g, const __half *__restrict__ AE, const float *__restrict__ scale,
+                                                         const float *__restrict__ x, const float *__restrict__ b,
+                                                         const float *__restrict__ Binv, const unsigned char *__restrict__ mask, float omega,
+                                                         float *__restrict__ out, double *slots, const FbScalars *sc) {
+  pdl_wait();
+  pdl_trigger();
+  if (sc && sc->done) return;
+  __shared__ float4 xs[9][ELL_T + 2];
+  const float inv = __ldg(scale + 1);
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  const uint2 *AR = reinterpret_cast<const uint2 *>(AE);
+  double part = 0.0;
+  const int nTiles = (g.nV + ELL_T - 1) / ELL_T;
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int v0 = tile * ELL_T;
+    // the nine runs of x this tile's rows can touch: vertices v0 + (di ny nz + dj nz) - 1 ... + ELL_T (clamped: out-of-range
+    // and wrapped positions only ever meet structurally zero blocks)
+    for (int e = threadIdx.x; e < 9 * (ELL_T + 2); e += ELL_T) {
+      const int seg = e / (ELL_T + 2), t = e - seg * (ELL_T + 2);
+      long long idx = (long long)v0 + (long long)(seg / 3 - 1) * g.nynz + (long long)(seg % 3 - 1) * g.nz - 1 + t;
+      idx = idx < 0 ? 0 : (idx >= g.nV ? g.nV - 1 : idx);
+      xs[seg][t] = __ldg(x4 + idx);
+    }
+    __syncthreads();
+    const int v = v0 + threadIdx.x;
+    if (v < g.nV) {
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+      for (int s0 = 0; s0 < g.nSlots; s0 += 5) {
+        uint2 w[5][3];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          const int sl = s0 + q;
+          if (sl < g.nSlots) {
+            const uint2 *p = AR + 3 * ((size_t)sl * g.nV + v);
+            w[q][0] = __ldcs(p); w[q][1] = __ldcs(p + 1); w[q][2] = __ldcs(p + 2);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          const int sl = s0 + q;
+          if (sl < g.nSlots) {
+            const float4 xv = xs[g.slotSeg[sl]][threadIdx.x + 1 + g.slotDk[sl]];
+            float a0, a1, a2;
+            mg_unpack(w[q][0], a0, a1, a2); acc0 = fmaf(a0, xv.x, fmaf(a1, xv.y, fmaf(a2, xv.z, acc0)));
+            mg_unpack(w[q][1], a0, a1, a2); acc1 = fmaf(a0, xv.x, fmaf(a1, xv.y, fmaf(a2, xv.z, acc1)));
+            mg_unpack(w[q][2], a0, a1, a2); acc2 = fmaf(a0, xv.x, fmaf(a1, xv.y, fmaf(a2, xv.z, acc2)));
+          }
+        }
+      }
+      acc0 *= inv; acc1 *= inv; acc2 *= inv;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 0) {
+        const float4 bv = *reinterpret_cast<const float4 *>(b + VS * (size_t)v);
+        o.x = mask[3 * (size_t)v] ? 0.f : bv.x - acc0;
+        o.y = mask[3 * (size_t)v + 1] ? 0.f : bv.y - acc1;
+        o.z = mask[3 * (size_t)v + 2] ? 0.f : bv.z - acc2;
+      } else {
+        float r0 = acc0, r1 = acc1, r2 = acc2;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 1) {
+          bv = *reinterpret_cast<const float4 *>(b + VS * (size_t)v);
+          r0 = bv.x - acc0; r1 = bv.y - acc1; r2 = bv.z - acc2;
+        }
+        const float *bi = Binv + 9 * (size_t)v;
+        o.x = fmaf(bi[0], r0, fmaf(bi[1], r1, bi[2] * r2));
+        o.y = fmaf(bi[3], r0, fmaf(bi[4], r1, bi[5] * r2));
+        o.z = fmaf(bi[6], r0, fmaf(bi[7], r1, bi[8] * r2));
+        if (MODE == 1) {
+          const float4 xc = xs[4][threadIdx.x + 1];   // the row's own vertex: run (di, dj) = (0, 0), dk = 0
+          o.x = fmaf(omega, o.x, xc.x); o.y = fmaf(omega, o.y, xc.y); o.z = fmaf(omega, o.z, xc.z);
+          if (DOT) part = fma((double)bv.x, (double)o.x, fma((double)bv.y, (double)o.y, fma((double)bv.z, (double)o.z, part)));
+        }
+      }
+      reinterpret_cast<float4 *>(out)[v] = o;
+    }
+    __syncthreads();
+  }
+  if (DOT) block_reduce_to_slot<ELL_T>(part, slots);
 }
 
 // x = omega Binv b  (a smoothing step from the zero initial guess)   [DOT: also sum b . x, for the one-level variant]
@@ -673,7 +799,7 @@ void grid_mesh(const std::vector<double> ax[3], std::vector<double> &verts, std:
 }
 
 void free_level(fb_context *owner, MgLevel &L, int li) {
-  void *ptrs[] = {L.AB, L.scale, L.Binv, L.b, L.x, L.xn, L.res, L.pv, L.u, L.twin, L.cidx[0], L.cidx[1], L.cidx[2], L.fa[0], L.fa[1], L.fa[2],
+  void *ptrs[] = {L.AE, L.AB, L.scale, L.Binv, L.b, L.x, L.xn, L.res, L.pv, L.u, L.twin, L.cidx[0], L.cidx[1], L.cidx[2], L.fa[0], L.fa[1], L.fa[2],
                   L.fw[0], L.fw[1], L.fw[2]};
   for (void *p : ptrs)
     if (p) fb_dev_free(p);
@@ -686,17 +812,14 @@ int alloc_level_vectors(fb_context *c, MgLevel &L, bool half) {
   fb_context *lc = L.ctx;
   L.nV = lc->nV; L.r = lc->r;
   {
-    unsigned char *ab = nullptr;   // 12 entries per block, 2 (FP16) or 4 (FP32) bytes each
-    FB_TRY(fb_dev_alloc(c, &ab, (size_t)lc->nB * 12 * (half ? 2 : 4) + 64));
-    L.AB = ab;
     FB_TRY(fb_dev_alloc(c, &L.scale, 4));
     const float init[4] = {1.f, 1.f, 0.f, 0.f};
     FB_CUDA(cudaMemcpyAsync(L.scale, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     const unsigned int inf = 0x7f800000u;
     FB_CUDA(cudaMemcpyAsync(L.scale + 2, &inf, sizeof(inf), cudaMemcpyHostToDevice, c->stream));
     FB_CUDA(cudaStreamSynchronize(c->stream));
+    (void)half;
   }
-  FB_TRY(fb_dev_alloc(c, &L.Binv, 9 * (size_t)lc->nV));
   float **vecs[] = {&L.b, &L.x, &L.xn, &L.res, &L.pv};
   for (float **v : vecs) {
     FB_TRY(fb_dev_alloc(c, v, (size_t)VS * lc->nV + 4));   // (x, y, z, 0) per vertex; the fourth entries stay zero for ever
@@ -719,6 +842,52 @@ void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, c
                     double *slots, const FbScalars *sc);
 
 void drop_subcycle_graph(FbMg *mg);
+
+// Storage of one level's reduced-precision matrix: slot-major (structured) when the level is a tensor grid whose rows use at
+// most 16 distinct grid offsets and FP16 storage is on; otherwise the padded block rows of k_mg_spmv.
+int setup_level_matrix(fb_context *c, FbMg *mg, MgLevel &L, int li) {
+  fb_context *lc = L.ctx;
+  L.AE = nullptr; L.nSlots = 0;
+  const bool grid = L.n[0] > 0 && (long long)L.n[0] * L.n[1] * L.n[2] == (long long)lc->nV;
+  if (mg->half && mg->useEll && grid && lc->nV > 0) {
+    std::vector<int> bp, bc;
+    FB_TRY(fb_fetch_structure(lc, bp, bc));
+    const int ny = L.n[1], nz = L.n[2];
+    bool used[27] = {false}, ok = true;
+    for (int v = 0; v < lc->nV && ok; v++) {
+      const int vk = v % nz, vj = (v / nz) % ny, vi = v / (nz * ny);
+      for (int p = bp[v]; p < bp[v + 1]; p++) {
+        const int cc = bc[p];
+        const int dk = cc % nz - vk, dj = (cc / nz) % ny - vj, di = cc / (nz * ny) - vi;
+        if (di < -1 || di > 1 || dj < -1 || dj > 1 || dk < -1 || dk > 1) { ok = false; break; }
+        used[(di + 1) * 9 + (dj + 1) * 3 + (dk + 1)] = true;
+      }
+    }
+    int n = 0;
+    for (int o = 0; o < 27; o++) {
+      L.slotOf[o] = -1;
+      if (used[o]) { if (n < 16) { L.slotOf[o] = (signed char)n; L.slotOff[n] = (o / 9 - 1) * ny * nz + ((o / 3) % 3 - 1) * nz + (o % 3 - 1); } n++; }
+    }
+    if (ok && n <= 16 && used[13]) {
+      L.nSlots = n;
+      FB_TRY(fb_dev_alloc(c, &L.AE, (size_t)n * lc->nV * 12 + 8));
+      FB_CUDA(cudaMemsetAsync(L.AE, 0, sizeof(__half) * ((size_t)n * lc->nV * 12 + 8), c->stream));   // empty slots stay zero for ever
+      FB_CUDA(cudaMemcpyAsync(mg->slotOfDev + 27 * li, L.slotOf, 27, cudaMemcpyHostToDevice, c->stream));
+      FB_CUDA(cudaStreamSynchronize(c->stream));
+      int perSM = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_mg_spmv_ell<1, true>, ELL_T, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
+      size_t cap = (size_t)c->sm_count * perSM;
+      if (cap > MG_SLOTS) cap = MG_SLOTS;
+      const size_t tiles = ((size_t)lc->nV + ELL_T - 1) / ELL_T;
+      L.grid_ell = (int)std::max<size_t>(1, std::min(tiles, cap));
+      return FB_OK;
+    }
+  }
+  unsigned char *ab = nullptr;   // 12 entries per block, 2 (FP16) or 4 (FP32) bytes each
+  FB_TRY(fb_dev_alloc(c, &ab, (size_t)lc->nB * 12 * (mg->half ? 2 : 4) + 64));
+  L.AB = ab;
+  return FB_OK;
+}
 
 // lambda_max(Binv A) of one level by power iteration (host reads the norms: only at setup and every 32 solves)
 int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
@@ -755,6 +924,16 @@ template <int MODE, bool DOT>
 void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, const float *x, const float *b, float omega, float *out,
                     double *slots, const FbScalars *sc) {
   const fb_context *lc = L.ctx;
+  if (L.AE && mg->useEll) {
+    EllArgs g;
+    g.nV = L.nV; g.nSlots = L.nSlots; g.nz = L.n[2]; g.nynz = L.n[1] * L.n[2];
+    for (int q = 0; q < 16; q++) { g.slotOff[q] = L.slotOff[q]; g.slotSeg[q] = 4; g.slotDk[q] = 0; }
+    for (int o27 = 0; o27 < 27; o27++)
+      if (L.slotOf[o27] >= 0) { g.slotSeg[L.slotOf[o27]] = (signed char)(o27 / 3); g.slotDk[L.slotOf[o27]] = (signed char)(o27 % 3 - 1); }
+    fb_launch(pdl, c->stream, k_mg_spmv_ell<MODE, DOT>, L.grid_ell, ELL_T, g, (const __half *)L.AE, (const float *)L.scale, x, b,
+              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
+    return;
+  }
   if (mg->half)
     fb_launch(pdl, c->stream, k_mg_spmv<__half, MODE, DOT>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, (const __half *)L.AB, (const float *)L.scale, x, b,
               (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
@@ -855,7 +1034,7 @@ int apply_preconditioner(fb_context *c, FbMg *mg, float **z) {
   if (mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1) {
     *z = vcycle(c, mg, 0);
     mg->vcycles++;
-    return L.grid_spmv;
+    return (L.AE && mg->useEll) ? L.grid_ell : L.grid_spmv;
   }
   fb_launch(true, c->stream, k_mg_presmooth<true>, L.grid_vec, MG_TB, L.nV, L.Binv, L.b, 1.0f, L.xn, mg->slotsZ, (const FbScalars *)c->sc);
   c->launches++;
@@ -873,6 +1052,7 @@ void fb_mg_release(fb_context *c) {
   if (mg->dense) fb_dev_free(mg->dense);
   if (mg->denseInv) fb_dev_free(mg->denseInv);
   if (mg->slotsM) fb_dev_free(mg->slotsM);
+  if (mg->slotOfDev) fb_dev_free(mg->slotOfDev);
   if (mg->slotsZ) fb_dev_free(mg->slotsZ);
   delete mg;
   c->mg = nullptr;
@@ -884,10 +1064,12 @@ static int mg_ensure(fb_context *c) {
   memset(mg, 0, sizeof(*mg));
   c->mg = mg;
   mg->half = !(getenv("FEMBRAIN_B200_MG_PREC") && !strcmp(getenv("FEMBRAIN_B200_MG_PREC"), "fp32"));
+  mg->useEll = !(getenv("FEMBRAIN_B200_MG_ELL") && atoi(getenv("FEMBRAIN_B200_MG_ELL")) == 0);
   mg->useGraph = !(getenv("FEMBRAIN_B200_MG_GRAPH") && atoi(getenv("FEMBRAIN_B200_MG_GRAPH")) == 0);
   mg->nu = 1;
   if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = atoi(getenv("FEMBRAIN_B200_MG_NU"));
   FB_TRY(fb_dev_alloc(c, &mg->slotsM, 2 * (size_t)MG_SLOTS));
+  FB_TRY(fb_dev_alloc(c, &mg->slotOfDev, 27 * (size_t)MG_MAX_LEVELS));
   FB_TRY(fb_dev_alloc(c, &mg->slotsZ, (size_t)MG_SLOTS));
   return FB_OK;
 }
@@ -1004,6 +1186,7 @@ static int mg_build(fb_context *c) {
     for (int d = 0; d < 3; d++) ax[d].swap(cax[d]);
     li++;
   }
+  for (int k = 0; k < mg->nLevels; k++) FB_TRY(setup_level_matrix(c, mg, mg->L[k], k));
   MgLevel &Lc = mg->L[mg->nLevels - 1];
   if (mg->nLevels > 1) {
     if (Lc.r > MG_MAX_DENSE) { fb_set_error("multigrid: coarsest level has %d unknowns (> %d)", Lc.r, MG_MAX_DENSE); return FB_ERR_NOT_SUPPORTED; }
@@ -1038,7 +1221,9 @@ int fb_mg_prepare(fb_context *c) {
     if (mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1) {   // (the one-level variant applies Binv only)
       k_mg_scale_min<<<L.grid_vec, MG_TB, 0, st>>>((size_t)lc->r, lc->invD, reinterpret_cast<unsigned int *>(L.scale + 2));
       k_mg_scale_final<<<1, 1, 0, st>>>(L.scale, mg->half);
-      if (mg->half) k_mg_pack<__half><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (__half *)L.AB);
+      if (L.AE) k_mg_pack_ell<<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->nV, L.n[1], L.n[2], lc->bp, lc->brow, lc->bc, lc->Keff, L.scale,
+                                                                                mg->slotOfDev + 27 * li, L.AE);
+      else if (mg->half) k_mg_pack<__half><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (__half *)L.AB);
       else k_mg_pack<float><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (float *)L.AB);
     }
     k_mg_block_inverse<<<(L.nV + 127) / 128, 128, 0, st>>>(L.nV, lc->bp, lc->diag, lc->Keff, lc->rowmask, L.Binv);
@@ -1177,7 +1362,11 @@ int fb_set_grid(fb_context *c, int nx, int ny, int nz) {
   if (c->dist || c->batch) { fb_set_error("fb_set_grid: partitioned and batch contexts use the reference's solver"); return FB_ERR_NOT_SUPPORTED; }
   FB_TRY(mg_ensure(c));
   c->mg->grid[0] = nx; c->mg->grid[1] = ny; c->mg->grid[2] = nz;
-  if (c->mg->variant == FB_SOLVER_MG_PCG) return mg_build(c);
+  if (c->mg->variant == FB_SOLVER_MG_PCG) {
+    const int st = mg_build(c);
+    if (st != FB_OK) { fb_mg_invalidate(c); c->mg->variant = FB_SOLVER_JACOBI_PCG; c->prm.solver_variant = FB_SOLVER_JACOBI_PCG; }
+    return st;
+  }
   return FB_OK;
 }
 
@@ -1198,7 +1387,13 @@ int fb_set_solver(fb_context *c, int variant, int warm_start) {
   if (variant == c->mg->variant && (variant == FB_SOLVER_JACOBI_PCG || c->mg->nLevels > 0)) return FB_OK;
   c->mg->variant = variant;
   c->prm.solver_variant = variant;
-  return mg_build(c);
+  const int st = mg_build(c);
+  if (st != FB_OK) {   // e.g. out of memory while creating a level: fall back to the reference's solver, context stays usable
+    fb_mg_invalidate(c);
+    c->mg->variant = FB_SOLVER_JACOBI_PCG;
+    c->prm.solver_variant = FB_SOLVER_JACOBI_PCG;
+  }
+  return st;
 }
 
 int fb_get_solver(const fb_context *c, int *variant, int *warm_start, int *levels) {

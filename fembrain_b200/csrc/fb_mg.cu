@@ -97,6 +97,7 @@ struct FbMg {
   double *slotsM, *slotsZ;   // per-CTA partial sums: weighted residual, r.z
   int nu;                    // smoothing sweeps before and after the coarse correction
   int useEll;                // structured slot-major storage + k_mg_spmv_ell on tensor-grid levels (FP16 storage only)
+  int ellMinV;               // ... on levels with at least this many vertices (a row per thread needs that many rows to fill the GPU)
   signed char *slotOfDev;    // device copies of every level's slotOf table, 27 bytes per level
   int useGraph, capturing, subFailed, subKernels;   // levels >= 1 replayed as one CUDA graph
   void *subGraph;            // cudaGraphExec_t
@@ -357,22 +358,31 @@ struct EllArgs {
 
 constexpr int ELL_T = 128;   // rows (threads) per tile
 
+// one thread per VERTEX walking its row's blocks: the 24-byte writes of a warp are contiguous (same slot, consecutive vertices);
+// the reads are 24-byte pieces of 32 different rows, but a row's next block is in the sector / line the previous one brought in
 __global__ void __launch_bounds__(MG_TB) k_mg_pack_ell(int nB, int nV, int ny, int nz, const int *__restrict__ bp, const int *__restrict__ brow,
                                                        const int *__restrict__ bc, const double *__restrict__ A, const float *__restrict__ scale,
                                                        const signed char *__restrict__ slotOf27, __half *__restrict__ AE) {
-  const float s = scale[0];
-  for (size_t b = (size_t)blockIdx.x * MG_TB + threadIdx.x; b < (size_t)nB; b += (size_t)gridDim.x * MG_TB) {
-    const int v = brow[b], c = bc[b], rs = bp[v], nb = bp[v + 1] - rs, j = (int)b - rs;
+  (void)nB; (void)brow;
+  const double s = (double)scale[0];
+  for (int v = blockIdx.x * MG_TB + threadIdx.x; v < nV; v += gridDim.x * MG_TB) {
+    const int rs = bp[v], nb = bp[v + 1] - rs;
     const int vk = v % nz, vj = (v / nz) % ny, vi = v / (nz * ny);
-    const int ck = c % nz, cj = (c / nz) % ny, ci = c / (nz * ny);
-    const int slot = slotOf27[(ci - vi + 1) * 9 + (cj - vj + 1) * 3 + (ck - vk + 1)];
-    const double *a = A + 9 * (size_t)rs + 3 * j;
-    __half *o = AE + 12 * ((size_t)slot * nV + v);
+    for (int j = 0; j < nb; j++) {
+      const int c = bc[rs + j];
+      const int ck = c % nz, cj = (c / nz) % ny, ci = c / (nz * ny);
+      const int slot = slotOf27[(ci - vi + 1) * 9 + (cj - vj + 1) * 3 + (ck - vk + 1)];
+      const double *a = A + 9 * (size_t)rs + 3 * j;
+      uint2 *o = reinterpret_cast<uint2 *>(AE) + 3 * ((size_t)slot * nV + v);
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-#pragma unroll
-      for (int l = 0; l < 3; l++) o[4 * k + l] = __float2half_rn((float)(a[(size_t)k * 3 * nb + l] * (double)s));
-      o[4 * k + 3] = __float2half_rn(0.f);
+      for (int k = 0; k < 3; k++) {
+        const __half2 lo = __floats2half2_rn((float)(a[(size_t)k * 3 * nb] * s), (float)(a[(size_t)k * 3 * nb + 1] * s));
+        const __half2 hi = __floats2half2_rn((float)(a[(size_t)k * 3 * nb + 2] * s), 0.f);
+        uint2 w;
+        w.x = *reinterpret_cast<const unsigned int *>(&lo);
+        w.y = *reinterpret_cast<const unsigned int *>(&hi);
+        o[k] = w;
+      }
     }
   }
 }
@@ -820,6 +830,7 @@ int alloc_level_vectors(fb_context *c, MgLevel &L, bool half) {
     FB_CUDA(cudaStreamSynchronize(c->stream));
     (void)half;
   }
+  FB_TRY(fb_dev_alloc(c, &L.Binv, 9 * (size_t)lc->nV));
   float **vecs[] = {&L.b, &L.x, &L.xn, &L.res, &L.pv};
   for (float **v : vecs) {
     FB_TRY(fb_dev_alloc(c, v, (size_t)VS * lc->nV + 4));   // (x, y, z, 0) per vertex; the fourth entries stay zero for ever
@@ -849,7 +860,7 @@ int setup_level_matrix(fb_context *c, FbMg *mg, MgLevel &L, int li) {
   fb_context *lc = L.ctx;
   L.AE = nullptr; L.nSlots = 0;
   const bool grid = L.n[0] > 0 && (long long)L.n[0] * L.n[1] * L.n[2] == (long long)lc->nV;
-  if (mg->half && mg->useEll && grid && lc->nV > 0) {
+  if (mg->half && mg->useEll && grid && lc->nV > 0 && lc->nV >= mg->ellMinV) {
     std::vector<int> bp, bc;
     FB_TRY(fb_fetch_structure(lc, bp, bc));
     const int ny = L.n[1], nz = L.n[2];
@@ -1064,7 +1075,10 @@ static int mg_ensure(fb_context *c) {
   memset(mg, 0, sizeof(*mg));
   c->mg = mg;
   mg->half = !(getenv("FEMBRAIN_B200_MG_PREC") && !strcmp(getenv("FEMBRAIN_B200_MG_PREC"), "fp32"));
+  // FEMBRAIN_B200_MG_ELL: unset = levels of >= 400,000 vertices (measured: 5 % faster steps at 1.77M vertices, 10 % slower at
+  // 185k where one thread per row cannot fill 148 SMs); 1 = every tensor-grid level; 0 = none
   mg->useEll = !(getenv("FEMBRAIN_B200_MG_ELL") && atoi(getenv("FEMBRAIN_B200_MG_ELL")) == 0);
+  mg->ellMinV = getenv("FEMBRAIN_B200_MG_ELL") ? 0 : 400000;
   mg->useGraph = !(getenv("FEMBRAIN_B200_MG_GRAPH") && atoi(getenv("FEMBRAIN_B200_MG_GRAPH")) == 0);
   mg->nu = 1;
   if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = atoi(getenv("FEMBRAIN_B200_MG_NU"));
@@ -1221,13 +1235,17 @@ int fb_mg_prepare(fb_context *c) {
     if (mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1) {   // (the one-level variant applies Binv only)
       k_mg_scale_min<<<L.grid_vec, MG_TB, 0, st>>>((size_t)lc->r, lc->invD, reinterpret_cast<unsigned int *>(L.scale + 2));
       k_mg_scale_final<<<1, 1, 0, st>>>(L.scale, mg->half);
-      if (L.AE) k_mg_pack_ell<<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->nV, L.n[1], L.n[2], lc->bp, lc->brow, lc->bc, lc->Keff, L.scale,
+      if (L.AE) k_mg_pack_ell<<<grid_for_n(c, (size_t)lc->nV), MG_TB, 0, st>>>(lc->nB, lc->nV, L.n[1], L.n[2], lc->bp, lc->brow, lc->bc, lc->Keff, L.scale,
                                                                                 mg->slotOfDev + 27 * li, L.AE);
       else if (mg->half) k_mg_pack<__half><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (__half *)L.AB);
       else k_mg_pack<float><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (float *)L.AB);
     }
     k_mg_block_inverse<<<(L.nV + 127) / 128, 128, 0, st>>>(L.nV, lc->bp, lc->diag, lc->Keff, lc->rowmask, L.Binv);
     c->launches += 4;
+    if (getenv("FEMBRAIN_B200_MG_SYNC")) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      fprintf(stderr, "[mg sync] level %d (nV %d, nSlots %d, AE %p AB %p) after pack + block inverse: %s\n", li, L.nV, L.nSlots, (void *)L.AE, L.AB, cudaGetErrorString(e));
+    }
   }
   if (mg->nLevels > 1) {
     MgLevel &Lc = mg->L[mg->nLevels - 1];

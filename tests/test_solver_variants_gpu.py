@@ -25,9 +25,13 @@ def _sims(dims, variant, warm=False):
     return v, t, fixed, ref, var
 
 
-@pytest.mark.parametrize("dims,variant", [((12, 12, 12), "mg"), ((9, 5, 14), "mg"), ((16, 16, 16), "mg"), ((6, 6, 6), "mg"), ((3, 3, 3), "mg"),
-                                          ((12, 12, 12), "block_jacobi")])
-def test_variant_solves_the_reference_system_to_the_oracle_solution(port_oracle, dims, variant):
+# ell: FEMBRAIN_B200_MG_ELL read by fb_set_solver — "1" forces the structured slot-major product (k_mg_spmv_ell, by default only
+# on levels of >= 400,000 vertices) on every tensor-grid level, "0" the lane-per-block product everywhere
+@pytest.mark.parametrize("dims,variant,ell", [((12, 12, 12), "mg", "1"), ((9, 5, 14), "mg", "1"), ((16, 16, 16), "mg", "0"), ((6, 6, 6), "mg", "1"),
+                                              ((3, 3, 3), "mg", "1"), ((9, 5, 14), "mg", "0"), ((12, 12, 12), "block_jacobi", None)])
+def test_variant_solves_the_reference_system_to_the_oracle_solution(port_oracle, dims, variant, ell, monkeypatch):
+    if ell is not None:
+        monkeypatch.setenv("FEMBRAIN_B200_MG_ELL", ell)
     v, t, fixed, ref, var = _sims(dims, variant)
     ora = port_oracle.Oracle(v, t, fixed, kind="port")
     u = cases.perturbation(v, 0.5, 3)   # rotations != I, so the coarse levels are re-assembled at a real deformation

@@ -276,7 +276,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   CR(fb_dev_alloc(c, &c->fixed, (size_t)c->r));
   c->rowmask = c->fixed;
   CR(fb_apply_constraints(c, nC, cdofs));
-  CR(fb_dev_alloc(c, &c->T, (size_t)c->nnzK));
+  // T = hK + D is allocated on first use by the two-phase path only (fb_launch_assembly): the gather path never stores it
   CR(fb_dev_alloc(c, &c->Keff, (size_t)c->nnzK + 4));  // + slack: fb_tma.cu copies whole 16-byte lines around a row tile
   if (p.keep_raw_stiffness) CR(fb_dev_alloc(c, &c->Kraw, (size_t)c->nnzK));
   CR(fb_build_gather_plan(c));  // two-phase scratch (1248 B/tet) is allocated on first use, only if this plan is off
@@ -380,11 +380,9 @@ int fb_do_step(fb_context *c) {
   cudaStream_t st = c->stream;
   FB_CUDA(cudaEventRecord(c->ev[0], st));
   // forceModel->GetForceAndMatrix(q, internalForces, tangentStiffnessMatrix) + Keff formation
-  FB_TRY(fb_launch_assembly(c, c->q, c->prm.keep_raw_stiffness ? c->Kraw : nullptr, true));
+  // ... and qresidual = (h K + D) qvel, in the reference's summation order; rhs = -h (qres + fint - fext)
+  FB_TRY(fb_launch_assembly(c, c->q, c->prm.keep_raw_stiffness ? c->Kraw : nullptr, true, true));
   FB_CUDA(cudaEventRecord(c->ev[1], st));
-  // qresidual = (h K + D) qvel, in the reference's summation order; rhs = -h (qres + fint - fext)
-  FB_TRY(fb_launch_spmv_exact(c, c->T, c->qvel, c->tmp));
-  FB_TRY(fb_launch_rhs(c));
   FB_CUDA(cudaEventRecord(c->ev[2], st));
   if (fb_mg_active(c)) FB_TRY(fb_mg_prepare(c));   // variants: coarse operators / FP32 copies of this step's Keff (timed with the solve)
   FB_TRY(fb_pcg_solve(c, c->prm.cg_epsilon, c->prm.cg_max_iterations));

@@ -1,5 +1,6 @@
-// fb_assembly.cu — row-gather assembly: K, T = hK + D, Keff and f in ONE pass over the elements' data, element
-// matrices never written to HBM.  COMPILED WITH -fmad=false (bit-identical to the reference, like fb_fem.cu).
+// fb_assembly.cu — row-gather assembly: K, Keff, f AND the right-hand side -h ((hK + D) qvel + f - fext) in ONE pass over the
+// elements' data; element matrices and T = hK + D are never written to HBM.  COMPILED WITH -fmad=false (bit-identical to the
+// reference, like fb_fem.cu).
 //
 // Reference (src/3rdparty/vegafem): CorotationalLinearFEM::ComputeForceAndStiffnessMatrixOfSubmesh
 // (corotationalLinearFEM/corotationalLinearFEM.cpp:219-293 warp=1 branch, scatter :456-468) and the matrix
@@ -21,6 +22,11 @@
 //                      overwrite the incidence's record in shared memory; then one thread per (block, row of 3
 //                      scalars) of the CTA's rows adds its contribution list IN ASCENDING ELEMENT ORDER — the order
 //                      in which the reference's element loop calls AddEntry — and applies the DoTimestep epilogue.
+//                      T = hK + D exists only in registers: each (block, row) thread multiplies its three entries with the
+//                      column vertex's velocity (staged beside x0/u), the nine products of every block pass through the
+//                      now idle `vals`, and the thread that sums a DOF's element forces also adds the products of its row
+//                      in CSR order from 0 — SparseMatrix::MultiplyVector's order (sparseMatrix.cpp:736-749) — and writes
+//                      qresidual / rhs (PS_VolumeConservingIntegrator.cpp:119-123, :160).
 // No atomics, no float reassociation: K, f, T, Keff are bit-identical to the reference's (and to the two-phase
 // path).  Blocks of a CTA are visited in order of decreasing list length (precomputed), so the lanes of a warp run
 // the same number of trips: a diagonal block of the cube collects 24 contributions, an edge block 4-6.
@@ -69,12 +75,14 @@ struct GaLists {
 // Shared memory of one CTA:
 //   vals [CAP][36]  per incidence: IN the element record (24 doubles)  ->  OUT four 3x3 blocks, slot = 4 li + j at slot*9
 //   xb   [BCAP][6]  per block of the CTA's rows: x0 and u of the block's column vertex
+//   qv   [BCAP][3]  ... and its velocity (right-hand side only)
 //                   (between the two, the quad's 4 x 9 force terms pass through the same 36 doubles)
 //   fel  [CAP][3]   element force rows of the incidence
 template <class C>
 struct GatherSmem {
   double vals[C::CAP * 36];
   double xb[C::BCAP * 6];
+  double qv[C::BCAP * 3];
   double fel[C::CAP * 3];
   GaLists<C::CAP, C::BCAP> L;
 };
@@ -236,16 +244,20 @@ __global__ void k_pack_xu(int nV, const double *__restrict__ x0, const double *_
 
 struct GatherParams {
   double scale, h, dampK, dampM;
-  int effective;
+  int effective, wantRhs;
   const void *lists;
-  const double *erec, *xu;
+  const double *erec, *xu, *qvel, *fext;
   const unsigned char *fixed;
-  double *Kraw, *T, *Keff, *invD, *f;
+  double *Kraw, *Keff, *invD, *f, *qres, *rhs;
 };
 
 __device__ __forceinline__ void cp_async16(void *smemDst, const void *src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smemDst, const void *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -288,6 +300,12 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
     cp_async16(dst, rec);
     cp_async16(dst + 2, rec + 2);
     cp_async16(dst + 4, rec + 4);
+    if (p.wantRhs) {
+      const double *qsrc = p.qvel + 3 * (size_t)S.L.bcol[t];
+      cp_async8(S.qv + 3 * t, qsrc);
+      cp_async8(S.qv + 3 * t + 1, qsrc + 1);
+      cp_async8(S.qv + 3 * t + 2, qsrc + 2);
+    }
   }
   cp_async_wait_all();
   __syncthreads();
@@ -352,49 +370,85 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
 
   // ---- K: one thread per (block, row k) of the CTA's rows; SparseMatrix::ResetToZero, then AddEntry in element order
   const int nItems = 3 * nBlk;
-  for (int item = tid; item < nItems; item += TB) {
-    const int bi = item / 3, k = item - 3 * bi;
-    const int bl = S.L.bol[bi];
-    const int vl = S.L.bvl[bl];
-    const int s0 = S.L.segl[bl], s1 = S.L.segl[bl + 1];
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int s = s0; s < s1; s++) {
-      const double *c = S.vals + (int)S.L.csl[s] * 9 + 3 * k;
-      a0 += c[0]; a1 += c[1]; a2 += c[2];
-    }
-    const int rs = S.L.bpl[vl], nb = S.L.bpl[vl + 1] - rs;
-    const size_t idx = 9 * (size_t)(blk0 + rs) + (size_t)(3 * nb) * k + 3 * (size_t)(bl - rs);
-    const double m = S.L.mb[bl];
-    const bool isDiag = (bl == S.L.dgl[vl]);
+  constexpr int NIT = (3 * C::BCAP + TB - 1) / TB;
+  double pr[NIT][3];  // T[k][l] * qvel[col][l] of this thread's items
 #pragma unroll
-    for (int l = 0; l < 3; l++) {
-      const double acc = (l == 0) ? a0 : ((l == 1) ? a1 : a2);
-      const double Kv = acc * p.scale;  // *tangentStiffnessMatrix *= internalForceScalingFactor  (:87)
-      if (p.Kraw) p.Kraw[idx + l] = Kv;
-      if (p.effective) {
-        double D = Kv * p.dampK;                 // ScalarMultiply(dampingStiffnessCoef, rayleigh)   (:100)
-        if (k == l) D += p.dampM * m;            // rayleigh->AddSubMatrix(dampingMassCoef, M)        (:102)
-        double Tv = Kv * p.h;                    // K *= h                                            (:110)
-        Tv += D;                                 // K += D                                            (:112)
-        p.T[idx + l] = Tv;                       // (K += 1.0 * empty dampingMatrix: no entries)      (:113)
-        double Ke = Tv * p.h;                    // K *= h                                            (:115)
-        if (k == l) Ke += 1.0 * m;               // K->AddSubMatrix(1.0, M)                           (:116)
-        p.Keff[idx + l] = Ke;
-        if (k == l && isDiag) {
-          const int dof = 3 * (v0 + vl) + k;
-          p.invD[dof] = p.fixed[dof] ? 0.0 : 1.0 / Ke;  // CGSolver.cpp:134-136 on the constrained system
+  for (int it = 0; it < NIT; it++) {
+    pr[it][0] = pr[it][1] = pr[it][2] = 0.0;
+    const int item = it * TB + tid;
+    if (item < nItems) {
+      const int bi = item / 3, k = item - 3 * bi;
+      const int bl = S.L.bol[bi];
+      const int vl = S.L.bvl[bl];
+      const int s0 = S.L.segl[bl], s1 = S.L.segl[bl + 1];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int s = s0; s < s1; s++) {
+        const double *c = S.vals + (int)S.L.csl[s] * 9 + 3 * k;
+        a0 += c[0]; a1 += c[1]; a2 += c[2];
+      }
+      const int rs = S.L.bpl[vl], nb = S.L.bpl[vl + 1] - rs;
+      const size_t idx = 9 * (size_t)(blk0 + rs) + (size_t)(3 * nb) * k + 3 * (size_t)(bl - rs);
+      const double m = S.L.mb[bl];
+      const bool isDiag = (bl == S.L.dgl[vl]);
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        const double acc = (l == 0) ? a0 : ((l == 1) ? a1 : a2);
+        const double Kv = acc * p.scale;  // *tangentStiffnessMatrix *= internalForceScalingFactor  (:87)
+        if (p.Kraw) p.Kraw[idx + l] = Kv;
+        if (p.effective) {
+          double D = Kv * p.dampK;                 // ScalarMultiply(dampingStiffnessCoef, rayleigh)   (:100)
+          if (k == l) D += p.dampM * m;            // rayleigh->AddSubMatrix(dampingMassCoef, M)        (:102)
+          double Tv = Kv * p.h;                    // K *= h                                            (:110)
+          Tv += D;                                 // K += D                                            (:112)
+                                                   // (K += 1.0 * empty dampingMatrix: no entries)      (:113)
+          if (p.wantRhs) pr[it][l] = S.qv[3 * bl + l] * Tv;   // K->MultiplyVector(qvel, qresidual), one term     (:119)
+          double Ke = Tv * p.h;                    // K *= h                                            (:115)
+          if (k == l) Ke += 1.0 * m;               // K->AddSubMatrix(1.0, M)                           (:116)
+          p.Keff[idx + l] = Ke;
+          if (k == l && isDiag) {
+            const int dof = 3 * (v0 + vl) + k;
+            p.invD[dof] = p.fixed[dof] ? 0.0 : 1.0 / Ke;  // CGSolver.cpp:134-136 on the constrained system
+          }
         }
       }
     }
   }
-  // ---- f: one thread per DOF of the CTA's rows, incident elements in ascending order (:288-293)
+  if (p.wantRhs) {
+    __syncthreads();  // every contribution has been read: vals now carries the products, nine per block in CSR position
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int item = it * TB + tid;
+      if (item < nItems) {
+        const int bi = item / 3, k = item - 3 * bi;
+        double *o = S.vals + 9 * (int)S.L.bol[bi] + 3 * k;
+        o[0] = pr[it][0]; o[1] = pr[it][1]; o[2] = pr[it][2];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- f: one thread per DOF of the CTA's rows, incident elements in ascending order (:288-293); then the row's products in
+  //      column order from 0, + (f - fext), * -h                                   (PS_VolumeConservingIntegrator.cpp:119-123)
   const int nF = 3 * nVl;
   for (int item = tid; item < nF; item += TB) {
     const int vl = item / 3, k = item - 3 * vl;
     const int a = S.L.ipl[vl], z = S.L.ipl[vl + 1];
     double acc = 0.0;
     for (int t = a; t < z; t++) acc += S.fel[t * 3 + k];
-    p.f[3 * (size_t)(v0 + vl) + k] = acc * p.scale;
+    const double fint = acc * p.scale;
+    const size_t dof = 3 * (size_t)(v0 + vl) + k;
+    p.f[dof] = fint;
+    if (p.wantRhs) {
+      double tq = 0.0;
+      for (int bl = S.L.bpl[vl]; bl < (int)S.L.bpl[vl + 1]; bl++) {
+        const double *t3 = S.vals + 9 * bl + 3 * k;
+        tq += t3[0]; tq += t3[1]; tq += t3[2];
+      }
+      double v = tq;
+      v += fint - p.fext[dof];
+      v *= -p.h;
+      p.qres[dof] = v;
+      p.rhs[dof] = p.fixed[dof] ? 0.0 : v;
+    }
   }
 }
 
@@ -561,16 +615,18 @@ int fb_build_gather_plan(fb_context *c) {
   return FB_OK;
 }
 
-int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool effective) {
+int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool effective, bool rhs) {
   k_rotation<<<grid_for((size_t)c->nT, 128), 128, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance, c->ga_erec);
   k_pack_xu<<<grid_for((size_t)c->r, 256), 256, 0, c->stream>>>(c->nV, c->x0, u, c->ga_xu);
   GatherParams p;
   p.scale = c->prm.internal_force_scaling; p.h = c->prm.timestep;
   p.dampK = c->prm.damping_stiffness; p.dampM = c->prm.damping_mass;
   p.effective = effective ? 1 : 0;
+  p.wantRhs = (effective && rhs) ? 1 : 0;
   p.lists = c->ga_lists;
   p.erec = c->ga_erec; p.xu = c->ga_xu; p.fixed = c->rowmask;
-  p.Kraw = Kraw; p.T = c->T; p.Keff = c->Keff; p.invD = c->invD; p.f = c->fint;
+  p.qvel = c->qvel; p.fext = c->fext; p.qres = c->qres; p.rhs = c->rhs;
+  p.Kraw = Kraw; p.Keff = c->Keff; p.invD = c->invD; p.f = c->fint;
   if (c->ga_cfg == 2) launch_gather<CfgBig>(c, p);
   else if (c->ga_cfg == 1) launch_gather<CfgMid>(c, p);
   else launch_gather<CfgSmall>(c, p);

@@ -303,9 +303,18 @@ int fb_launch_mass(fb_context *c) {
   return FB_OK;
 }
 
-int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effective) {
-  if (c->nT == 0) return FB_OK;
-  if (c->ga_ctas > 0) return fb_launch_assembly_gather(c, u, Kraw, effective);
+// rhs: also qresidual = (hK + D) qvel and the right-hand side of the velocity solve.  The gather path does it inside its one
+// kernel (T = hK + D is never stored); the two-phase path stores T and runs the exact-order product + k_rhs.
+int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effective, bool rhs) {
+  if (c->nT == 0) {
+    if (effective && rhs && c->r > 0) {   // no elements: T = 0
+      FB_CUDA(cudaMemsetAsync(c->tmp, 0, sizeof(double) * (size_t)c->r, c->stream));
+      return fb_launch_rhs(c);
+    }
+    return FB_OK;
+  }
+  if (c->ga_ctas > 0) return fb_launch_assembly_gather(c, u, Kraw, effective, rhs);
+  if (effective && !c->T) FB_TRY(fb_dev_alloc(c, &c->T, (size_t)c->nnzK));
   if (!c->scrK) FB_TRY(fb_dev_alloc(c, &c->scrK, 144 * (size_t)c->nT));
   if (!c->scrF) FB_TRY(fb_dev_alloc(c, &c->scrF, 12 * (size_t)c->nT));
   k_element<<<grid_for(c->nT, EL_TB), EL_TB, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance,
@@ -321,6 +330,10 @@ int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effect
                                                                  c->src, c->scrF, c->fint);
   c->launches += 3;
   FB_CUDA(cudaGetLastError());
+  if (effective && rhs) {
+    FB_TRY(fb_launch_spmv_exact(c, c->T, c->qvel, c->tmp));
+    FB_TRY(fb_launch_rhs(c));
+  }
   return FB_OK;
 }
 

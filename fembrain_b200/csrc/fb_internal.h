@@ -184,14 +184,14 @@ int fb_build_topology(fb_context *c);
 // ---- fb_fem.cu (compiled with -fmad=false) ---------------------------------------------------------
 int fb_launch_element_data(fb_context *c, const double *E, const double *nu, const double *rho);
 int fb_launch_mass(fb_context *c);
-int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effective);
+int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effective, bool rhs = false);
 int fb_launch_rhs(fb_context *c);
 int fb_launch_spmv_exact(fb_context *c, const double *A, const double *x, double *y);
 int fb_launch_state_update(fb_context *c);
 int fb_launch_expand_element(fb_context *c, double *minv16_dev, double *k0_dev, int el0, int n);
 // ---- fb_assembly.cu (compiled with -fmad=false) -----------------------------------------------------
 int fb_build_gather_plan(fb_context *c);  // after fb_build_topology
-int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool effective);
+int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool effective, bool rhs);
 // ---- fb_pcg.cu -------------------------------------------------------------------------------------
 int fb_pcg_solve(fb_context *c, double eps, int max_it);  // solves Keff x = rhs (masked), x0 = 0
 int fb_launch_spmv(fb_context *c, const double *A, const double *x, double *y, bool masked);

@@ -28,6 +28,7 @@
 //
 // Everything is deterministic: sums are per-CTA slots added in index order, no floating-point atomics.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -79,7 +80,7 @@ struct MgLevel {
   // structured storage of the level's matrix (tensor-grid levels: every row's blocks sit at a subset of ONE set of <= 16 grid
   // offsets): AE[slot][vertex][3][4] __half, empty slots zero; see k_mg_spmv_ell
   __half *AE;
-  int nSlots, grid_ell;
+  int nSlots, grid_ell, grid_pack;
   int slotOff[16];           // vertex-index offset of every slot
   signed char slotOf[27];    // (di+1)*9 + (dj+1)*3 + (dk+1) -> slot, -1 = not in the stencil
 };
@@ -91,11 +92,13 @@ struct FbMg {
   int grid[3];               // tensor-grid dimensions given with fb_set_grid (0 = none)
   int nLevels;
   MgLevel L[MG_MAX_LEVELS];
-  double *dense;             // [n*n] coarsest-level matrix, inverted in place every step
+  double *dense;             // (unused: the coarsest-level matrix is inverted in shared memory)
   float *denseInv;           // [n*n] fp32 copy of the inverse
   int nDense;
   double *slotsM, *slotsZ;   // per-CTA partial sums: weighted residual, r.z
   int nu;                    // smoothing sweeps before and after the coarse correction
+  int cheb;                  // nu >= 2: the sweeps are a Chebyshev iteration on [hi lambda_max / alpha, hi lambda_max] instead of nu damped steps
+  float chebAlpha, chebHi;
   int useEll;                // structured slot-major storage + k_mg_spmv_ell on tensor-grid levels (FP16 storage only)
   int ellMinV;               // ... on levels with at least this many vertices (a row per thread needs that many rows to fill the GPU)
   signed char *slotOfDev;    // device copies of every level's slotOf table, 27 bytes per level
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(MG_TB, 4) k_mg_spmv(int nV, const int *__restr
                                                      const T *__restrict__ AB, const float *__restrict__ scale,
                                                      const float *__restrict__ x, const float *__restrict__ b,
                                                      const float *__restrict__ Binv, const unsigned char *__restrict__ mask, float omega,
-                                                     float *__restrict__ out, double *slots, const FbScalars *sc) {
+                                                     float gamma, int usePrev, float *__restrict__ out, double *slots, const FbScalars *sc) {
   typedef typename MgRaw<T>::type Raw;
   pdl_wait();
   pdl_trigger();
@@ -330,7 +333,8 @@ __global__ void __launch_bounds__(MG_TB, 4) k_mg_spmv(int nV, const int *__restr
       } else {
         const float r0 = (MODE == 1) ? bv.x - a0v : a0v, r1 = (MODE == 1) ? bv.y - a1v : a1v, r2 = (MODE == 1) ? bv.z - a2v : a2v;
         const float corr = fmaf(bi0, r0, fmaf(bi1, r1, bi2 * r2));   // zero rows / columns at constrained DOFs
-        const float val = (MODE == 1) ? fmaf(omega, corr, xr) : corr;
+        float val = (MODE == 1) ? fmaf(omega, corr, xr) : corr;
+        if (MODE == 1 && gamma != 0.f) val = fmaf(gamma, xr - (usePrev ? out[row] : 0.f), val);   // Chebyshev momentum: out holds x_(k-1)
         out[row] = val;
         if (DOT) {
           const float bk = kk == 0 ? bv.x : (kk == 1 ? bv.y : bv.z);
@@ -349,6 +353,9 @@ __global__ void __launch_bounds__(MG_TB, 4) k_mg_spmv(int nV, const int *__restr
 // thread and slot), x staged through shared memory as nine runs of consecutive vertices (one per (di, dj)), no shuffles.
 // That removes the scattered float4 gathers whose L1 wavefronts bounded k_mg_spmv (77 % of the LSU data pipe at 4.5 TB/s,
 // profiles/r02_mg_spmv16_ncu_details.txt).
+// Tried and dropped: HALF storage (diagonal + blocks towards higher vertices; the block towards v - off read as the transpose
+// of AE[slot][v - off], a coalesced second read meant to come out of L2): correct, but 187 us per product instead of 142 at
+// 1.77M vertices — the same 15 x 24 B per row still cross L2 -> SM, plus the transposed FMAs, at lower occupancy.
 struct EllArgs {
   int nV, nSlots, nz, nynz;
   int slotOff[16];        // di * ny*nz + dj * nz + dk
@@ -358,32 +365,54 @@ struct EllArgs {
 
 constexpr int ELL_T = 128;   // rows (threads) per tile
 
-// one thread per VERTEX walking its row's blocks: the 24-byte writes of a warp are contiguous (same slot, consecutive vertices);
-// the reads are 24-byte pieces of 32 different rows, but a row's next block is in the sector / line the previous one brought in
-__global__ void __launch_bounds__(MG_TB) k_mg_pack_ell(int nB, int nV, int ny, int nz, const int *__restrict__ bp, const int *__restrict__ brow,
-                                                       const int *__restrict__ bc, const double *__restrict__ A, const float *__restrict__ scale,
-                                                       const signed char *__restrict__ slotOf27, __half *__restrict__ AE) {
-  (void)nB; (void)brow;
+// FP64 block rows -> slot-major FP16.  A tile of 32 consecutive vertices' rows is one contiguous range of Keff: read coalesced
+// into shared memory, then one lane per (block position j, vertex) so that a warp writes 32 consecutive 24-byte entries of one
+// slot.  (One thread per block: 24-byte writes nV entries apart; one thread per vertex: 24-byte reads a row apart — 1.25 ms at
+// 1.77M vertices for 2.5 GB of traffic, profiles/r02_mg_prepare_phases.txt.)
+constexpr int PK_V = 32, PK_T = 128;
+constexpr size_t PK_SMEM = sizeof(double) * PK_V * 16 * 9 + sizeof(int) * (PK_V * 16 + PK_V + 1);
+__global__ void __launch_bounds__(PK_T) k_mg_pack_ell(int nV, int ny, int nz, const int *__restrict__ bp, const int *__restrict__ bc,
+                                                      const double *__restrict__ A, const float *__restrict__ scale,
+                                                      const signed char *__restrict__ slotOf27, __half *__restrict__ AE) {
+  extern __shared__ double pk_sm[];
+  double *sa = pk_sm;
+  int *scol = reinterpret_cast<int *>(pk_sm + PK_V * 16 * 9);
+  int *sbp = scol + PK_V * 16;
   const double s = (double)scale[0];
-  for (int v = blockIdx.x * MG_TB + threadIdx.x; v < nV; v += gridDim.x * MG_TB) {
-    const int rs = bp[v], nb = bp[v + 1] - rs;
-    const int vk = v % nz, vj = (v / nz) % ny, vi = v / (nz * ny);
-    for (int j = 0; j < nb; j++) {
-      const int c = bc[rs + j];
+  const int nTiles = (nV + PK_V - 1) / PK_V;
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int v0 = tile * PK_V, nVt = min(PK_V, nV - v0);
+    if (threadIdx.x <= nVt) sbp[threadIdx.x] = bp[v0 + threadIdx.x];
+    __syncthreads();
+    const int b0 = sbp[0], nBt = sbp[nVt] - b0;
+    if (nBt <= PK_V * 16) {
+      const double *src = A + 9 * (size_t)b0;
+      for (int i = threadIdx.x; i < 9 * nBt; i += PK_T) sa[i] = __ldcs(src + i);
+      for (int i = threadIdx.x; i < nBt; i += PK_T) scol[i] = bc[b0 + i];
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < 16 * PK_V; item += PK_T) {
+      const int j = item / PK_V, vl = item - j * PK_V;
+      if (vl >= nVt || nBt > PK_V * 16) continue;
+      const int rs = sbp[vl] - b0, nb = sbp[vl + 1] - sbp[vl];
+      if (j >= nb) continue;
+      const int v = v0 + vl, c = scol[rs + j];
+      const int vk = v % nz, vj = (v / nz) % ny, vi = v / (nz * ny);
       const int ck = c % nz, cj = (c / nz) % ny, ci = c / (nz * ny);
       const int slot = slotOf27[(ci - vi + 1) * 9 + (cj - vj + 1) * 3 + (ck - vk + 1)];
-      const double *a = A + 9 * (size_t)rs + 3 * j;
+      const double *a = sa + 9 * rs + 3 * j;
       uint2 *o = reinterpret_cast<uint2 *>(AE) + 3 * ((size_t)slot * nV + v);
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const __half2 lo = __floats2half2_rn((float)(a[(size_t)k * 3 * nb] * s), (float)(a[(size_t)k * 3 * nb + 1] * s));
-        const __half2 hi = __floats2half2_rn((float)(a[(size_t)k * 3 * nb + 2] * s), 0.f);
+        const __half2 lo = __floats2half2_rn((float)(a[k * 3 * nb] * s), (float)(a[k * 3 * nb + 1] * s));
+        const __half2 hi = __floats2half2_rn((float)(a[k * 3 * nb + 2] * s), 0.f);
         uint2 w;
         w.x = *reinterpret_cast<const unsigned int *>(&lo);
         w.y = *reinterpret_cast<const unsigned int *>(&hi);
         o[k] = w;
       }
     }
+    __syncthreads();
   }
 }
 
@@ -392,7 +421,7 @@ template <int MODE, bool DOT>
 __global__ void __launch_bounds__(ELL_T, 8) k_mg_spmv_ell(EllArgs g, const __half *__restrict__ AE, const float *__restrict__ scale,
                                                          const float *__restrict__ x, const float *__restrict__ b,
                                                          const float *__restrict__ Binv, const unsigned char *__restrict__ mask, float omega,
-                                                         float *__restrict__ out, double *slots, const FbScalars *sc) {
+                                                         float gamma, int usePrev, float *__restrict__ out, double *slots, const FbScalars *sc) {
   pdl_wait();
   pdl_trigger();
   if (sc && sc->done) return;
@@ -459,6 +488,11 @@ __global__ void __launch_bounds__(ELL_T, 8) k_mg_spmv_ell(EllArgs g, const __hal
         if (MODE == 1) {
           const float4 xc = xs[4][threadIdx.x + 1];   // the row's own vertex: run (di, dj) = (0, 0), dk = 0
           o.x = fmaf(omega, o.x, xc.x); o.y = fmaf(omega, o.y, xc.y); o.z = fmaf(omega, o.z, xc.z);
+          if (gamma != 0.f) {   // Chebyshev momentum: out holds x_(k-1)
+            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (usePrev) pv = reinterpret_cast<const float4 *>(out)[v];
+            o.x = fmaf(gamma, xc.x - pv.x, o.x); o.y = fmaf(gamma, xc.y - pv.y, o.y); o.z = fmaf(gamma, xc.z - pv.z, o.z);
+          }
           if (DOT) part = fma((double)bv.x, (double)o.x, fma((double)bv.y, (double)o.y, fma((double)bv.z, (double)o.z, part)));
         }
       }
@@ -576,36 +610,40 @@ __global__ void k_mg_inject(int nVc, const int *__restrict__ twin, const double 
 }
 
 // ---- coarsest level: dense matrix, explicit inverse by Gauss-Jordan (SPD: no pivoting), one CTA ------------------------
-__global__ void k_mg_dense_build(int nV, const int *__restrict__ bp, const int *__restrict__ bc, const double *__restrict__ A,
-                                 const unsigned char *__restrict__ mask, double *__restrict__ D) {
-  const int n = 3 * nV;
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) D[i] = 0.0;
-  __syncthreads();
-  for (int row = threadIdx.x; row < n; row += blockDim.x) {
-    const int v = row / 3, k = row - 3 * v;
-    if (mask[row]) { D[(size_t)row * n + row] = 1.0; continue; }
-    const int rs = bp[v], nb = bp[v + 1] - rs;
-    for (int j = 0; j < nb; j++)
-      for (int l = 0; l < 3; l++) {
-        const int col = 3 * bc[rs + j] + l;
-        if (!mask[col]) D[(size_t)row * n + col] = A[9 * (size_t)rs + (size_t)k * 3 * nb + 3 * j + l];
-      }
-  }
-}
-__global__ void __launch_bounds__(256) k_mg_dense_invert(int n, double *__restrict__ D, const unsigned char *__restrict__ mask,
-                                                         float *__restrict__ inv) {
-  // Gauss-Jordan in place in global memory (n <= 96: the matrix lives in L1/L2); column p eliminated per trip
+// coarsest level: the constrained matrix as a dense array in SHARED memory (n <= 96: 72 KB of doubles), Gauss-Jordan in place —
+// column p eliminated per trip — and the inverse written out in FP32.  One CTA of 1024 threads; in global memory with 256
+// threads the same elimination took 320 us per step (profiles/r02_mg_prepare_phases.txt).
+constexpr int MG_DENSE_T = 1024;
+__global__ void __launch_bounds__(MG_DENSE_T) k_mg_dense_inverse(int nV, const int *__restrict__ bp, const int *__restrict__ bc,
+                                                                 const double *__restrict__ A, const unsigned char *__restrict__ mask,
+                                                                 float *__restrict__ inv) {
+  extern __shared__ double D[];
   __shared__ double prow[MG_MAX_DENSE], pcol[MG_MAX_DENSE];
   __shared__ double pivInv;
+  const int n = 3 * nV;
+  for (int i = threadIdx.x; i < n * n; i += MG_DENSE_T) D[i] = 0.0;
+  __syncthreads();
+  for (int item = threadIdx.x; item < n * 16; item += MG_DENSE_T) {   // (row, block of the row)
+    const int row = item >> 4, j = item & 15;
+    const int v = row / 3, k = row - 3 * v;
+    if (mask[row]) { if (j == 0) D[row * n + row] = 1.0; continue; }
+    const int rs = bp[v], nb = bp[v + 1] - rs;
+    for (int jj = j; jj < nb; jj += 16)
+      for (int l = 0; l < 3; l++) {
+        const int col = 3 * bc[rs + jj] + l;
+        if (!mask[col]) D[row * n + col] = A[9 * (size_t)rs + (size_t)k * 3 * nb + 3 * jj + l];
+      }
+  }
+  __syncthreads();
   for (int p = 0; p < n; p++) {
-    if (threadIdx.x == 0) pivInv = 1.0 / D[(size_t)p * n + p];
+    if (threadIdx.x == 0) pivInv = 1.0 / D[p * n + p];
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      prow[j] = D[(size_t)p * n + j] * pivInv;
-      pcol[j] = D[(size_t)j * n + p];
+    for (int j = threadIdx.x; j < n; j += MG_DENSE_T) {
+      prow[j] = D[p * n + j] * pivInv;
+      pcol[j] = D[j * n + p];
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+    for (int t = threadIdx.x; t < n * n; t += MG_DENSE_T) {
       const int i = t / n, j = t - i * n;
       double val;
       if (i == p) val = (j == p) ? pivInv : prow[j];
@@ -615,7 +653,7 @@ __global__ void __launch_bounds__(256) k_mg_dense_invert(int n, double *__restri
     }
     __syncthreads();
   }
-  for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+  for (int t = threadIdx.x; t < n * n; t += MG_DENSE_T) {
     const int i = t / n, j = t - i * n;
     inv[t] = (mask[i] || mask[j]) ? 0.f : (float)D[t];
   }
@@ -850,7 +888,7 @@ int alloc_level_vectors(fb_context *c, MgLevel &L, bool half) {
 // the cycle's product on one level, storage type chosen at run time
 template <int MODE, bool DOT>
 void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, const float *x, const float *b, float omega, float *out,
-                    double *slots, const FbScalars *sc);
+                    double *slots, const FbScalars *sc, float gamma = 0.f, int usePrev = 0);
 
 void drop_subcycle_graph(FbMg *mg);
 
@@ -891,6 +929,8 @@ int setup_level_matrix(fb_context *c, FbMg *mg, MgLevel &L, int li) {
       if (cap > MG_SLOTS) cap = MG_SLOTS;
       const size_t tiles = ((size_t)lc->nV + ELL_T - 1) / ELL_T;
       L.grid_ell = (int)std::max<size_t>(1, std::min(tiles, cap));
+      FB_CUDA(cudaFuncSetAttribute(k_mg_pack_ell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
+      L.grid_pack = (int)std::max<size_t>(1, std::min(((size_t)lc->nV + PK_V - 1) / PK_V, (size_t)c->sm_count * 5));
       return FB_OK;
     }
   }
@@ -923,6 +963,7 @@ int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
     c->launches += 3;
     if (!(nx > 0.0) || !(ny > 0.0) || !std::isfinite(ny)) break;
     lam = std::sqrt(ny / nx);
+    if (getenv("FEMBRAIN_B200_MG_TRACE")) fprintf(stderr, "[mg lmax] nV %d it %d lambda %.6f\n", L.nV, k, lam);
     k_mg_scale_copy<<<L.grid_vec, MG_TB, 0, st>>>((size_t)VS * L.nV, (float)(1.0 / std::sqrt(ny)), L.res, L.pv);
     c->launches++;
   }
@@ -933,7 +974,7 @@ int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
 
 template <int MODE, bool DOT>
 void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, const float *x, const float *b, float omega, float *out,
-                    double *slots, const FbScalars *sc) {
+                    double *slots, const FbScalars *sc, float gamma, int usePrev) {
   const fb_context *lc = L.ctx;
   if (L.AE && mg->useEll) {
     EllArgs g;
@@ -942,15 +983,33 @@ void launch_mg_spmv(fb_context *c, const FbMg *mg, const MgLevel &L, bool pdl, c
     for (int o27 = 0; o27 < 27; o27++)
       if (L.slotOf[o27] >= 0) { g.slotSeg[L.slotOf[o27]] = (signed char)(o27 / 3); g.slotDk[L.slotOf[o27]] = (signed char)(o27 % 3 - 1); }
     fb_launch(pdl, c->stream, k_mg_spmv_ell<MODE, DOT>, L.grid_ell, ELL_T, g, (const __half *)L.AE, (const float *)L.scale, x, b,
-              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
+              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, gamma, usePrev, out, slots, sc);
     return;
   }
   if (mg->half)
     fb_launch(pdl, c->stream, k_mg_spmv<__half, MODE, DOT>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, (const __half *)L.AB, (const float *)L.scale, x, b,
-              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
+              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, gamma, usePrev, out, slots, sc);
   else
     fb_launch(pdl, c->stream, k_mg_spmv<float, MODE, DOT>, L.grid_spmv, MG_TB, L.nV, lc->bp, lc->bc, (const float *)L.AB, (const float *)L.scale, x, b,
-              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, out, slots, sc);
+              (const float *)L.Binv, (const unsigned char *)lc->rowmask, omega, gamma, usePrev, out, slots, sc);
+}
+
+// Damped block Jacobi: w = 1.4 / lambda_max every sweep.  Chebyshev (nu >= 2): the three-term recurrence for the interval
+// [a, b] = [hi lambda_max / alpha, hi lambda_max] of Binv A (Saad, Iterative Methods, alg. 12.1): theta = (a + b) / 2,
+// delta = (b - a) / 2, rho_0 = delta / theta, rho_k = 1 / (2 theta / delta - rho_(k-1)); w_0 = 1 / theta, w_k = 2 rho_k / delta,
+// gm_k = rho_k rho_(k-1).  Both are polynomials in Binv A times Binv: symmetric, the same before and after the correction.
+void smoother_coefficients(const FbMg *mg, float lmax, float *w, float *gm) {
+  for (int k = 0; k < 8; k++) { w[k] = 1.4f / lmax; gm[k] = 0.f; }
+  if (!mg->cheb || mg->nu < 2) return;
+  const double b = (double)mg->chebHi * lmax, a = b / mg->chebAlpha, theta = 0.5 * (a + b), delta = 0.5 * (b - a);
+  double rho = delta / theta;
+  w[0] = (float)(1.0 / theta);
+  for (int k = 1; k < 8; k++) {
+    const double rn = 1.0 / (2.0 * theta / delta - rho);
+    w[k] = (float)(2.0 * rn / delta);
+    gm[k] = (float)(rn * rho);
+    rho = rn;
+  }
 }
 
 float *vcycle(fb_context *c, FbMg *mg, int li);
@@ -1000,9 +1059,12 @@ float *vcycle(fb_context *c, FbMg *mg, int li) {
     return L.xn;
   }
   MgLevel &C = mg->L[li + 1];
-  const float omega = 1.4f / L.lmax;
   const GridMaps g = maps_of(L);
   const int nu = mg->nu;
+  // step k of the smoother: x_(k+1) = x_k + w[k] Binv (b - A x_k) + gm[k] (x_k - x_(k-1))
+  float w[8], gm[8];
+  smoother_coefficients(mg, L.lmax, w, gm);
+  const float omega = w[0];
   const bool pdl = !mg->capturing;   // inside a captured sub-cycle the graph's own edges order the kernels
   // pre-smoothing from the zero guess: the first sweep needs no product (on the finest level the CG update kernel has
   // already written it together with r32, except before the first iteration)
@@ -1012,7 +1074,7 @@ float *vcycle(fb_context *c, FbMg *mg, int li) {
   }
   float *cur = L.x, *alt = L.xn;
   for (int s = 1; s < nu; s++) {
-    launch_mg_spmv<1, false>(c, mg, L, pdl, cur, L.b, omega, alt, nullptr, sc);
+    launch_mg_spmv<1, false>(c, mg, L, pdl, cur, L.b, w[s], alt, nullptr, sc, gm[s], s > 1);   // x_0 = 0
     c->launches++;
     std::swap(cur, alt);
   }
@@ -1030,8 +1092,8 @@ float *vcycle(fb_context *c, FbMg *mg, int li) {
   if (li == 0) tm_mark(st, "prolong (level 1 -> 0)");
   for (int s = 0; s < nu; s++) {   // the same sweeps after the correction: the cycle stays symmetric
     const bool last = s == nu - 1;
-    if (li == 0 && last) launch_mg_spmv<1, true>(c, mg, L, pdl, cur, L.b, omega, alt, mg->slotsZ, sc);
-    else launch_mg_spmv<1, false>(c, mg, L, pdl, cur, L.b, omega, alt, nullptr, sc);
+    if (li == 0 && last) launch_mg_spmv<1, true>(c, mg, L, pdl, cur, L.b, w[s], alt, mg->slotsZ, sc, gm[s], 1);
+    else launch_mg_spmv<1, false>(c, mg, L, pdl, cur, L.b, w[s], alt, nullptr, sc, gm[s], 1);
     c->launches++;
     std::swap(cur, alt);
   }
@@ -1080,8 +1142,12 @@ static int mg_ensure(fb_context *c) {
   mg->useEll = !(getenv("FEMBRAIN_B200_MG_ELL") && atoi(getenv("FEMBRAIN_B200_MG_ELL")) == 0);
   mg->ellMinV = getenv("FEMBRAIN_B200_MG_ELL") ? 0 : 400000;
   mg->useGraph = !(getenv("FEMBRAIN_B200_MG_GRAPH") && atoi(getenv("FEMBRAIN_B200_MG_GRAPH")) == 0);
-  mg->nu = 1;
-  if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = atoi(getenv("FEMBRAIN_B200_MG_NU"));
+  mg->nu = 3;   // measured at 10M / 1M tets (profiles/r02_mg_smoother_sweep.txt): 13-17 iterations, the fastest step of nu = 1..4
+  mg->cheb = !(getenv("FEMBRAIN_B200_MG_SMOOTHER") && !strcmp(getenv("FEMBRAIN_B200_MG_SMOOTHER"), "jacobi"));
+  mg->chebAlpha = getenv("FEMBRAIN_B200_MG_CHEB_ALPHA") ? (float)atof(getenv("FEMBRAIN_B200_MG_CHEB_ALPHA")) : 20.f;
+  mg->chebHi = getenv("FEMBRAIN_B200_MG_CHEB_HI") ? (float)atof(getenv("FEMBRAIN_B200_MG_CHEB_HI")) : 1.1f;
+  if (!(mg->chebAlpha > 1.f)) mg->chebAlpha = 20.f;
+  if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = std::min(8, atoi(getenv("FEMBRAIN_B200_MG_NU")));
   FB_TRY(fb_dev_alloc(c, &mg->slotsM, 2 * (size_t)MG_SLOTS));
   FB_TRY(fb_dev_alloc(c, &mg->slotOfDev, 27 * (size_t)MG_MAX_LEVELS));
   FB_TRY(fb_dev_alloc(c, &mg->slotsZ, (size_t)MG_SLOTS));
@@ -1205,7 +1271,7 @@ static int mg_build(fb_context *c) {
   if (mg->nLevels > 1) {
     if (Lc.r > MG_MAX_DENSE) { fb_set_error("multigrid: coarsest level has %d unknowns (> %d)", Lc.r, MG_MAX_DENSE); return FB_ERR_NOT_SUPPORTED; }
     mg->nDense = Lc.r;
-    FB_TRY(fb_dev_alloc(c, &mg->dense, (size_t)Lc.r * Lc.r + 1));
+    FB_CUDA(cudaFuncSetAttribute(k_mg_dense_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * MG_MAX_DENSE * MG_MAX_DENSE)));
     FB_TRY(fb_dev_alloc(c, &mg->denseInv, (size_t)Lc.r * Lc.r + 1));
   }
   return FB_OK;
@@ -1218,6 +1284,17 @@ int fb_mg_prepare(fb_context *c) {
   if (!mg || mg->variant == FB_SOLVER_JACOBI_PCG) return FB_OK;
   cudaStream_t st = c->stream;
   if (mg->nLevels == 0) FB_TRY(mg_build(c));
+  // developer aid (FEMBRAIN_B200_MG_TIMING=2): host clock around synchronised phases of the per-step preparation
+  const bool laps = getenv("FEMBRAIN_B200_MG_TIMING") && atoi(getenv("FEMBRAIN_B200_MG_TIMING")) == 2;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](int li, const char *what) {
+    if (!laps) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mg prepare] level %d %-24s %8.1f us\n", li, what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = std::chrono::steady_clock::now();
+  };
+  lap(-1, "(idle)");
   for (int li = 0; li < mg->nLevels; li++) {
     MgLevel &L = mg->L[li];
     fb_context *lc = L.ctx;
@@ -1231,17 +1308,19 @@ int fb_mg_prepare(fb_context *c) {
       const long long before = lc->launches;
       FB_TRY(fb_launch_assembly(lc, L.u, nullptr, true));
       c->launches += lc->launches - before;
+      lap(li, "inject + assembly");
     }
     if (mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1) {   // (the one-level variant applies Binv only)
       k_mg_scale_min<<<L.grid_vec, MG_TB, 0, st>>>((size_t)lc->r, lc->invD, reinterpret_cast<unsigned int *>(L.scale + 2));
       k_mg_scale_final<<<1, 1, 0, st>>>(L.scale, mg->half);
-      if (L.AE) k_mg_pack_ell<<<grid_for_n(c, (size_t)lc->nV), MG_TB, 0, st>>>(lc->nB, lc->nV, L.n[1], L.n[2], lc->bp, lc->brow, lc->bc, lc->Keff, L.scale,
-                                                                                mg->slotOfDev + 27 * li, L.AE);
+      if (L.AE) k_mg_pack_ell<<<L.grid_pack, PK_T, PK_SMEM, st>>>(lc->nV, L.n[1], L.n[2], lc->bp, lc->bc, lc->Keff, L.scale, mg->slotOfDev + 27 * li, L.AE);
       else if (mg->half) k_mg_pack<__half><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (__half *)L.AB);
       else k_mg_pack<float><<<grid_for_n(c, (size_t)lc->nB), MG_TB, 0, st>>>(lc->nB, lc->bp, lc->brow, lc->Keff, L.scale, (float *)L.AB);
+      lap(li, "scale + pack");
     }
     k_mg_block_inverse<<<(L.nV + 127) / 128, 128, 0, st>>>(L.nV, lc->bp, lc->diag, lc->Keff, lc->rowmask, L.Binv);
     c->launches += 4;
+    lap(li, "block inverse");
     if (getenv("FEMBRAIN_B200_MG_SYNC")) {
       cudaError_t e = cudaStreamSynchronize(st);
       fprintf(stderr, "[mg sync] level %d (nV %d, nSlots %d, AE %p AB %p) after pack + block inverse: %s\n", li, L.nV, L.nSlots, (void *)L.AE, L.AB, cudaGetErrorString(e));
@@ -1249,12 +1328,12 @@ int fb_mg_prepare(fb_context *c) {
   }
   if (mg->nLevels > 1) {
     MgLevel &Lc = mg->L[mg->nLevels - 1];
-    k_mg_dense_build<<<1, 256, 0, st>>>(Lc.nV, Lc.ctx->bp, Lc.ctx->bc, Lc.ctx->Keff, Lc.ctx->rowmask, mg->dense);
-    k_mg_dense_invert<<<1, 256, 0, st>>>(Lc.r, mg->dense, Lc.ctx->rowmask, mg->denseInv);
-    c->launches += 2;
+    k_mg_dense_inverse<<<1, MG_DENSE_T, sizeof(double) * (size_t)Lc.r * Lc.r, st>>>(Lc.nV, Lc.ctx->bp, Lc.ctx->bc, Lc.ctx->Keff, Lc.ctx->rowmask, mg->denseInv);
+    c->launches += 1;
+    lap(mg->nLevels - 1, "dense build + invert");
     const bool first = mg->L[0].lmax == 0.f;
     if (first || mg->solves >= 32) {
-      for (int li = 0; li + 1 < mg->nLevels; li++) FB_TRY(estimate_lmax(c, mg, mg->L[li], first ? 12 : 3));
+      for (int li = 0; li + 1 < mg->nLevels; li++) FB_TRY(estimate_lmax(c, mg, mg->L[li], first ? (getenv("FEMBRAIN_B200_MG_LMAX_ITS") ? atoi(getenv("FEMBRAIN_B200_MG_LMAX_ITS")) : 30) : 3));
       mg->solves = 0;
     }
   }
@@ -1296,7 +1375,9 @@ int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
   mg->preDone = 0;
   int nZ = apply_preconditioner(c, mg, &z);
   const bool cyc = mg->variant == FB_SOLVER_MG_PCG && mg->nLevels > 1;
-  const float omega0 = cyc ? 1.4f / L.lmax : 0.f;
+  float w0[8], g0[8];
+  smoother_coefficients(mg, L.lmax, w0, g0);
+  const float omega0 = cyc ? w0[0] : 0.f;
   k_mgcg_begin<<<gv, MG_TB, 0, st>>>(n, z, c->dir, c->sc, slotsM0, slotsM, mg->slotsZ, gv, nZ, eps, maxIt);
   c->launches++;
   const int CH = 6;

@@ -562,19 +562,23 @@ def variant_block(env, nx, steps, warmup, parity_iters, parity_ms, q_parity_end)
     sec_e2e, iters_e2e, _, _ = st.region(steps, True)
     info = sim.solver()
     nb64 = sim.nnz_K // 9
-    # algorithmic bytes of ONE iteration (nu = 1): the FP64 product + update + direction on the finest level, and per level of
-    # the cycle two FP16 products (28 B per block + per vertex: row pointer 4, x 16, b 16, out 16, Binv 36 in the smoothing
-    # product), pre-smoothing (68 B/vertex), restriction / prolongation (48 B per fine vertex + 32 B per coarse vertex)
+    # algorithmic bytes of ONE iteration: the FP64 product + update + direction on the finest level, and per level of the cycle
+    # 2 nu FP16 products (24 B per stored block — slot-major levels store nSlots = 15 per vertex — or 28 B per block with its
+    # column index; per vertex: x 16, b 16, out 16, Binv 36 in the smoothing products), the product-free first sweep
+    # (68 B/vertex), restriction / prolongation (48 B per fine vertex + 32 B per coarse vertex)
+    nu = max(1, info["smoothing_sweeps"])
     b_outer = 8.0 * 9 * nb64 + 4.0 * nb64 + 52.0 * (r / 3) + (61.0 + 21.0) * r
     b_cycle = 0.0
     lv, lb = info["level_vertices"], info["level_blocks"]
     for k in range(len(lv) - 1):
-        b_cycle += 2 * (28.0 * lb[k] + 52.0 * lv[k]) + 36.0 * lv[k] + 68.0 * lv[k] + 48.0 * lv[k] + 32.0 * lv[k + 1]
+        b_mat = 24.0 * 15 * lv[k] if k < info["structured_levels"] else 28.0 * lb[k]
+        b_cycle += 2 * nu * (b_mat + 52.0 * lv[k]) + 36.0 * lv[k] + 68.0 * lv[k] + 48.0 * lv[k] + 32.0 * lv[k + 1]
     b_iter = b_outer + b_cycle
     peak, _ = measured_peak_gbs()
     sim.close()
     out = {
         "solver": info["name"], "levels": info["levels"], "level_vertices": lv,
+        "smoother": {"sweeps": nu, "chebyshev": info["chebyshev"], "alpha": info["chebyshev_alpha"], "structured_levels": info["structured_levels"]},
         "value": steps / sec, "unit": UNIT, "ms_per_step": 1e3 * sec / steps, "steps": steps, "warmup": warmup,
         "e2e": {"value": steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": st.h2d, "d2h_bytes_per_step": st.d2h,
                 "same_iterations_as_resident": iters_e2e == iters},
@@ -662,7 +666,24 @@ def run_ours(args):
     # ---- configs[4]: 50M tets on the same GPUs -------------------------------------------------------------------------
     if not args.no_50m:
         def block50():
-            m, s50, _, _ = measure_mesh(env, args.nx50, args.steps50, args.warmup50, world > 1, full=False)
+            m, s50, _, mesh50 = measure_mesh(env, args.nx50, args.steps50, args.warmup50, world > 1, full=False)
+            var50 = None
+            if world == 1 and not args.no_variant:
+                # the labelled multigrid-preconditioned variant on the same context: same steps from rest
+                try:
+                    t0 = time.perf_counter()
+                    s50.set_grid(args.nx50)
+                    s50.set_solver("mg")
+                    t_set = time.perf_counter() - t0
+                    st50 = Stepper(env, s50, mesh50[3], False, mesh50[1])
+                    s50.reset_to_rest()
+                    _, itw, _, _ = st50.region(args.warmup50, False)
+                    sec50, it50, _, tsol50 = st50.region(args.steps50, False)
+                    var50 = {"solver": s50.solver()["name"], "value": args.steps50 / sec50, "unit": UNIT, "ms_per_step": 1e3 * sec50 / args.steps50,
+                             "cg_iterations_per_step": it50, "cg_iterations_warmup": itw, "ms_per_iteration": 1e3 * tsol50 / max(sum(it50), 1),
+                             "set_solver_seconds": t_set, "device_bytes": s50.device_bytes}
+                except Exception as e:  # noqa: BLE001
+                    var50 = {"error": f"{type(e).__name__}: {e}"[:300]}
             s50.close()
             if m is None:
                 return None
@@ -671,6 +692,8 @@ def run_ours(args):
             out = {k: m[k] for k in keep if k in m}
             out.update({"workload": config_dict(args.nx50, m["tets"], world, world > 1)["workload"], "unit": UNIT, "steps": args.steps50,
                         "warmup": args.warmup50, "parallelism": config_dict(args.nx50, m["tets"], world, world > 1)["parallelism"]})
+            if var50 is not None:
+                out["solver_variant"] = var50
             return out
         guarded("config5_50M", block50)
 

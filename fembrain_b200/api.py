@@ -94,6 +94,7 @@ def load_library():
         "fb_set_grid": (ci, [vp, ci, ci, ci]), "fb_set_solver": (ci, [vp, ci, ci]),
         "fb_get_solver": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]), "fb_solver_name": (C.c_char_p, [ci]),
         "fb_get_solver_levels": (ci, [vp, ci, vp, vp]),
+        "fb_get_solver_smoother": (ci, [vp, vp, vp, vp, vp]),
         "fb_step": (ci, [vp]),
         "fb_deformable_timestep": (ci, [vp]), "fb_deformable_set_gravity": (ci, [vp, ci]),
         "fb_deformable_set_floor": (ci, [vp, ci, cd]),
@@ -484,8 +485,11 @@ class Simulation:
         self._check(self._lib.fb_get_solver(self._h, C.byref(v), C.byref(w), C.byref(lv)), "fb_get_solver")
         nv, nb = np.zeros(max(lv.value, 1), np.int32), np.zeros(max(lv.value, 1), np.int64)
         self._check(self._lib.fb_get_solver_levels(self._h, lv.value, _ptr(nv), _ptr(nb)), "fb_get_solver_levels")
+        nu, ch, ns, al = C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0)
+        self._check(self._lib.fb_get_solver_smoother(self._h, C.byref(nu), C.byref(ch), C.byref(al), C.byref(ns)), "fb_get_solver_smoother")
         return {"variant": v.value, "name": self._lib.fb_solver_name(v.value).decode(), "warm_start": bool(w.value), "levels": lv.value,
-                "level_vertices": [int(x) for x in nv[:lv.value]], "level_blocks": [int(x) for x in nb[:lv.value]]}
+                "level_vertices": [int(x) for x in nv[:lv.value]], "level_blocks": [int(x) for x in nb[:lv.value]],
+                "smoothing_sweeps": nu.value, "chebyshev": bool(ch.value), "chebyshev_alpha": al.value, "structured_levels": ns.value}
 
     def set_timestep(self, h):
         self._check(self._lib.fb_set_timestep(self._h, h), "fb_set_timestep")

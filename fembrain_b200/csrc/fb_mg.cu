@@ -1513,11 +1513,23 @@ int fb_get_solver_levels(const fb_context *c, int capacity, int *num_vertices, l
   return FB_OK;
 }
 
+int fb_get_solver_smoother(const fb_context *c, int *sweeps, int *chebyshev, double *alpha, int *structured_levels) {
+  if (!c) return FB_ERR_INVALID_ARGUMENT;
+  const FbMg *mg = c->mg;
+  if (sweeps) *sweeps = mg ? mg->nu : 0;
+  if (chebyshev) *chebyshev = (mg && mg->cheb && mg->nu >= 2) ? 1 : 0;
+  if (alpha) *alpha = mg ? (double)mg->chebAlpha : 0.0;
+  int n = 0;
+  if (mg) for (int i = 0; i < mg->nLevels; i++) n += mg->L[i].AE != nullptr;
+  if (structured_levels) *structured_levels = n;
+  return FB_OK;
+}
+
 const char *fb_solver_name(int variant) {
   switch (variant) {
     case FB_SOLVER_JACOBI_PCG: return "jacobi_pcg (the reference's algorithm, CGSolver.cpp:129-190)";
     case FB_SOLVER_BLOCK_JACOBI_PCG: return "block_jacobi_pcg (variant: 3x3 block-diagonal preconditioner, FP32 apply)";
-    case FB_SOLVER_MG_PCG: return "mg_pcg (variant: geometric multigrid V(1,1) preconditioner on re-assembled coarse levels, FP32 cycle, FP64 CG)";
+    case FB_SOLVER_MG_PCG: return "mg_pcg (variant: geometric multigrid V-cycle preconditioner, Chebyshev block-Jacobi smoothing, re-assembled coarse levels, FP16/FP32 cycle, FP64 CG)";
     default: return "unknown";
   }
 }

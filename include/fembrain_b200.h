@@ -152,6 +152,9 @@ int fb_get_solver(const fb_context *ctx, int *variant, int *warm_start, int *lev
 const char *fb_solver_name(int variant);
 /* vertices and 3x3 blocks of every level of the variant's hierarchy, finest first (fb_get_solver gives the level count) */
 int fb_get_solver_levels(const fb_context *ctx, int capacity, int *num_vertices, long long *num_blocks);
+/* the cycle's smoother: sweeps before and after the coarse correction, 1 when they form a Chebyshev iteration on
+ * [1.1 lambda_max / alpha, 1.1 lambda_max] (0: damped block Jacobi), and how many levels use the structured slot-major product */
+int fb_get_solver_smoother(const fb_context *ctx, int *sweeps, int *chebyshev, double *alpha, int *structured_levels);
 
 /* ---- the step ---------------------------------------------------------------------------------
  * VolumeConservingIntegrator::DoTimestep (DEF/PS_VolumeConservingIntegrator.cpp:46-260), PCG branch,

@@ -89,6 +89,7 @@ def load_library():
         "fb_reset_to_rest": (ci, [vp]),
         "fb_set_external_forces_dev": (ci, [vp, vp]), "fb_get_state_dev": (ci, [vp, vp, vp, vp]),
         "fb_displacements_dev": (vp, [vp]),
+        "fb_set_warp": (ci, [vp, ci]), "fb_get_warp": (ci, [vp]),
         "fb_set_timestep": (ci, [vp, cd]), "fb_set_damping": (ci, [vp, cd, cd]),
         "fb_set_internal_force_scaling": (ci, [vp, cd]), "fb_set_cg": (ci, [vp, cd, ci]),
         "fb_set_grid": (ci, [vp, ci, ci, ci]), "fb_set_solver": (ci, [vp, ci, ci]),
@@ -490,6 +491,14 @@ class Simulation:
         return {"variant": v.value, "name": self._lib.fb_solver_name(v.value).decode(), "warm_start": bool(w.value), "levels": lv.value,
                 "level_vertices": [int(x) for x in nv[:lv.value]], "level_blocks": [int(x) for x in nb[:lv.value]],
                 "smoothing_sweeps": nu.value, "chebyshev": bool(ch.value), "chebyshev_alpha": al.value, "structured_levels": ns.value}
+
+    def set_warp(self, warp):
+        """CorotationalLinearFEMForceModel(fem, warp): 0 linear, 1 corotational (default), 2 exact tangent."""
+        self._check(self._lib.fb_set_warp(self._h, int(warp)), "fb_set_warp")
+
+    @property
+    def warp(self):
+        return self._lib.fb_get_warp(self._h)
 
     def set_timestep(self, h):
         self._check(self._lib.fb_set_timestep(self._h, h), "fb_set_timestep")

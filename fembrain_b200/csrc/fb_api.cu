@@ -228,6 +228,7 @@ int fb_create_local(fb_context **out, int nV, const double *x0, int nT, const in
   c->prm = p;
   c->nV = nV; c->nT = nT; c->r = 3 * nV;
   c->haptic_rings = 5;  // m_hapticForceNeighorhoodSize, DEF/Deformable.cpp ctor
+  c->warp = 1;          // CorotationalLinearFEMForceModel(fem) — warp defaults to 1, Deformable.cpp:186
   c->uniform_material = (!E && !nu && !rho) ? 1 : 0;
   c->row_lo = 0; c->row_hi = nV;
   int st = FB_OK;
@@ -595,6 +596,13 @@ int fb_set_damping(fb_context *c, double dm, double dk) {
   c->prm.damping_mass = dm; c->prm.damping_stiffness = dk;
   return FB_OK;
 }
+int fb_set_warp(fb_context *c, int warp) {
+  if (!c || warp < 0 || warp > 2) { fb_set_error("fb_set_warp: warp must be 0 (linear), 1 (corotational) or 2 (exact tangent)"); return FB_ERR_INVALID_ARGUMENT; }
+  if (warp != 1 && c->mg && fb_mg_active(c)) { fb_set_error("fb_set_warp: the solver variants re-assemble their coarse levels with warp = 1"); return FB_ERR_NOT_SUPPORTED; }
+  c->warp = warp;
+  return FB_OK;
+}
+int fb_get_warp(const fb_context *c) { return c ? c->warp : -1; }
 int fb_set_internal_force_scaling(fb_context *c, double s) { if (!c) return FB_ERR_INVALID_ARGUMENT; c->prm.internal_force_scaling = s; return FB_OK; }
 int fb_set_cg(fb_context *c, double eps, int maxIt) {
   if (!c || maxIt < 0) return FB_ERR_INVALID_ARGUMENT;

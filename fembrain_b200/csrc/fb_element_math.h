@@ -87,9 +87,9 @@ FB_HD void cross3(const double *a, const double *b, double *c) {
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-// PolarDecomposition::Compute, rotation only (S is not used on the warp=1 path).  Q row-major.
-// Identical iteration, scaling and stopping rule => identical trip count and bits.
-FB_HD double polar_rotation(const double *M, double *Q, double tolerance, int *itersOut) {
+// PolarDecomposition::Compute.  Q row-major; S (optional: only the exact-tangent branch, warp = 2, reads it) = Q^T M, then
+// symmetrised (polarDecomposition.cpp:94-105).  Identical iteration, scaling and stopping rule => identical trip count and bits.
+FB_HD double polar_rotation(const double *M, double *Q, double tolerance, int *itersOut, double *S = nullptr) {
   double Mk[9], Ek[9];
   double det, M1, Minf, E1;
   for (int i = 0; i < 3; i++)
@@ -121,6 +121,16 @@ FB_HD double polar_rotation(const double *M, double *Q, double tolerance, int *i
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) Q[3 * i + j] = Mk[3 * j + i];
   if (itersOut) *itersOut = it;
+  if (S) {
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double acc = 0;
+        for (int k = 0; k < 3; k++) acc += Mk[3 * i + k] * M[3 * k + j];
+        S[3 * i + j] = acc;
+      }
+    for (int i = 0; i < 3; i++)
+      for (int j = i; j < 3; j++) S[3 * i + j] = S[3 * j + i] = 0.5 * (S[3 * i + j] + S[3 * j + i]);
+  }
   return det;
 }
 
@@ -190,6 +200,162 @@ FB_HD void warp_block(const double *R, const double *K, double RK[9], double RKR
 FB_HD void force_accumulate(const double Kel[9], const double RK[9], const double *Pj, const double *X0j, double facc[3]) {
   for (int k = 0; k < 3; k++)
     for (int l = 0; l < 3; l++) facc[k] += Kel[3 * k + l] * Pj[l] - RK[3 * k + l] * X0j[l];
+}
+
+// ---- warp = 0 and warp = 2 (corotationalLinearFEM.cpp:296-449): whole 12x12 element matrices, one thread per element ------
+// w = A v, w = A^T v, c = a b, c = a b^T in the association order of Vega's matrixMultiplyMacros.h (:224-270)
+FB_HD void mv3(const double *A, const double *v, double *w) {
+  w[0] = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+  w[1] = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+  w[2] = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+}
+FB_HD void mtv3(const double *A, const double *v, double *w) {
+  w[0] = A[0] * v[0] + A[3] * v[1] + A[6] * v[2];
+  w[1] = A[1] * v[0] + A[4] * v[1] + A[7] * v[2];
+  w[2] = A[2] * v[0] + A[5] * v[1] + A[8] * v[2];
+}
+FB_HD void mm3(const double *a, const double *b, double *c) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+FB_HD void mmt3(const double *a, const double *b, double *c) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) c[3 * i + j] = a[3 * i] * b[3 * j] + a[3 * i + 1] * b[3 * j + 1] + a[3 * i + 2] * b[3 * j + 2];
+}
+// CorotationalLinearFEM::inverse3x3 (:506-524)
+FB_HD void inverse3(const double *A, double *AInv) {
+  AInv[0] = -A[5] * A[7] + A[4] * A[8];
+  AInv[1] = A[2] * A[7] - A[1] * A[8];
+  AInv[2] = -A[2] * A[4] + A[1] * A[5];
+  AInv[3] = A[5] * A[6] - A[3] * A[8];
+  AInv[4] = -A[2] * A[6] + A[0] * A[8];
+  AInv[5] = A[2] * A[3] - A[0] * A[5];
+  AInv[6] = -A[4] * A[6] + A[3] * A[7];
+  AInv[7] = A[1] * A[6] - A[0] * A[7];
+  AInv[8] = -A[1] * A[3] + A[0] * A[4];
+  const double invDet = 1.0 / (-A[2] * A[4] * A[6] + A[1] * A[5] * A[6] + A[2] * A[3] * A[7] - A[0] * A[5] * A[7] - A[1] * A[3] * A[8] +
+                               A[0] * A[4] * A[8]);
+  for (int i = 0; i < 9; i++) AInv[i] *= invDet;
+}
+
+// The exact-tangent terms of warp = 2 added to KElement (row-major 12x12), :296-428.  R, S from the polar decomposition (R already
+// flipped when det < 0, S not — as in the reference), G = the 4x3 of MInverse, Pw / X0 world and rest positions of the four
+// vertices, K0 / RK the element's undeformed and half-warped matrices.
+FB_HD void exact_tangent_add(const double *R, const double *S, const double *G, const double Pw[4][3], const double X0[4][3],
+                             const double *K0, const double *RK, double *KElement) {
+  double Gm[9], temp[9], invG[9];
+  const double tr = S[0] + S[4] + S[8];
+  for (int i = 0; i < 9; i++) temp[i] = -S[i];
+  temp[0] += tr; temp[4] += tr; temp[8] += tr;
+  mmt3(temp, R, Gm);          // G = (tr(S) I - S) R^T
+  inverse3(Gm, invG);
+  double rhs[27], omega[27];  // 3 x 9, column-major
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double t[9];
+      for (int k = 0; k < 9; k++) t[k] = 0.0;
+      for (int k = 0; k < 3; k++) t[3 * k + j] = R[3 * i + k];   // i-th row of R into column j
+      double *a = &rhs[3 * (3 * i + j)];                          // SKEW_PART
+      a[0] = 0.5 * (t[7] - t[5]);
+      a[1] = 0.5 * (t[2] - t[6]);
+      a[2] = 0.5 * (t[3] - t[1]);
+    }
+  for (int i = 0; i < 27; i++) rhs[i] *= 2.0;
+  for (int i = 0; i < 9; i++) mv3(invG, &rhs[3 * i], &omega[3 * i]);
+  double dRdF[81];            // each column is skew(omega) R; column-major
+  for (int i = 0; i < 9; i++) {
+    const double *a = &omega[3 * i];
+    double skew[9];
+    skew[0] = 0;     skew[1] = -a[2]; skew[2] = a[1];
+    skew[3] = a[2];  skew[4] = 0;     skew[5] = -a[0];
+    skew[6] = -a[1]; skew[7] = a[0];  skew[8] = 0;
+    mm3(skew, R, &dRdF[9 * i]);
+  }
+  double dRdx[108];           // d R / d x of the tet's 12 coordinates; column-major, each column a row-major 3x3
+  for (int k = 0; k < 4; k++)
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double B[9];          // B[i][j][3 kk + l] = dRdF[9 (3 j + l) + 3 i + kk]
+        for (int kk = 0; kk < 3; kk++)
+          for (int l = 0; l < 3; l++) B[3 * kk + l] = dRdF[9 * (3 * j + l) + 3 * i + kk];
+        mv3(B, &G[3 * k], &dRdx[9 * (3 * k + j) + 3 * i]);
+      }
+  // term 1: \hat{dR/dx_l} K (R^T x - m)
+  double tv[12], a[12];
+  for (int vtx = 0; vtx < 4; vtx++) {
+    mtv3(R, Pw[vtx], &tv[3 * vtx]);
+    for (int i = 0; i < 3; i++) tv[3 * vtx + i] -= X0[vtx][i];
+  }
+  for (int i = 0; i < 12; i++) {
+    double acc = 0.0;
+    for (int j = 0; j < 12; j++) acc += K0[12 * i + j] * tv[j];
+    a[i] = acc;
+  }
+  for (int column = 0; column < 12; column++) {
+    double b[12];
+    for (int j = 0; j < 4; j++) mv3(&dRdx[9 * column], &a[3 * j], &b[3 * j]);
+    for (int row = 0; row < 12; row++) KElement[12 * row + column] += b[row];
+  }
+  // term 2: (R K \hat{dR/dx_l}^T) x
+  for (int vtx = 0; vtx < 4; vtx++)
+    for (int i = 0; i < 3; i++) a[3 * vtx + i] = Pw[vtx][i];
+  for (int column = 0; column < 12; column++) {
+    double b[12];
+    for (int j = 0; j < 4; j++) mtv3(&dRdx[9 * column], &a[3 * j], &b[3 * j]);
+    for (int row = 0; row < 12; row++) {
+      double contrib = 0.0;
+      for (int j = 0; j < 12; j++) contrib += RK[12 * row + j] * b[j];
+      KElement[12 * row + column] += contrib;
+    }
+  }
+}
+
+// Whole element, any warp: KE (row-major 12x12) and fEl (12) as ComputeForceAndStiffnessMatrixOfSubmesh forms them (:232-449).
+FB_HD void element_full(int warp, const double X0[4][3], const double U[4][3], const double G[12], double vol, double lambda, double mu,
+                        double tol, double *KE, double *fEl) {
+  double K0[144];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      double eb[9], K[9];
+      eb_products(G + 3 * j, lambda, mu, eb);
+      k0_block(G + 3 * i, eb, vol, K);
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) K0[12 * (3 * i + k) + 3 * j + l] = K[3 * k + l];
+    }
+  if (warp == 0) {
+    // no warp: KElement = K0, f = K u with each vertex's three products summed first (:431-441)
+    for (int q = 0; q < 144; q++) KE[q] = K0[q];
+    for (int i = 0; i < 12; i++) {
+      double acc = 0;
+      for (int j = 0; j < 4; j++) acc += KE[12 * i + 3 * j + 0] * U[j][0] + KE[12 * i + 3 * j + 1] * U[j][1] + KE[12 * i + 3 * j + 2] * U[j][2];
+      fEl[i] = acc;
+    }
+    return;
+  }
+  double P[4][3], F[9], R[9], S[9], RK[144];
+  for (int v = 0; v < 4; v++)
+    for (int cc = 0; cc < 3; cc++) P[v][cc] = X0[v][cc] + U[v][cc];
+  deformation_gradient(P, G, F);
+  const double det = polar_rotation(F, R, tol, nullptr, S);
+  if (det < 0)
+    for (int i = 0; i < 9; i++) R[i] *= -1.0;
+  for (int i = 0; i < 4; i++) {
+    double facc[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < 4; j++) {
+      double Kb[9], RKb[9], Kel[9];
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) Kb[3 * k + l] = K0[12 * (3 * i + k) + 3 * j + l];
+      warp_block(R, Kb, RKb, Kel);
+      force_accumulate(Kel, RKb, P[j], X0[j], facc);
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) {
+          RK[12 * (3 * i + k) + 3 * j + l] = RKb[3 * k + l];
+          KE[12 * (3 * i + k) + 3 * j + l] = Kel[3 * k + l];
+        }
+    }
+    for (int k = 0; k < 3; k++) fEl[3 * i + k] = facc[k];
+  }
+  if (warp == 2) exact_tangent_add(R, S, G, P, X0, K0, RK, KE);
 }
 
 }  // namespace fbm

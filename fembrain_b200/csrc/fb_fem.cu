@@ -130,6 +130,38 @@ __global__ void __launch_bounds__(EL_TB) k_element(int nT, const int *__restrict
   }
 }
 
+// ---- phase 1 for warp = 0 (linear FEM) and warp = 2 (exact tangent): whole 12x12 element matrix per thread ------------------
+// corotationalLinearFEM.cpp:232-449.  Not on the reference's hot path (Deformable.cpp:186 builds its force model with the
+// default warp = 1); offered through fb_set_warp for callers of CorotationalLinearFEMForceModel(fem, warp).  Same scratch
+// layout as k_element ([16 blocks][nT][9] and [12][nT]), so phase 2 is shared.
+template <int WARP>
+__global__ void __launch_bounds__(64) k_element_full(int nT, const int *__restrict__ tets, const double *__restrict__ x0,
+                                                     const double *__restrict__ u, const double *__restrict__ ed, double tol,
+                                                     double *__restrict__ scrK, double *__restrict__ scrF) {
+  const int el = blockIdx.x * blockDim.x + threadIdx.x;
+  if (el >= nT) return;
+  const int4 vt = reinterpret_cast<const int4 *>(tets)[el];
+  const int vi[4] = {vt.x, vt.y, vt.z, vt.w};
+  double X0[4][3], U[4][3];
+  for (int v = 0; v < 4; v++)
+    for (int cc = 0; cc < 3; cc++) {
+      X0[v][cc] = x0[3 * (size_t)vi[v] + cc];
+      U[v][cc] = u[3 * (size_t)vi[v] + cc];
+    }
+  double G[12];
+  for (int k = 0; k < 12; k++) G[k] = ed[(size_t)k * nT + el];
+  const double vol = ed[(size_t)12 * nT + el], lambda = ed[(size_t)13 * nT + el], mu = ed[(size_t)14 * nT + el];
+  double KE[144], fEl[12];
+  fbm::element_full(WARP, X0, U, G, vol, lambda, mu, tol, KE, fEl);
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      double *dst = scrK + ((size_t)(4 * i + j) * nT + el) * 9;
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) dst[3 * k + l] = KE[12 * (3 * i + k) + 3 * j + l];
+    }
+  for (int i = 0; i < 12; i++) scrF[(size_t)i * nT + el] = fEl[i];
+}
+
 // ---- phase 2: one thread per scalar entry of K -----------------------------------------------------
 struct ReduceParams {
   int nB, nT;
@@ -313,12 +345,17 @@ int fb_launch_assembly(fb_context *c, const double *u, double *Kraw, bool effect
     }
     return FB_OK;
   }
-  if (c->ga_ctas > 0) return fb_launch_assembly_gather(c, u, Kraw, effective, rhs);
+  if (c->ga_ctas > 0 && c->warp == 1) return fb_launch_assembly_gather(c, u, Kraw, effective, rhs);
   if (effective && !c->T) FB_TRY(fb_dev_alloc(c, &c->T, (size_t)c->nnzK));
   if (!c->scrK) FB_TRY(fb_dev_alloc(c, &c->scrK, 144 * (size_t)c->nT));
   if (!c->scrF) FB_TRY(fb_dev_alloc(c, &c->scrF, 12 * (size_t)c->nT));
-  k_element<<<grid_for(c->nT, EL_TB), EL_TB, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance,
-                                                              c->scrK, c->scrF);
+  if (c->warp == 0)
+    k_element_full<0><<<grid_for(c->nT, 64), 64, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance, c->scrK, c->scrF);
+  else if (c->warp == 2)
+    k_element_full<2><<<grid_for(c->nT, 64), 64, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance, c->scrK, c->scrF);
+  else
+    k_element<<<grid_for(c->nT, EL_TB), EL_TB, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance,
+                                                                c->scrK, c->scrF);
   ReduceParams p;
   p.nB = c->nB; p.nT = c->nT;
   p.scale = c->prm.internal_force_scaling; p.h = c->prm.timestep;

@@ -101,6 +101,7 @@ struct fb_context {
   // row-gather assembly (fb_assembly.cu; default): per-CTA index lists, element and vertex records.
   // ga_ctas == 0 -> two-phase path (scrK/scrF, allocated on first use).
   int ga_ctas, ga_cfg;
+  int warp;                  // CorotationalLinearFEM's warp argument: 1 (default; the only one the gather path serves), 0 linear, 2 exact tangent
   int *ga_incp;              // [nV+1] incidence (vertex, element, i) counts, prefix sum
   int *ga_ctaV;              // [ga_ctas+1] first vertex of every CTA
   unsigned char *ga_lists;   // [ga_ctas] GaLists blobs

@@ -138,6 +138,13 @@ int fb_get_state_dev(fb_context *ctx, double *q_dev, double *qvel_dev, double *q
 const double *fb_displacements_dev(const fb_context *ctx);
 
 int fb_set_timestep(fb_context *ctx, double h);                        /* IntegratorBase::SetTimestep */
+/* the `warp` argument of CorotationalLinearFEMForceModel(fem, warp) / ComputeForceAndStiffnessMatrix
+ * (VEGA/corotationalLinearFEM/corotationalLinearFEM.cpp:219-449): 1 = corotational with the approximate tangent R K0 R^T (the
+ * default, what Deformable.cpp:186 builds and the only mode served by the one-pass gather assembly), 0 = linear FEM (no
+ * rotations), 2 = exact tangent (adds the dR/dx terms, :296-428).  0 and 2 run the two-phase assembly with one thread per
+ * element; K and f stay bit-identical to the reference's for every mode. */
+int fb_set_warp(fb_context *ctx, int warp);
+int fb_get_warp(const fb_context *ctx);
 int fb_set_damping(fb_context *ctx, double damping_mass, double damping_stiffness); /* SetDampingMassCoef / SetDampingStiffnessCoef */
 int fb_set_internal_force_scaling(fb_context *ctx, double s);          /* SetInternalForceScalingFactor */
 int fb_set_cg(fb_context *ctx, double epsilon, int max_iterations);

@@ -71,7 +71,8 @@ class CudaCorotationalForceModel : public ForceModel {
   // are read from the model's TetMesh; non-ENu materials are rejected the way CorotationalLinearFEM's constructor rejects
   // them (`throw 1`, corotationalLinearFEM.cpp:61-64).  (The CPU-side CorotationalLinearFEM object itself is then unused: a
   // host that wants the fast setup drops it and calls the mesh-array constructor above.)
-  explicit CudaCorotationalForceModel(CorotationalLinearFEM *fem, int device = 0) : ctx_(NULL) {
+  // `warp` as in CorotationalLinearFEMForceModel(fem, warp) (corotationalLinearFEMForceModel.h:42): 0 linear, 1 default, 2 exact tangent.
+  explicit CudaCorotationalForceModel(CorotationalLinearFEM *fem, int warp = 1, int device = 0) : ctx_(NULL) {
     TetMesh *mesh = fem->GetTetMesh();
     const int nV = mesh->getNumVertices(), nT = mesh->getNumElements();
     std::vector<double> x(3 * (size_t)nV + 1), E((size_t)nT + 1), nu((size_t)nT + 1), rho((size_t)nT + 1);
@@ -92,6 +93,10 @@ class CudaCorotationalForceModel : public ForceModel {
     p.device = device;
     int st = fb_create_with_materials(&ctx_, nV, &x[0], nT, &t[0], 0, NULL, &E[0], &nu[0], &rho[0], &p);
     if (st != FB_OK) vega_fail("fb_create_with_materials", st);
+    if (warp != 1) {
+      st = fb_set_warp(ctx_, warp);
+      if (st != FB_OK) vega_fail("fb_set_warp", st);
+    }
     r = 3 * nV;
   }
   virtual ~CudaCorotationalForceModel() { fb_destroy(ctx_); }

@@ -77,6 +77,9 @@ def _lib(kind: str):
         lib.fbref_num_tets.argtypes = [vp]
         lib.fbref_mesh.restype = None
         lib.fbref_mesh.argtypes = [vp, vp, vp, vp, vp, vp]
+        if hasattr(lib, "fbref_force_and_matrix_warp"):   # (a library built before the warp entry was added lacks it)
+            lib.fbref_force_and_matrix_warp.restype = None
+            lib.fbref_force_and_matrix_warp.argtypes = [vp, vp, ci, vp, vp]
     _loaded[kind] = lib
     return lib
 
@@ -201,6 +204,16 @@ class Oracle:
         u = _f64(u).reshape(-1)
         f, a = np.zeros(self.r), np.zeros(self.nnz_K)
         self._fn("force_and_matrix")(self._h, u.ctypes.data, f.ctypes.data, a.ctypes.data)
+        return f, a
+
+    def force_and_matrix_warp(self, u, warp):
+        """ComputeForceAndStiffnessMatrix(u, f, K, warp) of the compiled reference (kind "ref" only: the port restates warp = 1)."""
+        if self.kind != "ref":
+            raise NotImplementedError("warp modes are checked against the compiled reference")
+        u = _f64(u).reshape(-1)
+        f, a = np.zeros(self.r), np.zeros(self.nnz_K)
+        fn = self._fn("force_and_matrix_warp")
+        fn(self._h, u.ctypes.data, int(warp), f.ctypes.data, a.ctypes.data)
         return f, a
 
     def set_state(self, q, qvel=None):

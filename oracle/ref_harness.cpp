@@ -195,6 +195,16 @@ void fbref_force_and_matrix(void *p, const double *u, double *f, double *Ka) {
   if (Ka) K->GenerateCompressedRowMajorFormat(Ka, NULL, NULL, 0, 0);
 }
 
+// CorotationalLinearFEM::ComputeForceAndStiffnessMatrix with an explicit warp (0 linear, 1 corotational, 2 exact tangent),
+// corotationalLinearFEM.cpp:214-449 — what CorotationalLinearFEMForceModel(fem, warp)::GetForceAndMatrix calls
+void fbref_force_and_matrix_warp(void *p, const double *u, int warp, double *f, double *Ka) {
+  RefSim *s = (RefSim *)p;
+  std::vector<double> uu(u, u + 3 * (size_t)s->nV);
+  SparseMatrix *K = s->integrator->tangentStiffnessMatrix;
+  s->fem->ComputeForceAndStiffnessMatrix(&uu[0], f, K, warp);
+  if (Ka) K->GenerateCompressedRowMajorFormat(Ka, NULL, NULL, 0, 0);
+}
+
 void fbref_set_state(void *p, const double *q, const double *qvel) {
   ((RefSim *)p)->integrator->SetqState(q, qvel, NULL);
 }

@@ -70,5 +70,32 @@ void hm_assemble(int nV, int nT, const int *tets, const double *x0, const double
   }
 }
 
+// the same scatter for any warp (0 linear, 1 corotational, 2 exact tangent) through fbm::element_full — the function the
+// device kernel k_element_full calls
+void hm_assemble_warp(int nV, int nT, const int *tets, const double *x0, const double *u, double lambda, double mu, double tol,
+                      const int *Kia, const int *colIdx16, int warp, double *f, double *Ka) {
+  memset(f, 0, sizeof(double) * 3 * (size_t)nV);
+  memset(Ka, 0, sizeof(double) * (size_t)Kia[3 * nV]);
+  for (int el = 0; el < nT; el++) {
+    const int *vt = tets + 4 * el;
+    double X0[4][3], U[4][3];
+    for (int v = 0; v < 4; v++)
+      for (int c = 0; c < 3; c++) {
+        X0[v][c] = x0[3 * vt[v] + c];
+        U[v][c] = u[3 * vt[v] + c];
+      }
+    double G[12], KE[144], fEl[12];
+    fbm::minverse_4x3(X0, G, 0);
+    double vol = fbm::tet_volume(X0[0], X0[1], X0[2], X0[3]);
+    fbm::element_full(warp, X0, U, G, vol, lambda, mu, tol, KE, fEl);
+    for (int j = 0; j < 4; j++)
+      for (int l = 0; l < 3; l++) f[3 * vt[j] + l] += fEl[3 * j + l];
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++)
+        for (int k = 0; k < 3; k++)
+          for (int l = 0; l < 3; l++) Ka[Kia[3 * vt[i] + k] + 3 * colIdx16[16 * el + 4 * i + j] + l] += KE[12 * (3 * i + k) + 3 * j + l];
+  }
+}
+
 double hm_polar(const double *F, double *R, double tol, int *iters) { return fbm::polar_rotation(F, R, tol, iters); }
 }

@@ -234,6 +234,16 @@ def cpu_baseline_sample(nx_full, nT_full, nnz_full, mean_iters_full, nx_sample):
     t_asm, t_sol = o.assembly_time(), o.solve_time()
     _, its = o.solve(eps=1e-6)   # the same system again, to read the solver's own iteration count (CGSolver.cpp:189)
     nnz_s, nT_s = o.nnz_K, len(t)
+    # the reference's stronger assembly baseline, labelled separately: CorotationalLinearFEMMT, pthreads
+    mt = None
+    if kind == "ref" and hasattr(o, "mt_assembly_seconds"):
+        try:
+            threads = max(1, min(os.cpu_count() or 1, 16))
+            sec_mt, fdiff = o.mt_assembly_seconds(np.zeros(3 * len(v)), threads, 2)
+            mt = {"kind": "CorotationalLinearFEMMT::ComputeForceAndStiffnessMatrix (corotationalLinearFEMMT.cpp:126-177)", "threads": threads,
+                  "mtets_per_s": nT_s / sec_mt / 1e6, "seconds_on_sample": sec_mt, "max_force_diff_vs_single_thread": fdiff}
+        except Exception as e:  # noqa: BLE001
+            mt = {"error": str(e)[:200]}
     o.close()
     est = t_asm * nT_full / nT_s + t_sol * (nnz_full / nnz_s) * (mean_iters_full / max(its, 1)) + (t_step - t_asm - t_sol) * nT_full / nT_s
     return {"value": 1.0 / est, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
@@ -242,7 +252,7 @@ def cpu_baseline_sample(nx_full, nT_full, nnz_full, mean_iters_full, nx_sample):
                        f"({nT_full} tets, {mean_iters_full:.0f} iterations/step) by tets (assembly) and nnz x iterations (solve); 1 thread of "
                        f"{os.cpu_count()}; the full-size reference run is `bench.py --impl reference`"),
             "measured_steps_per_s_on_sample": 1.0 / t_step, "assembly_mtets_per_s": nT_s / t_asm / 1e6,
-            "seconds_per_cg_iteration_on_sample": t_sol / max(its, 1), "sample_tets": nT_s}
+            "seconds_per_cg_iteration_on_sample": t_sol / max(its, 1), "sample_tets": nT_s, "assembly_multithreaded": mt}
 
 
 def ncu_table(key, field):

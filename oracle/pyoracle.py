@@ -77,6 +77,9 @@ def _lib(kind: str):
         lib.fbref_num_tets.argtypes = [vp]
         lib.fbref_mesh.restype = None
         lib.fbref_mesh.argtypes = [vp, vp, vp, vp, vp, vp]
+        if hasattr(lib, "fbref_mt_assembly_seconds"):
+            lib.fbref_mt_assembly_seconds.restype = cd
+            lib.fbref_mt_assembly_seconds.argtypes = [vp, vp, ci, ci, vp]
         if hasattr(lib, "fbref_force_and_matrix_warp"):   # (a library built before the warp entry was added lacks it)
             lib.fbref_force_and_matrix_warp.restype = None
             lib.fbref_force_and_matrix_warp.argtypes = [vp, vp, ci, vp, vp]
@@ -215,6 +218,14 @@ class Oracle:
         fn = self._fn("force_and_matrix_warp")
         fn(self._h, u.ctypes.data, int(warp), f.ctypes.data, a.ctypes.data)
         return f, a
+
+    def mt_assembly_seconds(self, u, threads, reps=2):
+        """CorotationalLinearFEMMT (the reference's pthread assembly) on this mesh: (best wall-clock seconds per
+        ComputeForceAndStiffnessMatrix, max |f_mt - f_single|).  kind "ref" only."""
+        u = _f64(u).reshape(-1)
+        diff = C.c_double(0)
+        sec = self._lib.fbref_mt_assembly_seconds(self._h, u.ctypes.data, int(threads), int(reps), C.addressof(diff))
+        return float(sec), float(diff.value)
 
     def set_state(self, q, qvel=None):
         q = _f64(q).reshape(-1)

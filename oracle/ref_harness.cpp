@@ -21,6 +21,7 @@
 #include "implicitNewmarkSparse.h"
 #include "PS_VolumeConservingIntegrator.h"
 #include "corotationalLinearFEM.h"
+#include "corotationalLinearFEMMT.h"
 #include "corotationalLinearFEMForceModel.h"
 #include "generateMassMatrix.h"
 #include "polarDecomposition.h"
@@ -33,6 +34,8 @@
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <stdio.h>
 #include <vector>
 
 #define FBO_PREFIX fbref_
@@ -203,6 +206,36 @@ void fbref_force_and_matrix_warp(void *p, const double *u, int warp, double *f, 
   SparseMatrix *K = s->integrator->tangentStiffnessMatrix;
   s->fem->ComputeForceAndStiffnessMatrix(&uu[0], f, K, warp);
   if (Ka) K->GenerateCompressedRowMajorFormat(Ka, NULL, NULL, 0, 0);
+}
+
+// The reference's stronger CPU assembly baseline (optional): CorotationalLinearFEMMT
+// (corotationalLinearFEMMT.cpp:126-177) — numThreads pthreads over element ranges, one private force vector and stiffness
+// matrix per thread, summed afterwards.  Wall-clock seconds per ComputeForceAndStiffnessMatrix (best of `reps`), and the
+// largest |f_mt - f_single| as a sanity figure (the summation order differs from the single-threaded loop, so not bit-exact).
+double fbref_mt_assembly_seconds(void *p, const double *u, int threads, int reps, double *maxForceDiff) {
+  RefSim *s = (RefSim *)p;
+  std::vector<double> uu(u, u + 3 * (size_t)s->nV), f(3 * (size_t)s->nV), f1(3 * (size_t)s->nV);
+  CorotationalLinearFEMMT *mt = new CorotationalLinearFEMMT(s->mesh, threads);
+  SparseMatrix *K;
+  mt->GetStiffnessMatrixTopology(&K);
+  double best = 1e300;
+  for (int i = 0; i < reps; i++) {
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    mt->ComputeForceAndStiffnessMatrix(&uu[0], &f[0], K, 1);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    double dt = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    if (dt < best) best = dt;
+  }
+  if (maxForceDiff) {
+    s->fem->ComputeForceAndStiffnessMatrix(&uu[0], &f1[0], NULL, 1);
+    double m = 0;
+    for (size_t i = 0; i < f.size(); i++) { double d = f[i] - f1[i]; if (d < 0) d = -d; if (d > m) m = d; }
+    *maxForceDiff = m;
+  }
+  delete K;
+  delete mt;
+  return best;
 }
 
 void fbref_set_state(void *p, const double *q, const double *qvel) {

@@ -202,7 +202,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": 0,
         "steps_requested": args.steps, "warmup_requested": args.warmup,
-        "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and not args.replicas else "weak",
+        "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak" if (args.gpus > 1 and args.replicas) else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(nx, nT, 1, False),
         "cpu_baseline": {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": res["kind"], "sample": sample},
         "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -55,6 +55,29 @@ class FemBrainError(RuntimeError):
 _lib = None
 
 
+def _preload_bundled_nccl():
+    """The library's NEEDED libnccl.so.2 resolves to whichever copy the process maps first.  PyTorch ships its own (newer) NCCL
+    and fails to import (`undefined symbol: ncclDevCommCreate`) when an older system copy is already mapped — which is what
+    happens if this module is imported BEFORE torch.  Mapping the wheel's copy first makes the order irrelevant; without the
+    wheel the system library is used as linked."""
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    if spec is None or not spec.submodule_search_locations:
+        return
+    for root in spec.submodule_search_locations:
+        cand = os.path.join(root, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load_library():
     """Load libfembrain_b200.so; raise loudly if it has not been built (no fallback of any kind)."""
     global _lib
@@ -65,6 +88,7 @@ def load_library():
             f"{LIB_PATH} is missing: build it with `python -m fembrain_b200.build` (nvcc, sm_100a). "
             "fembrain_b200 has no CPU or PyTorch fallback."
         )
+    _preload_bundled_nccl()
     lib = C.CDLL(LIB_PATH)
     vp, ci, cd, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
     pp = C.POINTER(vp)

@@ -103,3 +103,14 @@ def test_batch_entry_points_validate_before_touching_the_device():
     assert lib.fb_batch_count(None) == 0
     assert lib.fb_batch_offsets(None, None, None) == api.FB_ERR_INVALID_ARGUMENT
     assert lib.fb_batch_last_cg_iterations(None, None, None) == api.FB_ERR_INVALID_ARGUMENT
+
+
+def test_loading_the_library_before_torch_does_not_break_torch():
+    """Both link libnccl.so.2; the first copy mapped wins.  api.load_library maps the PyTorch wheel's copy first, so a process
+    that touches fembrain_b200 before `import torch` (tests/test_fullsize_gpu.py run alone did) still imports torch."""
+    import subprocess
+    import sys
+
+    code = "import fembrain_b200.api as a; a.load_library(); import torch; print('ok', torch.__version__)"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stderr[-800:]

@@ -99,6 +99,7 @@ struct FbMg {
   int nu;                    // smoothing sweeps before and after the coarse correction
   int cheb;                  // nu >= 2: the sweeps are a Chebyshev iteration on [hi lambda_max / alpha, hi lambda_max] instead of nu damped steps
   float chebAlpha, chebHi;
+  float coarseScale;         // the prolongated correction is added times this factor (1: plain; the cycle stays symmetric for any > 0)
   int useEll;                // structured slot-major storage + k_mg_spmv_ell on tensor-grid levels (FP16 storage only)
   int ellMinV;               // ... on levels with at least this many vertices (a row per thread needs that many rows to fill the GPU)
   signed char *slotOfDev;    // device copies of every level's slotOf table, 27 bytes per level
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(MG_TB) k_mg_restrict(GridMaps g, const float *
 
 // x_f += P x_c : one thread per fine VERTEX, trilinear weights, float4 loads; constrained fine DOFs stay untouched (zero)
 __global__ void __launch_bounds__(MG_TB) k_mg_prolong_add(GridMaps g, const float *__restrict__ xc, const unsigned char *__restrict__ maskF,
-                                                          float *__restrict__ xf, const FbScalars *sc) {
+                                                          float *__restrict__ xf, float scale, const FbScalars *sc) {
   if (sc && sc->done) return;
   const size_t nF = (size_t)g.nf[0] * g.nf[1] * g.nf[2];
   const float4 *xc4 = reinterpret_cast<const float4 *>(xc);
@@ -594,9 +595,9 @@ __global__ void __launch_bounds__(MG_TB) k_mg_prolong_add(GridMaps g, const floa
       }
     }
     float4 x = xf4[v];
-    if (!maskF[3 * v]) x.x += sx;
-    if (!maskF[3 * v + 1]) x.y += sy;
-    if (!maskF[3 * v + 2]) x.z += sz;
+    if (!maskF[3 * v]) x.x = fmaf(scale, sx, x.x);
+    if (!maskF[3 * v + 1]) x.y = fmaf(scale, sy, x.y);
+    if (!maskF[3 * v + 2]) x.z = fmaf(scale, sz, x.z);
     xf4[v] = x;
   }
 }
@@ -1087,7 +1088,7 @@ float *vcycle(fb_context *c, FbMg *mg, int li) {
   if (li == 0 && mg->useGraph && !mg->capturing) coarse = subcycle_graph(c, mg);   // levels >= 1 as ONE graph launch (~30 small kernels)
   if (!coarse) coarse = vcycle(c, mg, li + 1);
   if (li == 0) tm_mark(st, "levels >= 1");
-  k_mg_prolong_add<<<L.grid_vec, MG_TB, 0, st>>>(g, coarse, lc->rowmask, cur, sc);
+  k_mg_prolong_add<<<L.grid_vec, MG_TB, 0, st>>>(g, coarse, lc->rowmask, cur, mg->coarseScale, sc);
   c->launches++;
   if (li == 0) tm_mark(st, "prolong (level 1 -> 0)");
   for (int s = 0; s < nu; s++) {   // the same sweeps after the correction: the cycle stays symmetric
@@ -1147,6 +1148,8 @@ static int mg_ensure(fb_context *c) {
   mg->chebAlpha = getenv("FEMBRAIN_B200_MG_CHEB_ALPHA") ? (float)atof(getenv("FEMBRAIN_B200_MG_CHEB_ALPHA")) : 20.f;
   mg->chebHi = getenv("FEMBRAIN_B200_MG_CHEB_HI") ? (float)atof(getenv("FEMBRAIN_B200_MG_CHEB_HI")) : 1.1f;
   if (!(mg->chebAlpha > 1.f)) mg->chebAlpha = 20.f;
+  mg->coarseScale = getenv("FEMBRAIN_B200_MG_CSCALE") ? (float)atof(getenv("FEMBRAIN_B200_MG_CSCALE")) : 1.f;
+  if (!(mg->coarseScale > 0.f)) mg->coarseScale = 1.f;
   if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = std::min(8, atoi(getenv("FEMBRAIN_B200_MG_NU")));
   FB_TRY(fb_dev_alloc(c, &mg->slotsM, 2 * (size_t)MG_SLOTS));
   FB_TRY(fb_dev_alloc(c, &mg->slotOfDev, 27 * (size_t)MG_MAX_LEVELS));

@@ -15,10 +15,12 @@
 //                      local index i) triple; the four 3x3 blocks (i, j=0..3) of that element land in the vertex's
 //                      block row.  The CTA's index lists are one precomputed blob (GaLists) copied to shared memory,
 //                      then all element / vertex records it names follow as 16-byte asynchronous copies: two
-//                      dependent memory round trips per CTA.  Four adjacent lanes take the four j of one incidence:
-//                      each recomputes its K0 block from the 4x3 of MInverse, rotates it (R K0, R K0 R^T) and forms
-//                      its nine force terms; the running f_el of the reference (j = 0..3 in order, 12 sequential
-//                      adds per component) is summed by one lane per component from shared memory.  The blocks
+//                      dependent memory round trips per CTA.  ONE THREAD PER INCIDENCE takes its record into registers
+//                      and walks j = 0..3: recomputes the K0 block from the 4x3 of MInverse, rotates it (R K0, R K0 R^T)
+//                      and adds its nine force terms to the running f_el in the reference's order (j outer, 12
+//                      sequential adds per component).  (Round 1 used four lanes per incidence exchanging the force
+//                      terms through the record behind __syncwarp: ~3x the shared-memory traffic, 5 % slower at 10M tets;
+//                      still selectable with FEMBRAIN_B200_GA_QUAD=1 for timing.)  The blocks
 //                      overwrite the incidence's record in shared memory; then one thread per (block, row of 3
 //                      scalars) of the CTA's rows adds its contribution list IN ASCENDING ELEMENT ORDER — the order
 //                      in which the reference's element loop calls AddEntry — and applies the DoTimestep epilogue.
@@ -48,9 +50,10 @@ namespace {
 constexpr int EREC = 24;  // doubles per element record: R[9], G[12], volume, lambda, mu
 
 // CAP incidences (4 CAP slots) and at most BCAP blocks per CTA, TB threads: 4 CAP / TB compute passes
-template <int CAP_, int TB_, int BCAP_, int MINB_>
+template <int CAP_, int TB_, int BCAP_, int MINB_, bool PERINC_ = false>
 struct GaCfg {
   static constexpr int CAP = CAP_, TB = TB_, BCAP = BCAP_, MINB = MINB_;
+  static constexpr bool PERINC = PERINC_;   // compute phase: one thread per incidence (its four blocks in turn) instead of four lanes
   static_assert((4 * CAP_) % TB_ == 0, "whole passes");
   static_assert(BCAP_ <= 4096 && 4 * CAP_ <= 65535 && CAP_ % 8 == 0 && BCAP_ % 8 == 0, "16-bit list entries, 16-byte sections");
 };
@@ -310,60 +313,101 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
   cp_async_wait_all();
   __syncthreads();
 
-  // ---- compute: one slot per thread and pass, operands from shared memory ---------------------------------------
-#pragma unroll 1
-  for (int ps = 0; ps < PASSES; ps++) {
-    if (ps * TB >= nSlots) break;
-    const int slot = ps * TB + tid;
-    const bool active = slot < nSlots;
-    const int sl = active ? slot : (nSlots - 1);  // idle lanes of the last pass repeat the last slot
-    const int li = sl >> 2, j = sl & 3;
-    const int sb = S.L.sbl[sl];
-    const int i = sb >> 12;
-    double *ir = S.vals + li * 36;
-    const double *xj = S.xb + 6 * (sb & 4095);
-    double R[9], gi[3], gj[3], X0j[3], Pj[3];
+  if constexpr (C::PERINC) {
+    // ---- compute, one thread per INCIDENCE: R, the 4x3 of MInverse and the material in registers, the four blocks (i, j = 0..3)
+    // in turn, the element force row accumulated in registers in the reference's (j, l) order.  Against the four-lanes version:
+    // ~13 instead of ~36 shared-memory reads and 9 instead of 18 writes per block, no __syncwarp (nobody else touches this
+    // incidence's 36 doubles).  Block j overwrites doubles 9j .. 9j+8 of the record — everything it covers is in registers.
+    const int nInc = nSlots >> 2;
+    for (int li = tid; li < nInc; li += TB) {
+      double *ir = S.vals + li * 36;
+      double R[9], G[12];
 #pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = ir[k];
+      for (int k = 0; k < 9; k++) R[k] = ir[k];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      gi[k] = ir[9 + 3 * i + k];
-      gj[k] = ir[9 + 3 * j + k];
-      X0j[k] = xj[k];
-      Pj[k] = X0j[k] + xj[3 + k];
-    }
-    const double vol = ir[21], lambda = ir[22], mu = ir[23];
-    double eb[9], K[9], RK[9], Kel[9];
-    fbm::eb_products(gj, lambda, mu, eb);
-    fbm::k0_block(gi, eb, vol, K);
-    fbm::warp_block(R, K, RK, Kel);
-    // fElement[3i+k] += Kel[k][l] P_j[l] - RK[k][l] x0_j[l], j = 0..3 outer, l inner, starting from 0
-    // (corotationalLinearFEM.cpp:275-286): every lane leaves its nine terms in the incidence's 36 doubles (the record
-    // has been read by all four lanes), lane k < 3 of the quad then adds the twelve terms of component k in the
-    // reference's order; finally the four blocks take the place of the terms
-    double d[9];
+      for (int k = 0; k < 12; k++) G[k] = ir[9 + k];
+      const double vol = ir[21], lambda = ir[22], mu = ir[23];
+      const int i = S.L.sbl[4 * li] >> 12;
+      double gi[3];
+      gi[0] = i == 0 ? G[0] : (i == 1 ? G[3] : (i == 2 ? G[6] : G[9]));
+      gi[1] = i == 0 ? G[1] : (i == 1 ? G[4] : (i == 2 ? G[7] : G[10]));
+      gi[2] = i == 0 ? G[2] : (i == 1 ? G[5] : (i == 2 ? G[8] : G[11]));
+      double facc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int k = 0; k < 3; k++)
+      for (int j = 0; j < 4; j++) {
+        const double *xj = S.xb + 6 * (S.L.sbl[4 * li + j] & 4095);
+        double X0j[3], Pj[3];
 #pragma unroll
-      for (int l = 0; l < 3; l++) d[3 * k + l] = Kel[3 * k + l] * Pj[l] - RK[3 * k + l] * X0j[l];
-    __syncwarp();
-    if (active) {
+        for (int k = 0; k < 3; k++) {
+          X0j[k] = xj[k];
+          Pj[k] = X0j[k] + xj[3 + k];
+        }
+        double eb[9], K[9], RK[9], Kel[9];
+        fbm::eb_products(&G[3 * j], lambda, mu, eb);
+        fbm::k0_block(gi, eb, vol, K);
+        fbm::warp_block(R, K, RK, Kel);
+        fbm::force_accumulate(Kel, RK, Pj, X0j, facc);   // fElement[3i+k], j outer, l inner, from 0 (corotationalLinearFEM.cpp:275-286)
 #pragma unroll
-      for (int q = 0; q < 9; q++) ir[9 * j + q] = d[q];
-    }
-    __syncwarp();
-    if (active && j < 3) {
-      double f = 0.0;
-#pragma unroll
-      for (int jj = 0; jj < 4; jj++) {
-        f += ir[9 * jj + 3 * j + 0]; f += ir[9 * jj + 3 * j + 1]; f += ir[9 * jj + 3 * j + 2];
+        for (int q = 0; q < 9; q++) ir[9 * j + q] = Kel[q];
       }
-      S.fel[li * 3 + j] = f;
+      S.fel[li * 3 + 0] = facc[0]; S.fel[li * 3 + 1] = facc[1]; S.fel[li * 3 + 2] = facc[2];
     }
-    __syncwarp();
-    if (active) {
-#pragma unroll
-      for (int q = 0; q < 9; q++) ir[9 * j + q] = Kel[q];
+  } else {
+  // ---- compute: one slot per thread and pass, operands from shared memory ---------------------------------------
+  #pragma unroll 1
+    for (int ps = 0; ps < PASSES; ps++) {
+      if (ps * TB >= nSlots) break;
+      const int slot = ps * TB + tid;
+      const bool active = slot < nSlots;
+      const int sl = active ? slot : (nSlots - 1);  // idle lanes of the last pass repeat the last slot
+      const int li = sl >> 2, j = sl & 3;
+      const int sb = S.L.sbl[sl];
+      const int i = sb >> 12;
+      double *ir = S.vals + li * 36;
+      const double *xj = S.xb + 6 * (sb & 4095);
+      double R[9], gi[3], gj[3], X0j[3], Pj[3];
+  #pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = ir[k];
+  #pragma unroll
+      for (int k = 0; k < 3; k++) {
+        gi[k] = ir[9 + 3 * i + k];
+        gj[k] = ir[9 + 3 * j + k];
+        X0j[k] = xj[k];
+        Pj[k] = X0j[k] + xj[3 + k];
+      }
+      const double vol = ir[21], lambda = ir[22], mu = ir[23];
+      double eb[9], K[9], RK[9], Kel[9];
+      fbm::eb_products(gj, lambda, mu, eb);
+      fbm::k0_block(gi, eb, vol, K);
+      fbm::warp_block(R, K, RK, Kel);
+      // fElement[3i+k] += Kel[k][l] P_j[l] - RK[k][l] x0_j[l], j = 0..3 outer, l inner, starting from 0
+      // (corotationalLinearFEM.cpp:275-286): every lane leaves its nine terms in the incidence's 36 doubles (the record
+      // has been read by all four lanes), lane k < 3 of the quad then adds the twelve terms of component k in the
+      // reference's order; finally the four blocks take the place of the terms
+      double d[9];
+  #pragma unroll
+      for (int k = 0; k < 3; k++)
+  #pragma unroll
+        for (int l = 0; l < 3; l++) d[3 * k + l] = Kel[3 * k + l] * Pj[l] - RK[3 * k + l] * X0j[l];
+      __syncwarp();
+      if (active) {
+  #pragma unroll
+        for (int q = 0; q < 9; q++) ir[9 * j + q] = d[q];
+      }
+      __syncwarp();
+      if (active && j < 3) {
+        double f = 0.0;
+  #pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          f += ir[9 * jj + 3 * j + 0]; f += ir[9 * jj + 3 * j + 1]; f += ir[9 * jj + 3 * j + 2];
+        }
+        S.fel[li * 3 + j] = f;
+      }
+      __syncwarp();
+      if (active) {
+  #pragma unroll
+        for (int q = 0; q < 9; q++) ir[9 * j + q] = Kel[q];
+      }
     }
   }
   __syncthreads();
@@ -452,9 +496,10 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
   }
 }
 
-typedef GaCfg<256, 512, 256, 1> CfgBig;
-typedef GaCfg<192, 256, 192, 2> CfgMid;
-typedef GaCfg<128, 256, 128, 4> CfgSmall;  // 64 registers, 51 KB: 4 CTAs/SM
+typedef GaCfg<256, 256, 256, 1, true> CfgBig;
+typedef GaCfg<192, 192, 192, 2, true> CfgMid;
+typedef GaCfg<128, 256, 128, 4> CfgSmall;  // four lanes per incidence (round 1), kept for A/B timing: 64 registers, 54 KB, 4 CTAs/SM
+typedef GaCfg<128, 128, 128, 4, true> CfgSmallInc;  // same lists, one thread per incidence, up to 128 registers
 
 template <class C>
 cudaError_t prepare_gather(size_t *smem, size_t *listBytes) {
@@ -556,7 +601,11 @@ int fb_build_gather_plan(fb_context *c) {
   cudaError_t attr;
   if (need > CfgMid::CAP) { c->ga_cfg = 2; CAP = CfgBig::CAP; BCAP = CfgBig::BCAP; attr = prepare_gather<CfgBig>(&smem, &listBytes); }
   else if (need > CfgSmall::CAP) { c->ga_cfg = 1; CAP = CfgMid::CAP; BCAP = CfgMid::BCAP; attr = prepare_gather<CfgMid>(&smem, &listBytes); }
-  else { c->ga_cfg = 0; CAP = CfgSmall::CAP; BCAP = CfgSmall::BCAP; attr = prepare_gather<CfgSmall>(&smem, &listBytes); }
+  else {
+    c->ga_cfg = 0; CAP = CfgSmall::CAP; BCAP = CfgSmall::BCAP;
+    attr = prepare_gather<CfgSmall>(&smem, &listBytes);
+    if (attr == cudaSuccess) attr = prepare_gather<CfgSmallInc>(&smem, &listBytes);
+  }
   if (attr != cudaSuccess) {
     fb_set_error("cudaFuncSetAttribute(smem %zu) -> %s", smem, cudaGetErrorString(attr));
     cleanup();
@@ -615,6 +664,11 @@ int fb_build_gather_plan(fb_context *c) {
   return FB_OK;
 }
 
+static bool ga_quad() {   // FEMBRAIN_B200_GA_QUAD=1: the four-lanes-per-incidence compute phase (A/B timing)
+  static const bool v = getenv("FEMBRAIN_B200_GA_QUAD") != nullptr;
+  return v;
+}
+
 int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool effective, bool rhs) {
   k_rotation<<<grid_for((size_t)c->nT, 128), 128, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance, c->ga_erec);
   k_pack_xu<<<grid_for((size_t)c->r, 256), 256, 0, c->stream>>>(c->nV, c->x0, u, c->ga_xu);
@@ -629,7 +683,8 @@ int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool
   p.Kraw = Kraw; p.Keff = c->Keff; p.invD = c->invD; p.f = c->fint;
   if (c->ga_cfg == 2) launch_gather<CfgBig>(c, p);
   else if (c->ga_cfg == 1) launch_gather<CfgMid>(c, p);
-  else launch_gather<CfgSmall>(c, p);
+  else if (ga_quad()) launch_gather<CfgSmall>(c, p);
+  else launch_gather<CfgSmallInc>(c, p);
   c->launches += 3;
   FB_CUDA(cudaGetLastError());
   return FB_OK;

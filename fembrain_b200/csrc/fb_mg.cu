@@ -99,6 +99,7 @@ struct FbMg {
   int nu;                    // smoothing sweeps before and after the coarse correction
   int cheb;                  // nu >= 2: the sweeps are a Chebyshev iteration on [hi lambda_max / alpha, hi lambda_max] instead of nu damped steps
   float chebAlpha, chebHi;
+  int fallbacks;             // solves repeated after a lambda_max re-estimate (see fb_mg_pcg_solve)
   float coarseScale;         // the prolongated correction is added times this factor (1: plain; the cycle stays symmetric for any > 0)
   int useEll;                // structured slot-major storage + k_mg_spmv_ell on tensor-grid levels (FP16 storage only)
   int ellMinV;               // ... on levels with at least this many vertices (a row per thread needs that many rows to fill the GPU)
@@ -1358,7 +1359,7 @@ int fb_mg_active(const fb_context *c) { return (c->mg && c->mg->variant != FB_SO
 int fb_mg_warm(const fb_context *c) { return c->mg ? c->mg->warm : 0; }
 
 // PCG with the variant's preconditioner on Keff x = rhs (masked).  Same contract as fb_pcg_solve.
-int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
+static int mg_pcg_solve_once(fb_context *c, double eps, int maxIt) {
   FbMg *mg = c->mg;
   cudaStream_t st = c->stream;
   if (c->r == 0) { c->last_iters = 0; c->last_ratio = 0.0; return FB_OK; }
@@ -1448,6 +1449,28 @@ int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
   c->last_ratio = (s.rho0 != 0.0) ? s.rq / s.rho0 : 0.0;
   mg->solves++;
   c->have_solution = !notConverged;
+  return FB_OK;
+}
+
+// The multigrid cycle with Chebyshev smoothing is only a valid (positive definite) preconditioner while the smoothing interval
+// covers the spectrum of Binv A: if lambda_max has grown past 1.1 x the running power-iteration estimate (the matrix changes
+// every step), CG stalls or diverges.  The healthy solver needs < 100 iterations on every mesh tried, so the first attempt is
+// capped at 300; on failure lambda_max is re-estimated on every level (30 more iterations), the interval's safety factor is
+// raised to >= 1.3 for the rest of the context's life, and the solve is repeated from x0 = 0 with the caller's limit.
+int fb_mg_pcg_solve(fb_context *c, double eps, int maxIt) {
+  FbMg *mg = c->mg;
+  const bool guarded = mg->variant == FB_SOLVER_MG_PCG && mg->cheb && mg->nu >= 2 && maxIt > 300;
+  FB_TRY(mg_pcg_solve_once(c, eps, guarded ? 300 : maxIt));
+  if (!guarded || c->last_iters >= 0 || mg->nLevels < 2) return FB_OK;
+  const int spent = -c->last_iters;
+  for (int li = 0; li + 1 < mg->nLevels; li++) FB_TRY(estimate_lmax(c, mg, mg->L[li], 30));
+  if (mg->chebHi < 1.3f) mg->chebHi = 1.3f;
+  drop_subcycle_graph(mg);
+  mg->fallbacks++;
+  c->have_solution = 0;
+  if (getenv("FEMBRAIN_B200_MG_TRACE")) fprintf(stderr, "[mg] no convergence in %d iterations: lambda_max re-estimated (%.4f on level 0), interval factor %.2f, retrying\n", spent, mg->L[0].lmax, mg->chebHi);
+  FB_TRY(mg_pcg_solve_once(c, eps, maxIt));
+  if (c->last_iters > 0) c->last_iters += spent;   // the iterations the caller paid for
   return FB_OK;
 }
 

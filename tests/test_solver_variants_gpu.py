@@ -114,3 +114,18 @@ def test_variant_error_paths():
         b.set_solver("block_jacobi")
     assert e.value.status == api.FB_ERR_NOT_SUPPORTED
     assert sim.solver()["variant"] == 0
+
+
+def test_mg_recovers_from_a_lost_smoothing_interval(monkeypatch):
+    """Chebyshev smoothing is a valid preconditioner only while its interval covers the spectrum of Binv A.  With the interval
+    deliberately cut to half of lambda_max the first attempt cannot converge; fb_mg_pcg_solve must notice within its 300-iteration
+    cap, re-estimate lambda_max, widen the interval and deliver the same solution as the reference's solver."""
+    monkeypatch.setenv("FEMBRAIN_B200_MG_CHEB_HI", "0.5")
+    v, t, fixed, ref, var = _sims((10, 10, 10), "mg")
+    ref.do_timestep()
+    var.do_timestep()
+    assert var.last_cg_iterations > 300, var.last_cg_iterations          # 300 spent + the repeated solve
+    assert var.last_cg_iterations < 300 + ref.last_cg_iterations
+    assert cases.rel_err(var.get_state()[0], ref.get_state()[0]) <= 1e-3
+    var.do_timestep(); ref.do_timestep()
+    assert 0 < var.last_cg_iterations < 100                              # the widened interval stays

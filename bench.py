@@ -549,6 +549,63 @@ def batch_block(env, per_gpu, steps, warmup, nx=33):
                          "frac": b_s / m_s / 1e9 / peak if m_s > 0 else None, "samples": n_s, "traffic": ncu_table(f"batch{per_gpu}x{nx}", "spmv_bytes_per_launch")}}
 
 
+def batch_variant_block(env, per_gpu, steps, warmup, nx=33, threads=8):
+    """configs[3] with the labelled multigrid variant: the same `per_gpu` independent meshes per GPU, each its own context with
+    FB_SOLVER_MG_PCG on its own stream (the batch context keeps the reference's solver), stepped by a pool of host threads so that
+    the latency-bound cycles of different meshes overlap on the GPU.  Wall clock between two device synchronisations (the work
+    runs on `per_gpu` streams), max over ranks."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    torch, fb = env.torch, env.fb
+    v, t, fixed, _ = workload(nx)
+    nT, r = len(t), 3 * len(v)
+    total = per_gpu * env.world
+    corner = 3 * (len(v) - 1)
+    sims = []
+    t0 = time.perf_counter()
+    for k in range(per_gpu):
+        m = env.rank * per_gpu + k
+        ang = 2.0 * np.pi * m / max(total, 1)
+        f = np.zeros(r)
+        f[corner], f[corner + 2] = 1e4 * np.cos(ang), 1e4 * np.sin(ang)
+        sim = fb.Simulation(v, t, fixed, device=env.local)
+        sim.set_grid(nx)
+        sim.set_solver("mg")
+        sim.set_external_forces(f)
+        sims.append(sim)
+    t_setup = time.perf_counter() - t0
+    threads = max(1, min(threads, per_gpu))
+    groups = [sims[i::threads] for i in range(threads)]
+
+    def run_group(g, n):
+        for _ in range(n):
+            for sim in g:
+                sim.do_timestep()
+
+    def region(n):
+        env.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda g: run_group(g, n), groups))
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        env.barrier()
+        return env.max_over_ranks(sec)[0]
+
+    region(warmup)
+    sec = region(steps)
+    its = [int(s.last_cg_iterations) for s in sims[:4]]
+    name = sims[0].solver()["name"]
+    for sim in sims:
+        sim.close()
+    if env.rank != 0:
+        return None
+    return {"solver": name, "value": total * steps / sec, "unit": "mesh-steps/s", "steps": steps, "warmup": warmup, "host_threads_per_gpu": threads,
+            "contexts_per_gpu": per_gpu, "ms_per_batch_step": 1e3 * sec / steps, "cg_iterations_last_step_first_meshes": its,
+            "setup_seconds": t_setup, "timing": "wall clock between device synchronisations (one stream per mesh), max over ranks"}
+
+
 def variant_block(env, nx, steps, warmup, parity_iters, parity_ms, q_parity_end):
     """The labelled solver variant on the headline mesh (single GPU): FB_SOLVER_MG_PCG — the same Keff and rhs, the same
     stopping rule, a multigrid-preconditioned CG instead of the reference's Jacobi-PCG (fembrain_b200/csrc/fb_mg.cu).  Same
@@ -710,6 +767,13 @@ def run_ours(args):
     # ---- configs[3]: batch of independent meshes, 32 per GPU -------------------------------------------------------------
     if not args.no_batch:
         guarded("config4_batch", lambda: batch_block(env, args.batch_per_gpu, args.steps_batch, args.warmup_batch))
+        if not args.no_variant:
+            def batch_var():
+                out = batch_variant_block(env, args.batch_per_gpu, args.steps_batch, args.warmup_batch)
+                if rank == 0 and isinstance(line.get("config4_batch"), dict):
+                    line["config4_batch"]["solver_variant"] = out
+                return None
+            guarded("config4_batch_variant", batch_var)
 
     # ---- configs[1] and the CPU baseline, single GPU only ------------------------------------------------------------------
     if world == 1 and not args.no_1m and nx != 56:

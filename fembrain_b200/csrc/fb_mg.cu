@@ -8,18 +8,22 @@
 // sum r_i^2 / diag_i <= eps^2 * sum b_i^2 / diag_i of CGSolver.cpp:147-150 — with a better preconditioner:
 //
 //   FB_SOLVER_BLOCK_JACOBI_PCG  z = B^-1 r with B the 3x3 diagonal blocks of Keff (any mesh)
-//   FB_SOLVER_MG_PCG            z = one multigrid V(1,1) cycle (meshes whose vertices form a tensor grid, fb_set_grid):
+//   FB_SOLVER_MG_PCG            z = one multigrid V(3,3) cycle (meshes whose vertices form a tensor grid, fb_set_grid):
 //       levels     the grid coarsened 2:1 per axis (every other node plane, plus the last one) down to <= 3 nodes per axis;
 //       operators  every coarse level is an ordinary context of the coarse TruthCube-split mesh (VolMeshSamples.cpp:76-116
 //                  pattern on the coarse node coordinates) whose Keff is RE-ASSEMBLED every step by the same assembly kernels
 //                  at the injected displacement (corotational rotations included) — no sparse triple products;
 //       transfer   trilinear interpolation P (3x3 identity blocks) and restriction P^T, constrained DOFs masked on both sides;
-//       smoother   damped 3x3-block Jacobi, omega = 1.4 / lambda_max(B^-1 A) (power iteration, refreshed every 32 solves);
-//       coarsest   explicit dense inverse (<= 81 unknowns), rebuilt every step;
+//       smoother   three sweeps of a Chebyshev iteration preconditioned by the 3x3 block diagonal B, on the interval
+//                  [1.1 lambda_max / 20, 1.1 lambda_max] of B^-1 A (lambda_max by power iteration: 30 iterations at build, 3 more
+//                  every 32 solves; damped block Jacobi with FEMBRAIN_B200_MG_SMOOTHER=jacobi);
+//       coarsest   explicit dense inverse (<= 81 unknowns), rebuilt every step in shared memory;
 //       precision  the whole cycle runs in FP32 arithmetic on a reduced-precision copy of each level's Keff: FP16 values
 //                  (default; scaled by a power of two per level so that the largest diagonal entry sits near 2^13) or FP32
 //                  (FEMBRAIN_B200_MG_PREC=fp32), 3x3 blocks padded to 3x4 so that one lane loads one block with three
-//                  8-byte (16-byte) loads and one float4 of x — 28 (52) instead of 76 bytes per block streamed;
+//                  8-byte (16-byte) loads and one float4 of x — 28 (52) instead of 76 bytes per block streamed; tensor-grid
+//                  levels of >= 400,000 vertices store the FP16 blocks slot-major instead (k_mg_spmv_ell: one thread per row,
+//                  24 coalesced bytes per block, x staged in shared memory: 0.87 of the HBM copy peak);
 //                  the outer CG — A d, the dot products, x, r, d — stays FP64 on the FP64 Keff.
 //   The cycle is a fixed symmetric positive definite linear operator (same pre/post smoother, R = P^T), so plain PCG applies.
 //   Iteration counts are mesh independent (CPU prototype on the reference's matrices: 34 at 16^3, 24^3 and 32^3 nodes
@@ -92,7 +96,6 @@ struct FbMg {
   int grid[3];               // tensor-grid dimensions given with fb_set_grid (0 = none)
   int nLevels;
   MgLevel L[MG_MAX_LEVELS];
-  double *dense;             // (unused: the coarsest-level matrix is inverted in shared memory)
   float *denseInv;           // [n*n] fp32 copy of the inverse
   int nDense;
   double *slotsM, *slotsZ;   // per-CTA partial sums: weighted residual, r.z
@@ -1124,7 +1127,6 @@ void fb_mg_release(fb_context *c) {
   if (!mg) return;
   drop_subcycle_graph(mg);
   for (int li = mg->nLevels - 1; li >= 0; li--) free_level(c, mg->L[li], li);
-  if (mg->dense) fb_dev_free(mg->dense);
   if (mg->denseInv) fb_dev_free(mg->denseInv);
   if (mg->slotsM) fb_dev_free(mg->slotsM);
   if (mg->slotOfDev) fb_dev_free(mg->slotOfDev);
@@ -1165,7 +1167,6 @@ static int mg_build(fb_context *c) {
   for (int li = mg->nLevels - 1; li >= 0; li--) free_level(c, mg->L[li], li);
   mg->nLevels = 0;
   mg->prepared = 0;
-  if (mg->dense) { fb_dev_free(mg->dense); mg->dense = nullptr; }
   if (mg->denseInv) { fb_dev_free(mg->denseInv); mg->denseInv = nullptr; }
   if (mg->variant == FB_SOLVER_JACOBI_PCG) return FB_OK;
   MgLevel &L0 = mg->L[0];

@@ -19,7 +19,7 @@
 //                      and walks j = 0..3: recomputes the K0 block from the 4x3 of MInverse, rotates it (R K0, R K0 R^T)
 //                      and adds its nine force terms to the running f_el in the reference's order (j outer, 12
 //                      sequential adds per component).  (Round 1 used four lanes per incidence exchanging the force
-//                      terms through the record behind __syncwarp: ~3x the shared-memory traffic, 5 % slower at 10M tets;
+//                      terms through the record behind __syncwarp: ~3x the shared-memory traffic, 12 % slower at 10M tets;
 //                      still selectable with FEMBRAIN_B200_GA_QUAD=1 for timing.)  The blocks
 //                      overwrite the incidence's record in shared memory; then one thread per (block, row of 3
 //                      scalars) of the CTA's rows adds its contribution list IN ASCENDING ELEMENT ORDER — the order
@@ -48,6 +48,11 @@
 namespace {
 
 constexpr int EREC = 24;  // doubles per element record: R[9], G[12], volume, lambda, mu
+// Doubles between two incidences' 36-double areas in shared memory.  One thread per incidence reads its own area, so the lanes
+// of a warp are VSTRIDE doubles apart: with 36 (72 words) only four bank groups are hit — an 8-way conflict on every access (ncu:
+// 49.6M shared bank conflicts at 1M tets); 37 (74 words, = 2 mod 4) spreads a half-warp's 8-byte accesses over all 32 banks.  The
+// areas are then only 8-byte aligned: the records are staged with 8-byte cp.async.
+constexpr int VSTRIDE = 37;
 
 // CAP incidences (4 CAP slots) and at most BCAP blocks per CTA, TB threads: 4 CAP / TB compute passes
 template <int CAP_, int TB_, int BCAP_, int MINB_, bool PERINC_ = false>
@@ -55,7 +60,7 @@ struct GaCfg {
   static constexpr int CAP = CAP_, TB = TB_, BCAP = BCAP_, MINB = MINB_;
   static constexpr bool PERINC = PERINC_;   // compute phase: one thread per incidence (its four blocks in turn) instead of four lanes
   static_assert((4 * CAP_) % TB_ == 0, "whole passes");
-  static_assert(BCAP_ <= 4096 && 4 * CAP_ <= 65535 && CAP_ % 8 == 0 && BCAP_ % 8 == 0, "16-bit list entries, 16-byte sections");
+  static_assert(BCAP_ <= 4096 && 4 * CAP_ <= 65535 && CAP_ * 37 <= 65535 && CAP_ % 8 == 0 && BCAP_ % 8 == 0, "16-bit list entries, 16-byte sections");
 };
 
 // Index lists of one CTA, built once at setup, CTA-relative, copied verbatim into shared memory (16-byte pieces).
@@ -65,7 +70,7 @@ struct GaLists {
   unsigned int inc[CAP];          // element*4 + i of every incidence
   unsigned int bcol[BCAP];        // column vertex of every block
   double mb[BCAP];                // mass scalar of every block (M = mb (x) I3)
-  unsigned short csl[CAP * 4];    // contribution (list order) -> slot
+  unsigned short csl[CAP * 4];    // contribution (list order) -> offset of its slot's block in vals (doubles)
   unsigned short sbl[CAP * 4];    // slot -> block | i << 12
   unsigned short segl[BCAP + 8];  // list start of every block (+ end)
   unsigned short bol[BCAP];       // blocks in order of decreasing list length
@@ -76,14 +81,14 @@ struct GaLists {
 };
 
 // Shared memory of one CTA:
-//   vals [CAP][36]  per incidence: IN the element record (24 doubles)  ->  OUT four 3x3 blocks, slot = 4 li + j at slot*9
+//   vals [CAP][VSTRIDE] per incidence (36 used): IN the element record (24 doubles)  ->  OUT four 3x3 blocks, slot = 4 li + j at slot*9
 //   xb   [BCAP][6]  per block of the CTA's rows: x0 and u of the block's column vertex
 //   qv   [BCAP][3]  ... and its velocity (right-hand side only)
 //                   (between the two, the quad's 4 x 9 force terms pass through the same 36 doubles)
 //   fel  [CAP][3]   element force rows of the incidence
 template <class C>
 struct GatherSmem {
-  double vals[C::CAP * 36];
+  double vals[C::CAP * VSTRIDE];
   double xb[C::BCAP * 6];
   double qv[C::BCAP * 3];
   double fel[C::CAP * 3];
@@ -175,7 +180,7 @@ __global__ void k_lists_block(int nB, const int *__restrict__ brow, const int *_
       if (inc[mid] < want) lo = mid + 1; else hi = mid;
     }
     const int slot = ((base + (lo - lo0)) << 2) | (int)(c & 3u);
-    L.csl[s - segBase] = (unsigned short)slot;
+    L.csl[s - segBase] = (unsigned short)((slot >> 2) * VSTRIDE + (slot & 3) * 9);   // offset of the slot's block in GatherSmem::vals
     L.sbl[slot] = (unsigned short)(bl | (int)(((c >> 2) & 3u) << 12));
   }
   L.segl[bl] = (unsigned short)(s0 - segBase);
@@ -291,10 +296,9 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
     if (slot < nSlots) {
       const unsigned ei = S.L.inc[slot >> 2];
       const double *rec = p.erec + (size_t)(ei >> 2) * EREC + 6 * (slot & 3);  // lane j of the quad copies doubles 6j .. 6j+5
-      double *dst = S.vals + (slot >> 2) * 36 + 6 * (slot & 3);
-      cp_async16(dst, rec);
-      cp_async16(dst + 2, rec + 2);
-      cp_async16(dst + 4, rec + 4);
+      double *dst = S.vals + (slot >> 2) * VSTRIDE + 6 * (slot & 3);
+#pragma unroll
+      for (int q = 0; q < 6; q++) cp_async8(dst + q, rec + q);
     }
   }
   for (int t = tid; t < nBlk; t += TB) {
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
     // incidence's 36 doubles).  Block j overwrites doubles 9j .. 9j+8 of the record — everything it covers is in registers.
     const int nInc = nSlots >> 2;
     for (int li = tid; li < nInc; li += TB) {
-      double *ir = S.vals + li * 36;
+      double *ir = S.vals + li * VSTRIDE;
       double R[9], G[12];
 #pragma unroll
       for (int k = 0; k < 9; k++) R[k] = ir[k];
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
       const int li = sl >> 2, j = sl & 3;
       const int sb = S.L.sbl[sl];
       const int i = sb >> 12;
-      double *ir = S.vals + li * 36;
+      double *ir = S.vals + li * VSTRIDE;
       const double *xj = S.xb + 6 * (sb & 4095);
       double R[9], gi[3], gj[3], X0j[3], Pj[3];
   #pragma unroll
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
       const int s0 = S.L.segl[bl], s1 = S.L.segl[bl + 1];
       double a0 = 0.0, a1 = 0.0, a2 = 0.0;
       for (int s = s0; s < s1; s++) {
-        const double *c = S.vals + (int)S.L.csl[s] * 9 + 3 * k;
+        const double *c = S.vals + (int)S.L.csl[s] + 3 * k;
         a0 += c[0]; a1 += c[1]; a2 += c[2];
       }
       const int rs = S.L.bpl[vl], nb = S.L.bpl[vl + 1] - rs;

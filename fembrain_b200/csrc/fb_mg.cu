@@ -102,6 +102,7 @@ struct FbMg {
   int nu;                    // smoothing sweeps before and after the coarse correction
   int cheb;                  // nu >= 2: the sweeps are a Chebyshev iteration on [hi lambda_max / alpha, hi lambda_max] instead of nu damped steps
   float chebAlpha, chebHi;
+  int nuCoarse;              // sweeps on levels >= 1 (0: the same as nu): they cost launch latency, not bandwidth
   int fallbacks;             // solves repeated after a lambda_max re-estimate (see fb_mg_pcg_solve)
   float coarseScale;         // the prolongated correction is added times this factor (1: plain; the cycle stays symmetric for any > 0)
   int useEll;                // structured slot-major storage + k_mg_spmv_ell on tensor-grid levels (FP16 storage only)
@@ -1065,7 +1066,7 @@ float *vcycle(fb_context *c, FbMg *mg, int li) {
   }
   MgLevel &C = mg->L[li + 1];
   const GridMaps g = maps_of(L);
-  const int nu = mg->nu;
+  const int nu = (li > 0 && mg->nuCoarse > 0) ? mg->nuCoarse : mg->nu;
   // step k of the smoother: x_(k+1) = x_k + w[k] Binv (b - A x_k) + gm[k] (x_k - x_(k-1))
   float w[8], gm[8];
   smoother_coefficients(mg, L.lmax, w, gm);
@@ -1151,6 +1152,7 @@ static int mg_ensure(fb_context *c) {
   mg->chebAlpha = getenv("FEMBRAIN_B200_MG_CHEB_ALPHA") ? (float)atof(getenv("FEMBRAIN_B200_MG_CHEB_ALPHA")) : 20.f;
   mg->chebHi = getenv("FEMBRAIN_B200_MG_CHEB_HI") ? (float)atof(getenv("FEMBRAIN_B200_MG_CHEB_HI")) : 1.1f;
   if (!(mg->chebAlpha > 1.f)) mg->chebAlpha = 20.f;
+  mg->nuCoarse = getenv("FEMBRAIN_B200_MG_NU_COARSE") ? std::max(0, std::min(8, atoi(getenv("FEMBRAIN_B200_MG_NU_COARSE")))) : 4;   // measured: 1 / 2 / 3 / 4 / 6 / 8 sweeps on the coarse levels -> 23-36 / 15-22 / 13-18 / 12-16 / 11-15 / 11-14 iterations at 10M tets; 4 is the fastest step
   mg->coarseScale = getenv("FEMBRAIN_B200_MG_CSCALE") ? (float)atof(getenv("FEMBRAIN_B200_MG_CSCALE")) : 1.f;
   if (!(mg->coarseScale > 0.f)) mg->coarseScale = 1.f;
   if (getenv("FEMBRAIN_B200_MG_NU") && atoi(getenv("FEMBRAIN_B200_MG_NU")) > 0) mg->nu = std::min(8, atoi(getenv("FEMBRAIN_B200_MG_NU")));

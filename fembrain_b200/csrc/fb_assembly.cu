@@ -252,7 +252,7 @@ __global__ void k_pack_xu(int nV, const double *__restrict__ x0, const double *_
 
 struct GatherParams {
   double scale, h, dampK, dampM;
-  int effective, wantRhs;
+  int effective, wantRhs, prefetchAhead;
   const void *lists;
   const double *erec, *xu, *qvel, *fext;
   const unsigned char *fixed;
@@ -280,6 +280,13 @@ __global__ void __launch_bounds__(C::TB, C::MINB) k_assemble_gather(const Gather
   const int tid = threadIdx.x;
 
   // ---- stage 1: the CTA's index lists, verbatim ------------------------------------------------------------------
+  if (C::PERINC) {   // the blob of the CTA that will run here two waves later: into L2 now, so that ITS first round trip is short
+    const unsigned ahead = blockIdx.x + (unsigned)p.prefetchAhead;
+    if (p.prefetchAhead > 0 && ahead < gridDim.x) {
+      const unsigned char *g = reinterpret_cast<const unsigned char *>(reinterpret_cast<const Lists *>(p.lists) + ahead);
+      for (int t = tid; t < (int)(sizeof(Lists) / 128); t += TB) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 128 * t));
+    }
+  }
   {
     const unsigned char *g = reinterpret_cast<const unsigned char *>(reinterpret_cast<const Lists *>(p.lists) + blockIdx.x);
     unsigned char *s = reinterpret_cast<unsigned char *>(&S.L);
@@ -681,6 +688,8 @@ int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool
   p.dampK = c->prm.damping_stiffness; p.dampM = c->prm.damping_mass;
   p.effective = effective ? 1 : 0;
   p.wantRhs = (effective && rhs) ? 1 : 0;
+  static const int ahead = getenv("FEMBRAIN_B200_GA_PREFETCH") ? atoi(getenv("FEMBRAIN_B200_GA_PREFETCH")) : 2 * 4 * 148;
+  p.prefetchAhead = ahead;
   p.lists = c->ga_lists;
   p.erec = c->ga_erec; p.xu = c->ga_xu; p.fixed = c->rowmask;
   p.qvel = c->qvel; p.fext = c->fext; p.qres = c->qres; p.rhs = c->rhs;

@@ -22,7 +22,7 @@
 //                  (default; scaled by a power of two per level so that the largest diagonal entry sits near 2^13) or FP32
 //                  (FEMBRAIN_B200_MG_PREC=fp32), 3x3 blocks padded to 3x4 so that one lane loads one block with three
 //                  8-byte (16-byte) loads and one float4 of x — 28 (52) instead of 76 bytes per block streamed; tensor-grid
-//                  levels of >= 400,000 vertices store the FP16 blocks slot-major instead (k_mg_spmv_ell: one thread per row,
+//                  levels of >= 200,000 vertices store the FP16 blocks slot-major instead (k_mg_spmv_ell: one thread per row,
 //                  24 coalesced bytes per block, x staged in shared memory: 0.87 of the HBM copy peak);
 //                  the outer CG — A d, the dot products, x, r, d — stays FP64 on the FP64 Keff.
 //   The cycle is a fixed symmetric positive definite linear operator (same pre/post smoother, R = P^T), so plain PCG applies.
@@ -1142,10 +1142,12 @@ static int mg_ensure(fb_context *c) {
   memset(mg, 0, sizeof(*mg));
   c->mg = mg;
   mg->half = !(getenv("FEMBRAIN_B200_MG_PREC") && !strcmp(getenv("FEMBRAIN_B200_MG_PREC"), "fp32"));
-  // FEMBRAIN_B200_MG_ELL: unset = levels of >= 400,000 vertices (measured: 5 % faster steps at 1.77M vertices, 10 % slower at
-  // 185k where one thread per row cannot fill 148 SMs); 1 = every tensor-grid level; 0 = none
+  // FEMBRAIN_B200_MG_ELL: unset = levels of >= 200,000 vertices (measured: 5 % faster steps at 1.77M vertices, even at 185k,
+  // slower on small levels where one thread per row cannot fill 148 SMs); 1 = every tensor-grid level; 0 = none;
+  // FEMBRAIN_B200_MG_ELL_MIN = the vertex threshold
   mg->useEll = !(getenv("FEMBRAIN_B200_MG_ELL") && atoi(getenv("FEMBRAIN_B200_MG_ELL")) == 0);
-  mg->ellMinV = getenv("FEMBRAIN_B200_MG_ELL") ? 0 : 400000;
+  mg->ellMinV = getenv("FEMBRAIN_B200_MG_ELL") ? 0 : 200000;   // (227k-vertex level 1 of the 10M-tet cube: -0.5 ms per step; 185k: +0.06)
+  if (getenv("FEMBRAIN_B200_MG_ELL_MIN")) mg->ellMinV = atoi(getenv("FEMBRAIN_B200_MG_ELL_MIN"));
   mg->useGraph = !(getenv("FEMBRAIN_B200_MG_GRAPH") && atoi(getenv("FEMBRAIN_B200_MG_GRAPH")) == 0);
   mg->nu = 3;   // measured at 10M / 1M tets (profiles/r02_mg_smoother_sweep.txt): 13-17 iterations, the fastest step of nu = 1..4
   mg->cheb = !(getenv("FEMBRAIN_B200_MG_SMOOTHER") && !strcmp(getenv("FEMBRAIN_B200_MG_SMOOTHER"), "jacobi"));

@@ -26,7 +26,7 @@ def _sims(dims, variant, warm=False):
 
 
 # ell: FEMBRAIN_B200_MG_ELL read by fb_set_solver — "1" forces the structured slot-major product (k_mg_spmv_ell, by default only
-# on levels of >= 400,000 vertices) on every tensor-grid level, "0" the lane-per-block product everywhere
+# on levels of >= 200,000 vertices) on every tensor-grid level, "0" the lane-per-block product everywhere
 @pytest.mark.parametrize("dims,variant,ell", [((12, 12, 12), "mg", "1"), ((9, 5, 14), "mg", "1"), ((16, 16, 16), "mg", "0"), ((6, 6, 6), "mg", "1"),
                                               ((3, 3, 3), "mg", "1"), ((9, 5, 14), "mg", "0"), ((12, 12, 12), "block_jacobi", None)])
 def test_variant_solves_the_reference_system_to_the_oracle_solution(port_oracle, dims, variant, ell, monkeypatch):

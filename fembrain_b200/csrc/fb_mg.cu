@@ -16,7 +16,7 @@
 //       transfer   trilinear interpolation P (3x3 identity blocks) and restriction P^T, constrained DOFs masked on both sides;
 //       smoother   three sweeps of a Chebyshev iteration preconditioned by the 3x3 block diagonal B, on the interval
 //                  [1.1 lambda_max / 20, 1.1 lambda_max] of B^-1 A (lambda_max by power iteration: 30 iterations at build, 3 more
-//                  every 32 solves; damped block Jacobi with FEMBRAIN_B200_MG_SMOOTHER=jacobi);
+//                  every 128 solves; damped block Jacobi with FEMBRAIN_B200_MG_SMOOTHER=jacobi);
 //       coarsest   explicit dense inverse (<= 81 unknowns), rebuilt every step in shared memory;
 //       precision  the whole cycle runs in FP32 arithmetic on a reduced-precision copy of each level's Keff: FP16 values
 //                  (default; scaled by a power of two per level so that the largest diagonal entry sits near 2^13) or FP32
@@ -946,7 +946,7 @@ int setup_level_matrix(fb_context *c, FbMg *mg, MgLevel &L, int li) {
   return FB_OK;
 }
 
-// lambda_max(Binv A) of one level by power iteration (host reads the norms: only at setup and every 32 solves)
+// lambda_max(Binv A) of one level by power iteration (host reads the norms: only at setup and every 128 solves)
 int estimate_lmax(fb_context *c, FbMg *mg, MgLevel &L, int its) {
   cudaStream_t st = c->stream;
   fb_context *lc = L.ctx;
@@ -1341,7 +1341,7 @@ int fb_mg_prepare(fb_context *c) {
     c->launches += 1;
     lap(mg->nLevels - 1, "dense build + invert");
     const bool first = mg->L[0].lmax == 0.f;
-    if (first || mg->solves >= 32) {
+    if (first || mg->solves >= 128) {
       for (int li = 0; li + 1 < mg->nLevels; li++) FB_TRY(estimate_lmax(c, mg, mg->L[li], first ? (getenv("FEMBRAIN_B200_MG_LMAX_ITS") ? atoi(getenv("FEMBRAIN_B200_MG_LMAX_ITS")) : 30) : 3));
       mg->solves = 0;
     }

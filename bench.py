@@ -778,12 +778,26 @@ def run_ours(args):
     # ---- configs[1] and the CPU baseline, single GPU only ------------------------------------------------------------------
     if world == 1 and not args.no_1m and nx != 56:
         def block1m():
-            m, s1, _, _ = measure_mesh(env, 56, 10, 3, False, full=True)
+            m, s1, _, mesh1 = measure_mesh(env, 56, 10, 3, False, full=True)
+            var1 = None
+            if not args.no_variant:
+                try:   # the labelled variant on the same context, same 3 + 10 steps from rest
+                    s1.set_grid(56)
+                    s1.set_solver("mg")
+                    st1 = Stepper(env, s1, mesh1[3], False, mesh1[1])
+                    s1.reset_to_rest()
+                    st1.region(3, False)
+                    sec1, it1, _, _ = st1.region(10, False)
+                    var1 = {"solver": s1.solver()["name"], "value": 10 / sec1, "unit": UNIT, "ms_per_step": 1e3 * sec1 / 10, "cg_iterations_per_step": it1}
+                except Exception as e:  # noqa: BLE001
+                    var1 = {"error": f"{type(e).__name__}: {e}"[:300]}
             s1.close()
             keep = ("value", "ms_per_step", "e2e", "cg_iterations_per_step", "ms_per_cg_iteration", "assembly_mtets_per_s", "setup_seconds", "tets",
                     "roofline", "assembly")
             out = {k: m[k] for k in keep if k in m}
             out.update({"workload": config_dict(56, m["tets"], 1, False)["workload"], "unit": UNIT, "steps": 10, "warmup": 3})
+            if var1 is not None:
+                out["solver_variant"] = var1
             return out
         guarded("config2_1M", block1m)
     if world == 1 and not args.no_cpu_baseline:

@@ -67,7 +67,7 @@ typedef struct fb_params {
  * sum r^2/diag <= eps^2 sum b^2/diag, CGSolver.cpp:147-150), a faster-converging preconditioner (fb_mg.cu). */
 #define FB_SOLVER_JACOBI_PCG 0        /* CGSolver::SolveLinearSystemWithJacobiPreconditioner, CGSolver.cpp:129-190 */
 #define FB_SOLVER_BLOCK_JACOBI_PCG 1  /* 3x3 block-diagonal preconditioner; any mesh */
-#define FB_SOLVER_MG_PCG 2            /* geometric multigrid V(1,1) preconditioner; meshes on a tensor grid (fb_set_grid) */
+#define FB_SOLVER_MG_PCG 2            /* geometric multigrid V-cycle preconditioner (Chebyshev smoothing); meshes on a tensor grid (fb_set_grid) */
 
 typedef struct fb_context fb_context;
 
@@ -159,7 +159,7 @@ int fb_get_solver(const fb_context *ctx, int *variant, int *warm_start, int *lev
 const char *fb_solver_name(int variant);
 /* vertices and 3x3 blocks of every level of the variant's hierarchy, finest first (fb_get_solver gives the level count) */
 int fb_get_solver_levels(const fb_context *ctx, int capacity, int *num_vertices, long long *num_blocks);
-/* the cycle's smoother: sweeps before and after the coarse correction, 1 when they form a Chebyshev iteration on
+/* the cycle's smoother: sweeps on the finest level before and after the coarse correction (coarse levels: 4), 1 when they form a Chebyshev iteration on
  * [1.1 lambda_max / alpha, 1.1 lambda_max] (0: damped block Jacobi), and how many levels use the structured slot-major product */
 int fb_get_solver_smoother(const fb_context *ctx, int *sweeps, int *chebyshev, double *alpha, int *structured_levels);
 

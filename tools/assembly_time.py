@@ -1,3 +1,5 @@
+"""Developer tool: assembly time on the 1M- and 10M-tet bench cubes, isolated (10 back-to-back assemblies) and inside a step
+(step minus solve).  python tools/assembly_time.py   (GPU box)"""
 import sys; sys.path.insert(0, ".")
 import fembrain_b200 as fb
 from bench import workload

@@ -1,3 +1,5 @@
+"""Developer tool: configs[3] with the multigrid variant — 32 contexts of 196,608 tets on 32 streams — for 1 .. 32 host threads.
+python tools/batch_variant_probe.py   (GPU box)"""
 import sys, json; sys.path.insert(0, ".")
 import bench
 env = bench.Env()

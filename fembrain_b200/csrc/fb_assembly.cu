@@ -215,18 +215,21 @@ __global__ void k_fill_erec(int nT, const double *__restrict__ ed, double *__res
 // ---- per step ------------------------------------------------------------------------------------------------
 // one thread per tetrahedron: P = x0 + u, F = P MInverse, R from the polar decomposition, det < 0 -> -R
 // (corotationalLinearFEM.cpp:246-268)
-__global__ void __launch_bounds__(128) k_rotation(int nT, const int *__restrict__ tets, const double *__restrict__ x0,
-                                                  const double *__restrict__ u, const double *__restrict__ ed, double tol,
-                                                  double *__restrict__ erec) {
+__global__ void __launch_bounds__(128) k_rotation(int nT, const int *__restrict__ tets, const double *__restrict__ xu,
+                                                  const double *__restrict__ ed, double tol, double *__restrict__ erec) {
   const int el = blockIdx.x * blockDim.x + threadIdx.x;
   if (el >= nT) return;
   const int4 vt = reinterpret_cast<const int4 *>(tets)[el];
   const int vi[4] = {vt.x, vt.y, vt.z, vt.w};
   double P[4][3];
 #pragma unroll
-  for (int v = 0; v < 4; v++)
-#pragma unroll
-    for (int cc = 0; cc < 3; cc++) P[v][cc] = x0[3 * (size_t)vi[v] + cc] + u[3 * (size_t)vi[v] + cc];
+  for (int v = 0; v < 4; v++) {   // the packed (x0, u) record of the vertex: three 16-byte loads instead of six scattered 8-byte ones
+    const double2 *r2 = reinterpret_cast<const double2 *>(xu + 6 * (size_t)vi[v]);
+    const double2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2);   // x0.x x0.y | x0.z u.x | u.y u.z
+    P[v][0] = a.x + b.y;
+    P[v][1] = a.y + c.x;
+    P[v][2] = b.x + c.y;
+  }
   double *rec = erec + (size_t)el * EREC;
   double G[12];  // from the structure-of-arrays planes: coalesced (the records' 192-byte stride cost 85 vs 53 us at 1M tets)
 #pragma unroll
@@ -681,8 +684,8 @@ static bool ga_quad() {   // FEMBRAIN_B200_GA_QUAD=1: the four-lanes-per-inciden
 }
 
 int fb_launch_assembly_gather(fb_context *c, const double *u, double *Kraw, bool effective, bool rhs) {
-  k_rotation<<<grid_for((size_t)c->nT, 128), 128, 0, c->stream>>>(c->nT, c->tets, c->x0, u, c->edata, c->prm.polar_tolerance, c->ga_erec);
   k_pack_xu<<<grid_for((size_t)c->r, 256), 256, 0, c->stream>>>(c->nV, c->x0, u, c->ga_xu);
+  k_rotation<<<grid_for((size_t)c->nT, 128), 128, 0, c->stream>>>(c->nT, c->tets, c->ga_xu, c->edata, c->prm.polar_tolerance, c->ga_erec);
   GatherParams p;
   p.scale = c->prm.internal_force_scaling; p.h = c->prm.timestep;
   p.dampK = c->prm.damping_stiffness; p.dampM = c->prm.damping_mass;

@@ -30,3 +30,24 @@ def test_reference_arm_other_ranks_are_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--nx", "8"], env=env,
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_gpu_line_carries_the_whole_contract():
+    """The last B200 line of the round (profiles/): every key the measurement contract names, internally consistent."""
+    with open(os.path.join(ROOT, "profiles", "r02_bench_1gpu_10Mtets_v5.json")) as fh:
+        d = json.load(fh)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "solver_variant", "config5_50M", "config4_batch",
+                "config2_1M"):
+        assert key in d, key
+    assert d["metric"] == "fem_steps_per_s" and d["dtype"] == "f64" and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert "10110954 tets" in d["config"]["workload"] and "model" not in d["config"]
+    assert abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.5 < r["frac"] < 1.0
+    assert abs(r["traffic"] - r["algorithmic_bytes_per_launch"]) < 0.01 * r["traffic"]       # ncu DRAM bytes = the byte model
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 1000
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] < 0.01
+    v = d["solver_variant"]
+    assert v["value"] > 10 * d["value"] and max(v["cg_iterations_per_step"]) < 30 and v["final_displacement_rel_diff_vs_parity_path"] < 1e-5
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])

@@ -551,11 +551,9 @@ def batch_block(env, per_gpu, steps, warmup, nx=33):
 
 def batch_variant_block(env, per_gpu, steps, warmup, nx=33, threads=8):
     """configs[3] with the labelled multigrid variant: the same `per_gpu` independent meshes per GPU, each its own context with
-    FB_SOLVER_MG_PCG on its own stream (the batch context keeps the reference's solver), stepped by a pool of host threads so that
-    the latency-bound cycles of different meshes overlap on the GPU.  Wall clock between two device synchronisations (the work
+    FB_SOLVER_MG_PCG on its own stream (the batch context keeps the reference's solver), stepped by fb_step_many's pool of host
+    threads so that the latency-bound cycles of different meshes overlap on the GPU.  Wall clock between two device synchronisations (the work
     runs on `per_gpu` streams), max over ranks."""
-    from concurrent.futures import ThreadPoolExecutor
-
     torch, fb = env.torch, env.fb
     v, t, fixed, _ = workload(nx)
     nT, r = len(t), 3 * len(v)
@@ -575,19 +573,13 @@ def batch_variant_block(env, per_gpu, steps, warmup, nx=33, threads=8):
         sims.append(sim)
     t_setup = time.perf_counter() - t0
     threads = max(1, min(threads, per_gpu))
-    groups = [sims[i::threads] for i in range(threads)]
-
-    def run_group(g, n):
-        for _ in range(n):
-            for sim in g:
-                sim.do_timestep()
 
     def region(n):
         env.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(lambda g: run_group(g, n), groups))
+        for _ in range(n):
+            fb.step_many(sims, threads)   # fb_step_many: one step of every context from `threads` native host threads
         torch.cuda.synchronize()
         sec = time.perf_counter() - t0
         env.barrier()

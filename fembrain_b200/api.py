@@ -55,6 +55,19 @@ class FemBrainError(RuntimeError):
 _lib = None
 
 
+def step_many(sims, host_threads=8):
+    """fb_step_many: one DoTimestep of every Simulation in `sims` (independent contexts), issued from `host_threads` native threads.
+    Returns the list of per-context status codes; raises FemBrainError for the first failure."""
+    lib = load_library()
+    n = len(sims)
+    handles = (C.c_void_p * n)(*[s._h for s in sims])
+    status = (C.c_int * n)()
+    st = lib.fb_step_many(handles, n, int(host_threads), status)
+    if st != 0:
+        raise FemBrainError(st, "fb_step_many", lib.fb_last_error_string().decode(errors="replace"))
+    return list(status)
+
+
 def _preload_bundled_nccl():
     """The library's NEEDED libnccl.so.2 resolves to whichever copy the process maps first.  PyTorch ships its own (newer) NCCL
     and fails to import (`undefined symbol: ncclDevCommCreate`) when an older system copy is already mapped — which is what
@@ -114,6 +127,7 @@ def load_library():
         "fb_set_external_forces_dev": (ci, [vp, vp]), "fb_get_state_dev": (ci, [vp, vp, vp, vp]),
         "fb_displacements_dev": (vp, [vp]),
         "fb_set_warp": (ci, [vp, ci]), "fb_get_warp": (ci, [vp]),
+        "fb_step_many": (ci, [vp, ci, ci, vp]),
         "fb_set_timestep": (ci, [vp, cd]), "fb_set_damping": (ci, [vp, cd, cd]),
         "fb_set_internal_force_scaling": (ci, [vp, cd]), "fb_set_cg": (ci, [vp, cd, ci]),
         "fb_set_grid": (ci, [vp, ci, ci, ci]), "fb_set_solver": (ci, [vp, ci, ci]),

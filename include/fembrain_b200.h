@@ -169,6 +169,10 @@ int fb_get_solver_smoother(const fb_context *ctx, int *sweeps, int *chebyshev, d
  * rhs = -h*((h*K + D)*qvel + f_int - f_ext); solve the constrained system by Jacobi-PCG from x0 = 0;
  * qvel += dv; q += h*qvel; constrained DOFs zeroed.  Returns FB_OK or FB_ERR_SOLVER_NOT_CONVERGED. */
 int fb_step(fb_context *ctx);
+/* One fb_step of each of n DISTINCT, independent contexts (the batch of BASELINE configs[3] when every mesh needs its own
+ * context, e.g. with a solver variant), issued from `host_threads` host threads so that the contexts' kernels overlap on the
+ * device.  status (may be NULL) receives every context's fb_step result; the return value is the first one that is not FB_OK. */
+int fb_step_many(fb_context *const *ctxs, int n, int host_threads, int *status);
 
 /* Deformable::timestep (DEF/Deformable.cpp:318-420) around fb_step: zero forces, optional gravity
  * (-10000 on y when enabled and no contact, :331-338), haptic forces with ring spreading

@@ -110,3 +110,40 @@ def test_batch_against_oracle_and_errors(port_oracle):
     assert e.value.status == api.FB_ERR_SOLVER_NOT_CONVERGED
     its, _ = bad.batch_cg_iterations()
     assert its[0] == -5 and its[1] in (0, -5)  # the unloaded mesh iterates on rounding noise in fint; it cannot finish in 5 either
+
+
+def test_step_many_equals_sequential_steps():
+    """fb_step_many: independent contexts stepped from several host threads give the bits of sequential fb_step calls;
+    a duplicate or NULL entry is rejected; a failing context is reported without stopping the others."""
+    import ctypes as C
+
+    import fembrain_b200 as fb
+    from fembrain_b200 import api
+
+    v, t, fixed, load = cases.cube_case(6)
+    sims, refs = [], []
+    for k in range(5):
+        f = cases.point_load(3 * len(v), load)
+        f *= 1.0 + 0.25 * k
+        for group in (sims, refs):
+            s = fb.Simulation(v, t, fixed)
+            if k == 4:
+                s.set_grid(6)
+                s.set_solver("mg")
+            s.set_external_forces(f)
+            group.append(s)
+    for _ in range(3):
+        assert fb.step_many(sims, 3) == [0] * 5
+        for s in refs:
+            s.do_timestep()
+    for a, b in zip(sims, refs):
+        assert a.last_cg_iterations == b.last_cg_iterations
+        assert np.array_equal(a.get_state()[0], b.get_state()[0])
+    lib = api.load_library()
+    dup = (C.c_void_p * 2)(sims[0]._h, sims[0]._h)
+    assert lib.fb_step_many(dup, 2, 2, None) == api.FB_ERR_INVALID_ARGUMENT
+    # one context that cannot converge (max 1 iteration): its status comes back, the others still step
+    sims[1].set_cg(1e-6, 1)
+    with pytest.raises(fb.FemBrainError) as e:
+        fb.step_many(sims, 4)
+    assert e.value.status == api.FB_ERR_SOLVER_NOT_CONVERGED and "context 1" in str(e.value)

@@ -137,22 +137,38 @@ def partition_parity(part, ref, rank, world, r_global, traj_part=None, traj_step
         ok &= dit <= max(3, int(ref.last_cg_iterations) // 40)
         log(f"[parity] equal-state step: rhs bit-exact {rhs_equal}, iterations {part.last_cg_iterations} vs {ref.last_cg_iterations}")
     # ---- (c) tight solve from equal states ----------------------------------------------------------------------------
+    # FP64 PCG stagnates above eps = 1e-12 on some states (196,608 tets after six steps under the point load: 40000 iterations
+    # on one GPU and on two alike), so the tolerance is relaxed — for BOTH sides, 1e-12 -> 1e-10 -> 1e-9 — until the single-GPU
+    # solve converges; the 1e-8 bar on the solutions stays.
     eps0, max0 = part.params.cg_epsilon, part.params.cg_max_iterations
-    broadcast_state(part, ref, r_global)
-    part.set_cg(tight_eps, 40000)
-    conv_p = part.step_raw() == 0   # every rank takes the same decision (same scalars), so nobody is left in a collective
-    q_t, qv_t = global_state(part, r_global)
+    start = ref.get_state()[:2] if rank == 0 else None
+    tried = []
+    for eps_t in sorted({tight_eps, max(tight_eps, 1e-10), max(tight_eps, 1e-9)}):
+        if rank == 0:
+            ref.set_state(start[0], start[1], np.zeros(r_global))
+        broadcast_state(part, ref, r_global)
+        part.set_cg(eps_t, 40000)
+        conv_p = part.step_raw() == 0   # every rank takes the same decision (same scalars), so nobody is left in a collective
+        q_t, qv_t = global_state(part, r_global)
+        conv_r = False
+        if rank == 0:
+            ref.set_cg(eps_t, 40000)
+            conv_r = ref.step_raw() == 0
+        both = torch.tensor([1 if (conv_p and conv_r) else 0], device="cuda")
+        dist.broadcast(both, 0)
+        tried.append(eps_t)
+        if int(both[0]):
+            break
     if rank == 0:
-        ref.set_cg(tight_eps, 40000)
-        conv_r = ref.step_raw() == 0
         rq, rqv, _ = ref.get_state()
         eq, ev = _rel(q_t, rq), _rel(qv_t, rqv)
         ok &= conv_p and conv_r
-        res["tight_step"] = {"cg_eps": tight_eps, "converged_partitioned": conv_p, "converged_single_gpu": conv_r, "displacement_rel_err": eq, "velocity_rel_err": ev, "tolerance": 1e-8,
+        res["tight_step"] = {"cg_eps": tried[-1], "cg_eps_tried": tried, "converged_partitioned": conv_p, "converged_single_gpu": conv_r,
+                             "displacement_rel_err": eq, "velocity_rel_err": ev, "tolerance": 1e-8,
                              "iterations_partitioned": int(part.last_cg_iterations), "iterations_single_gpu": int(ref.last_cg_iterations)}
         ok &= eq <= 1e-8 and ev <= 1e-8
         ref.set_cg(eps0, max0)
-        log(f"[parity] tight step: |dq| {eq:.2e}, |dv| {ev:.2e}, iterations {part.last_cg_iterations} vs {ref.last_cg_iterations}")
+        log(f"[parity] tight step (eps {tried[-1]:g}): |dq| {eq:.2e}, |dv| {ev:.2e}, iterations {part.last_cg_iterations} vs {ref.last_cg_iterations}")
     part.set_cg(eps0, max0)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
